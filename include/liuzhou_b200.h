@@ -1,0 +1,201 @@
+/*
+ * liuzhou_b200.h -- C ABI of libliuzhou_b200.so: hand-written sm_100a kernels for the Liuzhou Chess
+ * (六洲棋) batched-MCTS self-play hot path.
+ *
+ * Drop-in boundary: every entry point below replaces one function of the reference's `v0_core` torch
+ * extension (pybind11 module, /root/reference/v0/src/bindings/module.cpp:874-1482) or one step of its
+ * v1 wave loop; the Python shim `liuzhou_b200.v0_core` presents them under the reference's names,
+ * argument order and dtypes.  See INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all data pointers are DEVICE pointers on the current
+ *     device unless the parameter is named h_*;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); launches are
+ *     asynchronous on it; no global mutable state, re-entrant from several host threads;
+ *   - return value: 0 = LZB_OK, negative = error (lzb_last_error() gives a thread-local message);
+ *     the Python shim raises RuntimeError like TORCH_CHECK does in the reference;
+ *   - reference tensor layout ("SoA of bytes", v1/python/mcts_gpu.py:40-55): board int8[B,36]
+ *     (+1 black, -1 white, 0 empty), marks_black / marks_white bool(uint8)[B,36], nine int64[B] scalars;
+ *   - native layout: one game state = 4 x uint64 (32 B) packed bitboards, see lzb_pack_states.
+ */
+#ifndef LIUZHOU_B200_H
+#define LIUZHOU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LZB_API __attribute__((visibility("default")))
+#else
+#define LZB_API
+#endif
+
+#define LZB_OK 0
+#define LZB_ERR_INVALID_ARGUMENT (-1)
+#define LZB_ERR_CUDA (-2)
+#define LZB_ERR_CAPACITY (-3)
+
+#define LZB_ACTION_DIM 220
+#define LZB_STATE_WORDS 4 /* uint64 words per packed state */
+
+/* Reference tensor layout of a state batch (12 tensors). move_count / moves_since_capture may be NULL
+ * where the reference op does not take them (encode_actions_fast, states_to_model_input). */
+typedef struct {
+    const int8_t *board;          /* [B,36] */
+    const uint8_t *marks_black;   /* [B,36] */
+    const uint8_t *marks_white;   /* [B,36] */
+    const int64_t *phase, *current_player;
+    const int64_t *pending_marks_required, *pending_marks_remaining;
+    const int64_t *pending_captures_required, *pending_captures_remaining;
+    const int64_t *forced_removals_done, *move_count, *moves_since_capture;
+} lzb_states_in;
+
+typedef struct {
+    int8_t *board;
+    uint8_t *marks_black, *marks_white;
+    int64_t *phase, *current_player;
+    int64_t *pending_marks_required, *pending_marks_remaining;
+    int64_t *pending_captures_required, *pending_captures_remaining;
+    int64_t *forced_removals_done, *move_count, *moves_since_capture;
+} lzb_states_out;
+
+LZB_API const char *lzb_last_error(void);
+/* ABI / build identification: returns e.g. "liuzhou_b200 0.1 sm_100a". */
+LZB_API const char *lzb_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+LZB_API uint64_t lzb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a2) legal mask -- replaces v0_core.encode_actions_fast
+ *      reference: v0/src/game/fast_legal_mask_cuda.cu:282-404 (kernel), :406-485 (launcher),
+ *                 binding module.cpp:1294-1310.
+ * mask u8[B,T], metadata i32[B,T,4] with T = sum of the four dims; fully written (no pre-fill needed).
+ * ---------------------------------------------------------------------------------------------- */
+LZB_API int lzb_encode_actions_fast(const lzb_states_in *st, int64_t B, int64_t placement_dim, int64_t movement_dim,
+                            int64_t selection_dim, int64_t auxiliary_dim, uint8_t *mask, int32_t *metadata,
+                            void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a4) apply move -- replaces v0_core.batch_apply_moves / batch_apply_moves_inplace
+ *      reference: v0/src/game/fast_apply_moves_cuda.cu:548-744 / :746-917, binding module.cpp:1311-1327.
+ * action_codes i32[N,4] = (kind, primary, secondary, extra) rows as emitted in `metadata`;
+ * parent_indices / slot_indices i64[N].  Illegal actions are silent no-ops exactly like the reference
+ * CUDA kernel (move_count still advances for every kind except placement).
+ * ---------------------------------------------------------------------------------------------- */
+LZB_API int lzb_batch_apply_moves(const lzb_states_in *parents, int64_t B, const int32_t *action_codes,
+                          const int64_t *parent_indices, int64_t N, const lzb_states_out *children, void *stream);
+LZB_API int lzb_batch_apply_moves_inplace(const lzb_states_out *states, int64_t B, const int32_t *action_codes,
+                                  const int64_t *slot_indices, int64_t N, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a6) states_to_model_input -- v0/src/net/encoding.cpp:26-79, binding module.cpp:1286-1293.
+ * out f32[B,11,6,6].
+ * ---------------------------------------------------------------------------------------------- */
+LZB_API int lzb_states_to_model_input(const lzb_states_in *st, int64_t B, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a7) project_policy_logits_fast -- v0/src/net/project_policy_logits_fast.cpp:16-164,
+ *      binding module.cpp:1328-1338.  fp32 heads [B,36]; legal_mask u8[B,220];
+ *      probs f32[B,220], masked_logits f32[B,220].
+ * ---------------------------------------------------------------------------------------------- */
+LZB_API int lzb_project_policy_logits_fast(const float *log_p1, const float *log_p2, const float *log_pmc,
+                                   const uint8_t *legal_mask, int64_t B, float *probs, float *masked_logits,
+                                   void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a9) root-PUCT -- replaces v0_core.root_puct_allocate_visits
+ *      reference: v0/src/mcts/root_puct_fused.cu:12-183, binding module.cpp:1349-1356.
+ * priors / leaf_values f32[R,M], valid_mask u8[R,M] -> visits f32[R,M], value_sum f32[R,M],
+ * root_values f32[R].  One warp per root, N/W/P in registers, warp-shuffle argmax (ties -> lowest index).
+ * ---------------------------------------------------------------------------------------------- */
+LZB_API int lzb_root_puct_allocate_visits(const float *priors, const float *leaf_values, const uint8_t *valid_mask,
+                                  int64_t R, int64_t M, int64_t num_simulations, float exploration_weight,
+                                  float *visits, float *value_sum, float *root_values, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a8) root_pack_sparse_actions -- module.cpp:258-363.  Two calls because the output shapes (R, M, N)
+ * are data dependent (the reference syncs on `.item()` at :310 as well):
+ *   1. lzb_root_pack_count: row_counts i64[B], terminal_mask u8[B], root_rank i64[B] (index among valid
+ *      roots), flat_offset i64[B] (exclusive prefix of counts over valid roots), summary i64[3] = {R, M, N};
+ *   2. host reads `summary`, allocates, then lzb_root_pack_fill writes the padded [R,M] matrices and the
+ *      flat [N] child list.
+ * ---------------------------------------------------------------------------------------------- */
+LZB_API int lzb_root_pack_count(const uint8_t *legal_mask, int64_t B, int64_t A, int64_t *row_counts, uint8_t *terminal_mask,
+                        int64_t *root_rank, int64_t *flat_offset, int64_t *summary, void *stream);
+LZB_API int lzb_root_pack_fill(const uint8_t *legal_mask, const float *probs, const int32_t *metadata, int64_t B, int64_t A,
+                       const int64_t *row_counts, const int64_t *root_rank, const int64_t *flat_offset, int64_t R,
+                       int64_t M, int64_t *valid_root_indices, int64_t *counts, uint8_t *valid_mask,
+                       int64_t *legal_index_mat, float *priors_mat, int32_t *action_code_mat, int64_t *flat_indices,
+                       int32_t *action_codes_all, int64_t *parent_indices_all, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a10) root_finalize_from_visits (sample_moves = false) -- module.cpp:441-535.
+ * Outputs cover all `batch_size` rows (rows that are not valid roots get zeros / -1 / false).
+ * ---------------------------------------------------------------------------------------------- */
+LZB_API int lzb_root_finalize_from_visits(const int64_t *legal_index_mat, const int32_t *action_code_mat,
+                                  const uint8_t *valid_mask, const float *visits, const float *value_sum,
+                                  const int64_t *valid_root_indices, int64_t R, int64_t M, int64_t batch_size,
+                                  int64_t total_action_dim, const float *root_temperatures, float *policy_dense,
+                                  int64_t *chosen_action_indices, int32_t *chosen_action_codes,
+                                  uint8_t *chosen_valid_mask, float *root_value, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a14) self_play_step_inplace -- module.cpp:632-871.  Mutates the 12 state tensors, plies, done.
+ * Output buffers must hold K entries; *num_finalized (device i64) receives F.  Order of the F entries:
+ * immediate-done slots in active order, then finished-by-move slots in active order (as the reference).
+ * scratch: K * 16 bytes.
+ * ---------------------------------------------------------------------------------------------- */
+LZB_API int lzb_self_play_step_inplace(const lzb_states_out *states, int64_t B, int64_t *plies, uint8_t *done,
+                               const int64_t *active_idx, const int32_t *chosen_action_codes,
+                               const uint8_t *terminal_mask, const uint8_t *chosen_valid_mask, int64_t K,
+                               int64_t max_game_plies, float soft_value_k, int64_t *finalize_slots,
+                               float *result_from_black, float *soft_value_from_black, int64_t *num_finalized,
+                               void *scratch, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a15) finalize_trajectory_inplace -- module.cpp:547-630.
+ * final_slots / final_counts hold F entries; summary i64[4] = {kept, black wins, white wins, draws}.
+ * ---------------------------------------------------------------------------------------------- */
+LZB_API int lzb_finalize_trajectory_inplace(float *value_targets, float *soft_value_targets, const int8_t *player_signs,
+                                    const int64_t *step_index_matrix, int64_t G, int64_t T, const int64_t *step_counts,
+                                    const int64_t *slots, const float *result_from_black,
+                                    const float *soft_value_from_black, int64_t F, int64_t *final_slots,
+                                    int64_t *final_counts, int64_t *summary, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Native packed layout (a1): state i = packed[4*i .. 4*i+3]
+ *   w0 = black(36 bits) | meta << 36, w1 = white, w2 = marks_black, w3 = marks_white
+ *   meta = phase:3 | white_to_move:1 | forced:2 | pm_req:2 | pm_rem:2 | pc_req:2 | pc_rem:2 |
+ *          move_count:8 | moves_since_capture:6
+ * Replaces v0::TensorStateBatch conversions (v0/src/game/tensor_state_batch.cpp) at the boundary.
+ * ---------------------------------------------------------------------------------------------- */
+LZB_API int lzb_pack_states(const lzb_states_in *st, int64_t B, uint64_t *packed, void *stream);
+LZB_API int lzb_unpack_states(const uint64_t *packed, int64_t B, const lzb_states_out *st, void *stream);
+LZB_API int lzb_init_states(uint64_t *packed, int64_t B, void *stream);
+
+/* Native legal mask: 220-bit masks as 4 x uint64 per state (bit a of word a/64) + legal counts i32[B].
+ * scalar_semantics != 0 -> v0::GenerateAllLegalMoves (empty on game over), else encode_actions_fast. */
+LZB_API int lzb_legal_masks_packed(const uint64_t *packed, int64_t B, int scalar_semantics, uint64_t *mask_words,
+                           int32_t *counts, void *stream);
+/* Native apply by 220-d action index: children[i] = apply(parents[parent_indices[i]], actions[i]);
+ * parent_indices may be NULL (identity). In place if children == parents and parent_indices == NULL. */
+LZB_API int lzb_apply_actions_packed(const uint64_t *parents, const int64_t *parent_indices, const int32_t *actions, int64_t N,
+                             uint64_t *children, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Config-2 workload: uniform-random playouts on the scalar-engine rules, counter-based RNG
+ * pick = mulhi32(mix64(mix64(seed ^ game*K) + ply) >> 32, n)   (same function in oracle/lz_oracle.c).
+ * lzb_playout_run advances every unfinished game by up to `max_steps` plies inside one launch (state
+ * lives in registers); result i8[B]: 2 = running, else result_from_black (+1, -1, 0).
+ * plies i32[B] counts plies played; hash u64[B] chains mix64(hash ^ state_hash) per ply (optional).
+ * ---------------------------------------------------------------------------------------------- */
+LZB_API int lzb_playout_run(uint64_t *packed, int32_t *plies, int8_t *result, uint64_t *hash, int64_t B, uint64_t seed,
+                    uint64_t game_offset, int32_t max_steps, int32_t max_game_plies, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIUZHOU_B200_H */

@@ -1,0 +1,391 @@
+// lz_dropin.cu -- sm_100a kernels behind the reference's v0_core tensor-op surface (reference byte layout).
+//
+// Design: one warp per state / action.  The 36 board bytes and 2x36 mark bytes are read by the 32 lanes
+// (cells lane and 32+lane) and turned into bitboards with warp ballots, so every lane holds the whole
+// state in registers; the rule logic (lz_rules.cuh) then runs warp-uniform without divergence, and the
+// wide outputs (3,520 B of metadata per state, 180 B per child) are written with fully coalesced
+// 16 B / 1 B per-lane stores.  These ops are HBM-bound byte work: 3,888 B/state for the legal mask,
+// 384 B/action for apply.
+#include "lz_common.cuh"
+
+using namespace lz;
+
+namespace lzb {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------
+// (a2) encode_actions_fast  -- fast_legal_mask_cuda.cu:282-404
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+encode_actions_kernel(lzb_states_in st, int64_t B, int pd, int md, int sd, int ad, uint8_t* __restrict__ mask,
+                      int32_t* __restrict__ metadata) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    const int total = pd + md + sd + ad;
+    for (int64_t b = warp; b < B; b += nwarps) {
+        State<int> s;
+        int8_t blo, bhi;
+        warp_load_state<int>(st, b, lane, s, blo, bhi);
+        Legal L;
+        legal_actions<int, false>(s, L, ad > 0);
+        uint8_t* m = mask + b * total;
+        int4* meta = reinterpret_cast<int4*>(metadata) + b * total;
+        const int sel_off = pd + md, rem_idx = pd + md + sd;
+        for (int a = lane; a < total; a += 32) {
+            // Region resolution in the reference's write order (placement, movement, selection, removal;
+            // later writers win if a caller passes overlapping dims).
+            int4 code = make_int4(-1, -1, -1, -1);
+            bool legal = false;
+            if (a < 36 && ((L.place >> a) & 1)) { legal = true; code = make_int4(kActPlace, a, -1, -1); }
+            const int mo = a - pd;
+            if (mo >= 0 && mo < 144 && mo < md) {
+                const int from = mo >> 2, d = mo & 3;
+                if ((L.mv[d] >> from) & 1) {
+                    legal = true;
+                    code = make_int4(kActMove, from, d, from + (d == 0 ? -6 : d == 1 ? 6 : d == 2 ? -1 : 1));
+                }
+            }
+            const int so = a - sel_off;
+            if (so >= 0 && so < 36 && so < sd && ((L.sel >> so) & 1)) {
+                legal = true; code = make_int4(L.sel_kind, so, -1, -1);
+            }
+            if (a == rem_idx && L.process) { legal = true; code = make_int4(kActProcess, -1, -1, -1); }
+            m[a] = legal ? 1 : 0;
+            meta[a] = code;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// (a4) batch_apply_moves / _inplace -- fast_apply_moves_cuda.cu:548-917
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_store_state(const lzb_states_out& out, int64_t i, int lane,
+                                                 const State<long long>& s, int8_t blo, int8_t bhi) {
+    int8_t* bp = out.board + i * 36;
+    uint8_t* mbp = out.marks_black + i * 36;
+    uint8_t* mwp = out.marks_white + i * 36;
+    auto cell_byte = [&](int cell, int8_t orig) -> int8_t {
+        const uint64_t b = 1ULL << cell;
+        return (s.black & b) ? (int8_t)1 : (s.white & b) ? (int8_t)-1 : (s.other & b) ? orig : (int8_t)0;
+    };
+    bp[lane] = cell_byte(lane, blo);
+    mbp[lane] = (uint8_t)((s.mb >> lane) & 1);
+    mwp[lane] = (uint8_t)((s.mw >> lane) & 1);
+    if (lane < 4) {
+        bp[32 + lane] = cell_byte(32 + lane, bhi);
+        mbp[32 + lane] = (uint8_t)((s.mb >> (32 + lane)) & 1);
+        mwp[32 + lane] = (uint8_t)((s.mw >> (32 + lane)) & 1);
+    }
+    // nine int64 scalars: lane l writes scalar l
+    long long v = s.phase;
+    int64_t* dst = out.phase;
+    switch (lane) {
+        case 1: v = s.player; dst = out.current_player; break;
+        case 2: v = s.pm_req; dst = out.pending_marks_required; break;
+        case 3: v = s.pm_rem; dst = out.pending_marks_remaining; break;
+        case 4: v = s.pc_req; dst = out.pending_captures_required; break;
+        case 5: v = s.pc_rem; dst = out.pending_captures_remaining; break;
+        case 6: v = s.forced; dst = out.forced_removals_done; break;
+        case 7: v = s.move_count; dst = out.move_count; break;
+        case 8: v = s.msc; dst = out.moves_since_capture; break;
+        default: break;
+    }
+    if (lane < 9) dst[i] = v;
+}
+
+template <bool kInplace>
+__global__ void __launch_bounds__(kThreads)
+apply_moves_kernel(lzb_states_in in, int64_t B, const int32_t* __restrict__ codes, const int64_t* __restrict__ parents,
+                   int64_t N, lzb_states_out out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t i = warp; i < N; i += nwarps) {
+        const int64_t p = parents[i];
+        if (p < 0 || p >= B) continue;                         // :584-587 / :770-773
+        State<long long> s;
+        int8_t blo, bhi;
+        warp_load_state<long long>(in, p, lane, s, blo, bhi);
+        const int4 code = reinterpret_cast<const int4*>(codes)[i];
+        apply_action(s, code.x, code.y, code.z);
+        warp_store_state(out, kInplace ? p : i, lane, s, blo, bhi);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// (a6) states_to_model_input -- encoding.cpp:26-79 : f32[B,11,6,6]
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+model_input_kernel(lzb_states_in st, int64_t B, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t b = warp; b < B; b += nwarps) {
+        const int8_t* bp = st.board + b * 36;
+        const bool hi = lane < 4;
+        const int8_t blo = bp[lane], bhi = hi ? bp[32 + lane] : (int8_t)0;
+        // `current` is cast to the board dtype before the compare (encoding.cpp:51)
+        const int64_t cur64 = st.current_player[b];
+        const int8_t cur = (int8_t)cur64, neg = (int8_t)(-cur);
+        const uint64_t self_p = ballot36(blo == cur, hi && bhi == cur);
+        const uint64_t opp_p = ballot36(blo == neg, hi && bhi == neg);
+        const uint8_t* mbp = st.marks_black + b * 36;
+        const uint8_t* mwp = st.marks_white + b * 36;
+        const uint64_t mb = ballot36(mbp[lane] != 0, hi && mbp[32 + lane] != 0);
+        const uint64_t mw = ballot36(mwp[lane] != 0, hi && mwp[32 + lane] != 0);
+        const bool is_black = cur64 == 1;
+        const uint64_t planes[4] = {self_p, opp_p, is_black ? mb : mw, is_black ? mw : mb};
+        const int64_t phase = st.phase[b];
+        float4* o = reinterpret_cast<float4*>(out + b * 396);
+        for (int k = lane; k < 99; k += 32) {                  // 99 float4 = 396 floats
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = 4 * k + j, plane = e / 36, cell = e - plane * 36;
+                v[j] = plane < 4 ? (float)((planes[plane] >> cell) & 1) : ((phase == plane - 3) ? 1.0f : 0.0f);
+            }
+            o[k] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// (a7) project_policy_logits_fast -- project_policy_logits_fast.cpp:16-164 (fp32, dims 36/144/36/4)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float combined_logit(const float* p1, const float* p2, const float* pmc, int a) {
+    if (a < 36) return p1[a];
+    if (a < 180) {
+        const int from = (a - 36) >> 2, d = (a - 36) & 3;
+        const int r = from / 6, c = from - r * 6;
+        const int rt = r + (d == 0 ? -1 : d == 1 ? 1 : 0), ct = c + (d == 2 ? -1 : d == 3 ? 1 : 0);
+        if (rt < 0 || rt >= 6 || ct < 0 || ct >= 6) return -INFINITY;
+        return p2[from] + p1[rt * 6 + ct];
+    }
+    if (a < 216) return pmc[a - 180];
+    return 0.0f;
+}
+
+__global__ void __launch_bounds__(kThreads)
+project_policy_kernel(const float* __restrict__ log_p1, const float* __restrict__ log_p2,
+                      const float* __restrict__ log_pmc, const uint8_t* __restrict__ legal, int64_t B,
+                      float* __restrict__ probs, float* __restrict__ masked_logits) {
+    __shared__ float heads[kWarpsPerBlock][3][36];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + w;
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t b = warp; b < B; b += nwarps) {
+        __syncwarp();
+        for (int i = lane; i < 36; i += 32) {
+            heads[w][0][i] = log_p1[b * 36 + i];
+            heads[w][1][i] = log_p2[b * 36 + i];
+            heads[w][2][i] = log_pmc[b * 36 + i];
+        }
+        __syncwarp();
+        float logit[7];
+        bool leg[7];
+        float mx = -INFINITY;
+        bool any_legal = false;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int a = lane + 32 * k;
+            leg[k] = a < 220 && legal[b * 220 + a] != 0;
+            logit[k] = leg[k] ? combined_logit(heads[w][0], heads[w][1], heads[w][2], a) : -INFINITY;
+            mx = fmaxf(mx, logit[k]);
+            any_legal |= leg[k];
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        any_legal = __any_sync(0xffffffffu, any_legal);
+        const bool has_finite = mx > -INFINITY && mx < INFINITY;   // row has a finite legal logit
+        float e[7], sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            e[k] = (has_finite && logit[k] > -INFINITY) ? expf(logit[k] - mx) : 0.0f;
+            sum += e[k];
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int a = lane + 32 * k;
+            if (a >= 220) continue;
+            probs[b * 220 + a] = has_finite ? e[k] / sum : 0.0f;
+            // rows with legal actions but no finite logit: legal entries of masked_logits become 0 (:150-159)
+            masked_logits[b * 220 + a] = (any_legal && !has_finite && leg[k]) ? 0.0f : logit[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// (a9) root_puct_allocate_visits -- root_puct_fused.cu:12-117
+// One warp per root; lane l owns actions l, l+32, ... (kSlots per lane) with N / W / c*P in registers.
+// Per simulation: recompute u for the owned slots (sqrt(total+1) changes every step), keep q cached
+// (it only changes for the chosen action), warp argmax with lowest-index tie-break via shuffles.
+// fp32 expression order is the reference's: u = ((c * p) * sqrt_total) / (1 + n), score = q + u.
+// ------------------------------------------------------------------------------------------------------
+template <int kSlots>
+__global__ void __launch_bounds__(kThreads)
+root_puct_kernel(const float* __restrict__ priors, const float* __restrict__ leaf, const uint8_t* __restrict__ valid,
+                 int64_t R, int M, int64_t sims, float c_puct, float* __restrict__ visits,
+                 float* __restrict__ value_sum, float* __restrict__ root_values) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t r = warp; r < R; r += nwarps) {
+        float cp[kSlots], lv[kSlots], n[kSlots], w[kSlots], q[kSlots];
+        bool ok[kSlots];
+#pragma unroll
+        for (int k = 0; k < kSlots; ++k) {
+            const int a = lane + 32 * k;
+            ok[k] = a < M && valid[r * M + a] != 0;
+            cp[k] = ok[k] ? __fmul_rn(c_puct, priors[r * M + a]) : 0.0f;
+            lv[k] = ok[k] ? leaf[r * M + a] : 0.0f;
+            n[k] = 0.0f; w[k] = 0.0f; q[k] = 0.0f;
+        }
+        float total = 0.0f;
+        for (int64_t sim = 0; sim < sims; ++sim) {
+            const float sqrt_total = __fsqrt_rn(__fadd_rn(total, 1.0f));
+            float best = -INFINITY;
+            int best_idx = 0x7fffffff;
+#pragma unroll
+            for (int k = 0; k < kSlots; ++k) {
+                const float u = __fdiv_rn(__fmul_rn(cp[k], sqrt_total), __fadd_rn(1.0f, n[k]));
+                const float score = __fadd_rn(q[k], u);
+                // ascending index within a lane, so strict > keeps the lowest index on ties; a NaN score is
+                // never selected and a -inf score only as the first candidate (root_puct_fused.cu:58)
+                if (ok[k] && (score > best || (score == best && best_idx == 0x7fffffff))) {
+                    best = score; best_idx = lane + 32 * k;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, best_idx, off);
+                const bool take = (oi != 0x7fffffff) &&
+                                  (best_idx == 0x7fffffff || ob > best || (ob == best && oi < best_idx));
+                if (take) { best = ob; best_idx = oi; }
+            }
+            if (best_idx == 0x7fffffff) continue;             // no valid action: the reference does nothing
+#pragma unroll
+            for (int k = 0; k < kSlots; ++k) {
+                if (best_idx == lane + 32 * k) {
+                    n[k] = __fadd_rn(n[k], 1.0f);
+                    w[k] = __fadd_rn(w[k], lv[k]);
+                    q[k] = __fdiv_rn(w[k], fmaxf(n[k], 1e-8f));
+                }
+            }
+            total = __fadd_rn(total, 1.0f);
+        }
+        float pv = 0.0f, pw = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kSlots; ++k) {
+            const int a = lane + 32 * k;
+            if (a < M) { visits[r * M + a] = n[k]; value_sum[r * M + a] = w[k]; }
+            pv += n[k]; pw += w[k];
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            pv += __shfl_xor_sync(0xffffffffu, pv, off);
+            pw += __shfl_xor_sync(0xffffffffu, pw, off);
+        }
+        if (lane == 0) root_values[r] = pw / fmaxf(pv, 1.0f);
+    }
+}
+
+}  // namespace
+}  // namespace lzb
+
+using namespace lzb;
+
+extern "C" int lzb_encode_actions_fast(const lzb_states_in* st, int64_t B, int64_t pd, int64_t md, int64_t sd,
+                                       int64_t ad, uint8_t* mask, int32_t* metadata, void* stream) {
+    LZB_REQUIRE(st && B >= 0 && pd >= 0 && md >= 0 && sd >= 0 && ad >= 0, "bad arguments");
+    LZB_REQUIRE(pd + md + sd + ad < (1 << 20), "action dims too large");
+    if (B == 0 || pd + md + sd + ad == 0) return LZB_OK;
+    LZB_REQUIRE(mask && metadata, "null output");
+    LZB_REQUIRE((reinterpret_cast<uintptr_t>(metadata) & 15) == 0, "metadata must be 16-byte aligned");
+    encode_actions_kernel<<<warp_grid(B), kThreads, 0, (cudaStream_t)stream>>>(*st, B, (int)pd, (int)md, (int)sd,
+                                                                                (int)ad, mask, metadata);
+    return check_launch("encode_actions_kernel");
+}
+
+static lzb_states_in as_in(const lzb_states_out* o) {
+    lzb_states_in in;
+    in.board = o->board; in.marks_black = o->marks_black; in.marks_white = o->marks_white;
+    in.phase = o->phase; in.current_player = o->current_player;
+    in.pending_marks_required = o->pending_marks_required; in.pending_marks_remaining = o->pending_marks_remaining;
+    in.pending_captures_required = o->pending_captures_required;
+    in.pending_captures_remaining = o->pending_captures_remaining;
+    in.forced_removals_done = o->forced_removals_done; in.move_count = o->move_count;
+    in.moves_since_capture = o->moves_since_capture;
+    return in;
+}
+
+extern "C" int lzb_batch_apply_moves(const lzb_states_in* parents, int64_t B, const int32_t* codes,
+                                     const int64_t* parent_indices, int64_t N, const lzb_states_out* children,
+                                     void* stream) {
+    LZB_REQUIRE(parents && children && B >= 0 && N >= 0, "bad arguments");
+    if (N == 0) return LZB_OK;
+    LZB_REQUIRE(codes && parent_indices, "null action arrays");
+    LZB_REQUIRE(parents->move_count && parents->moves_since_capture, "move_count / moves_since_capture required");
+    LZB_REQUIRE((reinterpret_cast<uintptr_t>(codes) & 15) == 0, "action_codes must be 16-byte aligned");
+    apply_moves_kernel<false><<<warp_grid(N), kThreads, 0, (cudaStream_t)stream>>>(*parents, B, codes, parent_indices,
+                                                                                  N, *children);
+    return check_launch("apply_moves_kernel");
+}
+
+extern "C" int lzb_batch_apply_moves_inplace(const lzb_states_out* states, int64_t B, const int32_t* codes,
+                                             const int64_t* slot_indices, int64_t N, void* stream) {
+    LZB_REQUIRE(states && B >= 0 && N >= 0, "bad arguments");
+    if (N == 0) return LZB_OK;
+    LZB_REQUIRE(codes && slot_indices, "null action arrays");
+    LZB_REQUIRE((reinterpret_cast<uintptr_t>(codes) & 15) == 0, "action_codes must be 16-byte aligned");
+    apply_moves_kernel<true><<<warp_grid(N), kThreads, 0, (cudaStream_t)stream>>>(as_in(states), B, codes,
+                                                                                 slot_indices, N, *states);
+    return check_launch("apply_moves_inplace_kernel");
+}
+
+extern "C" int lzb_states_to_model_input(const lzb_states_in* st, int64_t B, float* out, void* stream) {
+    LZB_REQUIRE(st && B >= 0, "bad arguments");
+    if (B == 0) return LZB_OK;
+    LZB_REQUIRE(out && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
+    model_input_kernel<<<warp_grid(B), kThreads, 0, (cudaStream_t)stream>>>(*st, B, out);
+    return check_launch("model_input_kernel");
+}
+
+extern "C" int lzb_project_policy_logits_fast(const float* log_p1, const float* log_p2, const float* log_pmc,
+                                              const uint8_t* legal_mask, int64_t B, float* probs,
+                                              float* masked_logits, void* stream) {
+    LZB_REQUIRE(B >= 0, "bad arguments");
+    if (B == 0) return LZB_OK;
+    LZB_REQUIRE(log_p1 && log_p2 && log_pmc && legal_mask && probs && masked_logits, "null pointer");
+    project_policy_kernel<<<warp_grid(B), kThreads, 0, (cudaStream_t)stream>>>(log_p1, log_p2, log_pmc, legal_mask, B,
+                                                                                probs, masked_logits);
+    return check_launch("project_policy_kernel");
+}
+
+extern "C" int lzb_root_puct_allocate_visits(const float* priors, const float* leaf_values, const uint8_t* valid_mask,
+                                             int64_t R, int64_t M, int64_t sims, float c_puct, float* visits,
+                                             float* value_sum, float* root_values, void* stream) {
+    LZB_REQUIRE(R >= 0 && M >= 0, "bad shape");
+    LZB_REQUIRE(sims > 0, "num_simulations must be positive");        // module.cpp:191
+    LZB_REQUIRE(M <= 1024, "at most 1024 actions per root");
+    if (R == 0) return LZB_OK;
+    if (M == 0) return LZB_OK;
+    LZB_REQUIRE(priors && leaf_values && valid_mask && visits && value_sum && root_values, "null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = warp_grid(R);
+#define LZB_PUCT(K)                                                                                             \
+    root_puct_kernel<K><<<grid, kThreads, 0, s>>>(priors, leaf_values, valid_mask, R, (int)M, sims, c_puct, visits, \
+                                                  value_sum, root_values)
+    if (M <= 32) LZB_PUCT(1);
+    else if (M <= 64) LZB_PUCT(2);
+    else if (M <= 96) LZB_PUCT(3);
+    else if (M <= 128) LZB_PUCT(4);
+    else if (M <= 256) LZB_PUCT(8);
+    else if (M <= 512) LZB_PUCT(16);
+    else LZB_PUCT(32);
+#undef LZB_PUCT
+    return check_launch("root_puct_kernel");
+}

@@ -272,6 +272,15 @@ def random_playout(seed: int, game: int, max_plies: int = 512, want_trace: bool 
     return out
 
 
+def random_playouts_range(seed: int, g0: int, g1: int, max_plies: int = 512):
+    """Bench helper: plays games [g0, g1) in C (releases the GIL) -> dict(plies, black, white, draws, hash_xor)."""
+    out = (ctypes.c_uint64 * 5)()
+    lib().or_random_playouts_range(ctypes.c_uint64(seed), ctypes.c_uint64(g0), ctypes.c_uint64(g1),
+                                   ctypes.c_int(max_plies), out)
+    return {"plies": int(out[0]), "black": int(out[1]), "white": int(out[2]), "draws": int(out[3]),
+            "hash_xor": int(out[4])}
+
+
 def state_hash(st: dict, i: int = 0) -> int:
     arr = states_to_structs({k: v[i:i + 1] for k, v in st.items()})
     return int(lib().or_state_hash(ctypes.byref(arr[0])))

@@ -762,3 +762,17 @@ int or_random_playout(uint64_t seed, uint64_t game, int max_plies, or_state *fin
     if (state_hash) *state_hash = hh;
     return ply;
 }
+
+/* Bench helper (cpu_baseline leg): play games [g0, g1) and accumulate plies + outcome counts.
+ * out[0] = plies, out[1] = black wins, out[2] = white wins, out[3] = draws, out[4] = xor of state hashes */
+void or_random_playouts_range(uint64_t seed, uint64_t g0, uint64_t g1, int max_plies, uint64_t *out) {
+    uint64_t plies = 0, bw = 0, ww = 0, dr = 0, hx = 0;
+    for (uint64_t g = g0; g < g1; ++g) {
+        int res = 0;
+        uint64_t h = 0;
+        plies += (uint64_t)or_random_playout(seed, g, max_plies, 0, &res, 0, &h);
+        if (res > 0) ++bw; else if (res < 0) ++ww; else ++dr;
+        hx ^= h;
+    }
+    out[0] = plies; out[1] = bw; out[2] = ww; out[3] = dr; out[4] = hx;
+}

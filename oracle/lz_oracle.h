@@ -124,6 +124,8 @@ uint32_t or_playout_pick(uint64_t seed, uint64_t game, uint32_t ply, uint32_t n)
 int or_random_playout(uint64_t seed, uint64_t game, int max_plies, or_state *final_state,
                       int *result_from_black, int16_t *trace, uint64_t *state_hash);
 
+void or_random_playouts_range(uint64_t seed, uint64_t g0, uint64_t g1, int max_plies, uint64_t *out);
+
 /* FNV-style hash of a state in canonical field order (used for checksum-of-checksums properties). */
 uint64_t or_state_hash(const or_state *s);
 
