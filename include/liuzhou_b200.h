@@ -195,6 +195,58 @@ LZB_API int lzb_apply_actions_packed(const uint64_t *parents, const int64_t *par
 LZB_API int lzb_playout_run(uint64_t *packed, int32_t *plies, int8_t *result, uint64_t *hash, int64_t B, uint64_t seed,
                     uint64_t game_offset, int32_t max_steps, int32_t max_game_plies, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (a12/a13) Device-resident full-tree MCTS -- replaces the reference's CPU `PortableTreeBatch`
+ *      (v1/cpp/portable_mcts.cpp:437-977; protocol prepare_roots -> complete_pending -> select_leaves ->
+ *      ... -> root_outputs, bound at :1069-1112) and the v0 `MCTSCore` virtual-loss batching
+ *      (v0/src/mcts/mcts_core.cpp:252-268,640-701).
+ * Node arena (structure of arrays, `capacity` nodes; nodes [0, num_trees) are the roots):
+ *   visit i32 | value_sum f64 | prior f64 | info u32 (action:8 | nchild:8 | flags) | first_child i32 |
+ *   parent i32 | state u64[4] | root_value f64[num_trees] | counters i32[4] = {top, overflow, expansions,
+ *   terminal hits}.
+ * One warp per tree; K leaves per tree per wave (K = 1 reproduces the reference exactly).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t *visit;
+    double *value_sum;
+    double *prior;
+    uint32_t *info;
+    int32_t *first_child;
+    int32_t *parent;
+    uint64_t *state;
+    double *root_value;
+    int32_t *counters;
+    int64_t capacity;
+    int64_t num_trees;
+} lzb_tree;
+
+/* Reset the arena to `num_trees` unexpanded roots (PortableTreeBatch ctor, :443-459). active u8[T] or NULL. */
+LZB_API int lzb_tree_init_roots(const lzb_tree *tree, const uint64_t *root_states, const uint8_t *active, void *stream);
+/* prepare_roots / select_leaves (:483-552): per slot (tree*K + k): leaf_node i32 (-1 if none), leaf_status i32
+ * (0 = evaluate, 1 = terminal/inactive, already backed up, 2 = duplicate of a pending leaf), leaf_states u64[.,4]. */
+LZB_API int lzb_tree_select(const lzb_tree *tree, int32_t K, double exploration_weight, double virtual_loss,
+                            int32_t *leaf_node, int32_t *leaf_status, uint64_t *leaf_states, void *stream);
+/* complete_pending (:554-590): expand every status-0 leaf with dense priors f32[T*K,220] / values f32[T*K],
+ * then back up (do_backup = 0 for roots, :575). */
+LZB_API int lzb_tree_expand_backup(const lzb_tree *tree, int32_t K, const int32_t *leaf_node, const int32_t *leaf_status,
+                                   const float *priors, const float *values, int32_t do_backup, double virtual_loss,
+                                   void *stream);
+/* root_outputs + root_priors (:592-624,:664-737); any output pointer may be NULL. */
+LZB_API int lzb_tree_root_outputs(const lzb_tree *tree, int32_t *visit_counts, float *root_action_values,
+                                  float *root_values, uint8_t *legal_masks, uint8_t *terminal, float *root_priors,
+                                  void *stream);
+/* set_root_priors (:626-662): renormalises priors f32[T,220] over each root's children. */
+LZB_API int lzb_tree_set_root_priors(const lzb_tree *tree, const float *priors, void *stream);
+
+/* Model-input planes from packed states (a6 on the native layout): layout 0 = f32 [n,11,6,6];
+ * layout 1 = bf16 channels-last ([n,6,6,11] physical) ready for the bf16 network. */
+LZB_API int lzb_encode_inputs_packed(const uint64_t *states, int64_t n, int32_t layout, void *out, void *stream);
+/* Fused a7 + value decode on packed states: fp32 heads [n,36] x3 + value logits [n,bins] ->
+ * priors f32[n,220] (softmax over the scalar-engine legal set) and values f32[n]. */
+LZB_API int lzb_heads_to_priors(const uint64_t *states, int64_t n, const float *log_p1, const float *log_p2,
+                                const float *log_pmc, const float *value_logits, int32_t bins, float *priors,
+                                float *values, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

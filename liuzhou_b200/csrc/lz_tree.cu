@@ -1,0 +1,512 @@
+// lz_tree.cu -- device-resident full-tree MCTS: selection (PUCT descent, virtual loss), expansion (legal-move
+// generation + atomic phase transitions on bitboards + node allocation from a bump arena) and player-aware
+// backup, one warp per game tree.
+//
+// Semantics = the reference's portable tree search (/root/reference/v1/cpp/portable_mcts.cpp:483-939):
+//   select : while expanded & has children & !terminal: argmax_a q + c*P*sqrt(max(1,N_parent))/(1+N_child),
+//            q = 0 if N_child == 0 else mean(child) negated iff child.player != node.player; ties -> lowest action
+//   expand : children for all legal actions (scalar-engine rules) in ascending action index,
+//            prior = p[a] / sum_legal p (uniform if the sum is <= 0), child.terminal = IsGameOver(child)
+//   backup : visit += 1, value_sum += v up the path, v negated when parent.player != node.player
+// Arithmetic is fp64 with the reference's operation order (fp64 priors / value sums, int32 visits), so that
+// visit counts are bit-identical for identical network outputs.
+//
+// HBM layout (structure of arrays over a node arena; the children of a node are contiguous, so a warp reads
+// N / W / P / info of all siblings with coalesced loads):
+//   visit i32[cap] | value_sum f64[cap] | prior f64[cap] | info u32[cap] | first_child i32[cap] |
+//   parent i32[cap] | state u64[cap][4]
+// Nodes 0..T-1 are the roots; the rest is handed out by an atomic bump pointer (one atomicAdd per expansion).
+// A tree is only ever touched by its own warp, so N / W updates need no atomics and results are
+// deterministic regardless of scheduling.
+#include "lz_common.cuh"
+
+using namespace lz;
+
+namespace lzb {
+namespace {
+
+constexpr uint32_t kInfoActionMask = 0xFFu;
+constexpr uint32_t kInfoTerminal = 1u << 16;
+constexpr uint32_t kInfoExpanded = 1u << 17;
+constexpr uint32_t kInfoNoLegal = 1u << 18;
+constexpr uint32_t kInfoWhite = 1u << 19;
+constexpr uint32_t kInfoPending = 1u << 20;
+constexpr uint32_t kInfoInactive = 1u << 21;
+__device__ __forceinline__ int info_nchild(uint32_t inf) { return (int)((inf >> 8) & 0xFFu); }
+
+__device__ __forceinline__ Packed load_packed(const uint64_t* p, int64_t i) {
+    const ulonglong2* v = reinterpret_cast<const ulonglong2*>(p + 4 * i);
+    const ulonglong2 a = v[0], b = v[1];
+    Packed r; r.w[0] = a.x; r.w[1] = a.y; r.w[2] = b.x; r.w[3] = b.y;
+    return r;
+}
+__device__ __forceinline__ void store_packed(uint64_t* p, int64_t i, const Packed& s) {
+    ulonglong2* v = reinterpret_cast<ulonglong2*>(p + 4 * i);
+    v[0] = make_ulonglong2(s.w[0], s.w[1]);
+    v[1] = make_ulonglong2(s.w[2], s.w[3]);
+}
+
+// TerminalValue, portable_mcts.cpp:267-273
+__device__ __forceinline__ double terminal_value(const State<int>& s) {
+    const int w = winner(s);
+    return w == 0 ? 0.0 : (w == s.player ? 1.0 : -1.0);
+}
+
+__global__ void __launch_bounds__(kThreads)
+tree_init_kernel(lzb_tree A, const uint64_t* __restrict__ roots, const uint8_t* __restrict__ active) {
+    const int64_t T = A.num_trees;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
+        const Packed p = load_packed(roots, t);
+        State<int> s;
+        unpack(p, s);
+        store_packed(A.state, t, p);
+        A.visit[t] = 0; A.value_sum[t] = 0.0; A.prior[t] = 1.0; A.first_child[t] = -1; A.parent[t] = -1;
+        uint32_t inf = 0xFFu;
+        if (game_over(s)) inf |= kInfoTerminal;                       // Node::terminal = IsGameOver (:414)
+        if (s.player == -1) inf |= kInfoWhite;
+        if (active && !active[t]) inf |= kInfoInactive;
+        A.info[t] = inf;
+        A.root_value[t] = 0.0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        A.counters[0] = (int32_t)T; A.counters[1] = 0; A.counters[2] = 0; A.counters[3] = 0;
+    }
+}
+
+// Backup, portable_mcts.cpp:876-892 (one lane walks the parent chain)
+__device__ __forceinline__ void backup_path(const lzb_tree& A, int node, double v) {
+    while (true) {
+        A.visit[node] += 1;
+        A.value_sum[node] = __dadd_rn(A.value_sum[node], v);
+        const int p = A.parent[node];
+        if (p < 0) break;
+        if ((A.info[p] ^ A.info[node]) & kInfoWhite) v = -v;
+        node = p;
+    }
+}
+// Virtual loss for K > 1 leaves per tree per wave: every node on the path gets +1 visit; its value sum moves
+// by `vl` AGAINST the player who chose it, so q seen from the parent always drops.  sign = +1 apply, -1 revert.
+__device__ __forceinline__ void virtual_loss_path(const lzb_tree& A, int node, double vl, int sign) {
+    while (true) {
+        const int p = A.parent[node];
+        A.visit[node] += sign;
+        if (p >= 0) {
+            const bool same = !((A.info[p] ^ A.info[node]) & kInfoWhite);
+            A.value_sum[node] = __dadd_rn(A.value_sum[node], (same ? -vl : vl) * (double)sign);
+        }
+        if (p < 0) break;
+        node = p;
+    }
+}
+
+// status codes written per leaf slot
+constexpr int kLeafEval = 0;       // needs a network evaluation, then expand (+ backup)
+constexpr int kLeafDone = 1;       // terminal / inactive: nothing to evaluate (backup already done)
+constexpr int kLeafDuplicate = 2;  // K > 1 only: same leaf already pending in this wave (simulation dropped)
+
+__global__ void __launch_bounds__(kThreads)
+tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restrict__ leaf_node,
+                   int32_t* __restrict__ leaf_status, uint64_t* __restrict__ leaf_states) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t t = warp; t < A.num_trees; t += nwarps) {
+        for (int k = 0; k < K; ++k) {
+            const int64_t slot = t * K + k;
+            int node = (int)t;
+            uint32_t inf = A.info[node];
+            if (inf & (kInfoTerminal | kInfoInactive)) {            // SelectLeaves :519-521
+                if (lane == 0) { leaf_node[slot] = -1; leaf_status[slot] = kLeafDone; }
+                continue;
+            }
+            // SelectPath :862-874
+            while ((inf & kInfoExpanded) && info_nchild(inf) > 0 && !(inf & kInfoTerminal)) {
+                const int fc = A.first_child[node], n = info_nchild(inf);
+                const int nv = A.visit[node];
+                const double sqrt_total = sqrt((double)(nv > 1 ? nv : 1));
+                const uint32_t node_white = inf & kInfoWhite;
+                double best = -INFINITY;
+                int best_i = 0x7fffffff;
+                for (int i = lane; i < n; i += 32) {                 // SelectChild :832-860
+                    const int c = fc + i;
+                    const int vc = A.visit[c];
+                    double q = 0.0;
+                    if (vc > 0) {
+                        q = __ddiv_rn(A.value_sum[c], (double)vc);
+                        if ((A.info[c] & kInfoWhite) != node_white) q = -q;
+                    }
+                    const double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, A.prior[c]), sqrt_total), (double)(1 + vc));
+                    const double score = __dadd_rn(q, u);
+                    if (score > best || (score == best && i < best_i)) { best = score; best_i = i; }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+                    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+                }
+                if (best_i == 0x7fffffff) break;                     // child == nullptr
+                node = fc + best_i;
+                inf = A.info[node];
+            }
+            int status;
+            if (inf & kInfoTerminal) {                               // :527-532
+                if (lane == 0) {
+                    State<int> s;
+                    unpack(load_packed(A.state, node), s);
+                    backup_path(A, node, (inf & kInfoNoLegal) ? -1.0 : terminal_value(s));
+                    atomicAdd(&A.counters[3], 1);
+                }
+                status = kLeafDone;
+            } else if ((inf & kInfoExpanded) && info_nchild(inf) == 0) {   // :533-538
+                if (lane == 0) {
+                    A.info[node] = inf | kInfoTerminal | kInfoNoLegal;
+                    backup_path(A, node, -1.0);
+                }
+                status = kLeafDone;
+            } else if (inf & kInfoPending) {
+                status = kLeafDuplicate;
+            } else {
+                status = kLeafEval;
+                if (lane == 0) {
+                    A.info[node] = inf | kInfoPending;
+                    store_packed(leaf_states, slot, load_packed(A.state, node));
+                    if (K > 1 && vl > 0.0) virtual_loss_path(A, node, vl, +1);
+                }
+            }
+            if (lane == 0) { leaf_node[slot] = status == kLeafEval ? node : -1; leaf_status[slot] = status; }
+            __syncwarp();
+        }
+    }
+}
+
+// Expand (portable_mcts.cpp:894-939) + Backup for every evaluated leaf slot of a tree, sequentially in slot
+// order (deterministic).  priors f32[slots,220] dense over the 220-d action space, values f32[slots].
+__global__ void __launch_bounds__(kThreads)
+tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, const int32_t* __restrict__ leaf_status,
+                   const float* __restrict__ priors, const float* __restrict__ values, int do_backup, double vl) {
+    __shared__ float s_pri[kWarpsPerBlock][kActionDim];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + w;
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t t = warp; t < A.num_trees; t += nwarps) {
+        for (int k = 0; k < K; ++k) {
+            const int64_t slot = t * K + k;
+            if (leaf_status[slot] != kLeafEval) continue;
+            const int node = leaf_node[slot];
+            State<int> s;
+            unpack(load_packed(A.state, node), s);
+            Legal L;
+            legal_actions<int, true>(s, L, true);
+            const int n = legal_count(L);
+            double value = (double)values[slot];
+            const uint32_t inf = A.info[node] & ~kInfoPending;
+            if (lane == 0 && K > 1 && vl > 0.0) virtual_loss_path(A, node, vl, -1);
+            __syncwarp();
+            if (n == 0) {                                             // :900-907
+                const bool over = game_over(s);
+                value = over ? terminal_value(s) : -1.0;
+                if (lane == 0) {
+                    A.info[node] = inf | kInfoExpanded | kInfoTerminal | (over ? 0u : kInfoNoLegal);
+                    if (node < A.num_trees) A.root_value[node] = value;
+                }
+            } else {
+                __syncwarp();
+                for (int a = lane; a < kActionDim; a += 32) s_pri[w][a] = priors[slot * kActionDim + a];
+                __syncwarp();
+                // prior_sum accumulated sequentially in ascending action order, in fp64 (:909-918)
+                double prior_sum = 0.0;
+                int fc = 0;
+                if (lane == 0) {
+                    for (int i = 0; i < n; ++i) prior_sum = __dadd_rn(prior_sum, (double)s_pri[w][legal_kth(L, i)]);
+                    fc = atomicAdd(&A.counters[0], n);
+                    if ((int64_t)fc + n > A.capacity) { A.counters[1] = 1; fc = -1; }
+                    else atomicAdd(&A.counters[2], 1);
+                }
+                prior_sum = __shfl_sync(0xffffffffu, prior_sum, 0);
+                fc = __shfl_sync(0xffffffffu, fc, 0);
+                if (fc >= 0) {
+                    const bool uniform = !(prior_sum > 0.0) || isinf(prior_sum);      // :919
+                    for (int a = lane; a < 224; a += 32) {
+                        if (a < kActionDim && legal_test(L, a)) {
+                            const int c = fc + legal_rank(L, a);
+                            State<int> cs = s;
+                            apply_index(cs, a);
+                            store_packed(A.state, c, pack(cs));
+                            A.visit[c] = 0; A.value_sum[c] = 0.0;
+                            A.prior[c] = uniform ? __ddiv_rn(1.0, (double)n) : __ddiv_rn((double)s_pri[w][a], prior_sum);
+                            A.first_child[c] = -1; A.parent[c] = node;
+                            uint32_t ci = (uint32_t)a;
+                            if (game_over(cs)) ci |= kInfoTerminal;
+                            if (cs.player == -1) ci |= kInfoWhite;
+                            A.info[c] = ci;
+                        }
+                    }
+                    if (lane == 0) {
+                        A.first_child[node] = fc;
+                        A.info[node] = (inf & ~(0xFFu << 8)) | ((uint32_t)n << 8) | kInfoExpanded;
+                        if (node < A.num_trees) A.root_value[node] = value;      // Node::initial_value
+                    }
+                } else if (lane == 0) {
+                    A.info[node] = inf;      // arena exhausted: leave the leaf unexpanded, flag is reported to the host
+                }
+            }
+            __syncwarp();
+            if (do_backup && lane == 0) backup_path(A, node, value);
+            __syncwarp();
+        }
+    }
+}
+
+// RootOutputs (portable_mcts.cpp:664-737) + RootPriors (:592-624)
+__global__ void __launch_bounds__(kThreads)
+tree_root_outputs_kernel(lzb_tree A, int32_t* __restrict__ visits, float* __restrict__ qvalues,
+                         float* __restrict__ root_values, uint8_t* __restrict__ legal, uint8_t* __restrict__ terminal,
+                         float* __restrict__ priors) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t t = warp; t < A.num_trees; t += nwarps) {
+        const uint32_t inf = A.info[t];
+        const int n = (inf & kInfoExpanded) ? info_nchild(inf) : 0;
+        const int fc = A.first_child[t];
+        for (int a = lane; a < kActionDim; a += 32) {
+            const int64_t o = t * kActionDim + a;
+            if (visits) visits[o] = 0;
+            if (qvalues) qvalues[o] = 0.0f;
+            if (legal) legal[o] = 0;
+            if (priors) priors[o] = 0.0f;
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            const int c = fc + i;
+            const uint32_t ci = A.info[c];
+            const int64_t o = t * kActionDim + (int)(ci & kInfoActionMask);
+            const int vc = A.visit[c];
+            if (visits) visits[o] = vc;
+            if (legal) legal[o] = 1;
+            if (priors) priors[o] = (float)A.prior[c];
+            if (qvalues && vc > 0) {
+                double q = __ddiv_rn(A.value_sum[c], (double)vc);
+                if ((ci ^ inf) & kInfoWhite) q = -q;
+                qvalues[o] = (float)q;
+            }
+        }
+        if (lane == 0) {
+            if (terminal) terminal[t] = ((inf & kInfoTerminal) || n == 0) ? 1 : 0;
+            if (root_values) {
+                const int nv = A.visit[t];
+                double v;
+                if (nv > 0) v = __ddiv_rn(A.value_sum[t], (double)nv);
+                else if (inf & kInfoNoLegal) v = -1.0;
+                else if (inf & kInfoTerminal) {
+                    State<int> s;
+                    unpack(load_packed(A.state, t), s);
+                    v = (inf & kInfoExpanded) ? A.root_value[t] : terminal_value(s);
+                } else v = A.root_value[t];
+                root_values[t] = (float)v;
+            }
+        }
+    }
+}
+
+// SetRootPriors (portable_mcts.cpp:626-662): prior_c = p[action_c] / sum_children p (fp64, child order)
+__global__ void __launch_bounds__(kThreads)
+tree_set_root_priors_kernel(lzb_tree A, const float* __restrict__ priors) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t t = warp; t < A.num_trees; t += nwarps) {
+        const uint32_t inf = A.info[t];
+        const int n = (inf & kInfoExpanded) ? info_nchild(inf) : 0;
+        if ((inf & (kInfoTerminal | kInfoInactive)) || n == 0) continue;
+        const int fc = A.first_child[t];
+        double sum = 0.0;
+        if (lane == 0)
+            for (int i = 0; i < n; ++i)
+                sum = __dadd_rn(sum, (double)priors[t * kActionDim + (int)(A.info[fc + i] & kInfoActionMask)]);
+        sum = __shfl_sync(0xffffffffu, sum, 0);
+        if (!(sum > 0.0) || isinf(sum)) continue;                     // the reference throws; we keep the old priors
+        for (int i = lane; i < n; i += 32)
+            A.prior[fc + i] = __ddiv_rn((double)priors[t * kActionDim + (int)(A.info[fc + i] & kInfoActionMask)], sum);
+    }
+}
+
+// Model input planes straight from packed states (EncodeModelInput :241-265 == encoding.cpp:26-79).
+// layout 0: f32 [n,11,6,6] (NCHW);  layout 1: bf16 channels-last, i.e. physical [n,6,6,11].
+template <int kLayout>
+__global__ void __launch_bounds__(kThreads)
+encode_inputs_kernel(const uint64_t* __restrict__ states, int64_t n, void* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t i = warp; i < n; i += nwarps) {
+        State<int> s;
+        unpack(load_packed(states, i), s);
+        const bool black = s.player == 1;
+        const uint64_t p0 = black ? s.black : s.white, p1 = black ? s.white : s.black;
+        const uint64_t p2 = black ? s.mb : s.mw, p3 = black ? s.mw : s.mb;
+        const int phase_plane = 3 + s.phase;
+        for (int e = lane; e < 396; e += 32) {
+            int plane, cell;
+            if (kLayout == 0) { plane = e / 36; cell = e - plane * 36; }
+            else { cell = e / 11; plane = e - cell * 11; }
+            const uint64_t bits = plane == 0 ? p0 : plane == 1 ? p1 : plane == 2 ? p2 : p3;
+            const bool on = plane < 4 ? ((bits >> cell) & 1) : (plane == phase_plane);
+            if (kLayout == 0) reinterpret_cast<float*>(out)[i * 396 + e] = on ? 1.0f : 0.0f;
+            else reinterpret_cast<uint16_t*>(out)[i * 396 + e] = on ? (uint16_t)0x3F80 : (uint16_t)0;   // bf16 1.0
+        }
+    }
+}
+
+// Policy heads -> dense priors over the legal actions of each leaf (masked softmax, fp32) and bucketed value
+// head -> scalar (expectation over linspace(-1, 1, bins)): fuses project_policy_logits_fast.cpp:16-164 with
+// neural_network.py:201-210 and takes the legal set from the packed state (scalar-engine semantics).
+__global__ void __launch_bounds__(kThreads)
+heads_to_priors_kernel(const uint64_t* __restrict__ states, int64_t n, const float* __restrict__ log_p1,
+                       const float* __restrict__ log_p2, const float* __restrict__ log_pmc,
+                       const float* __restrict__ value_logits, int bins, float* __restrict__ priors,
+                       float* __restrict__ values) {
+    __shared__ float heads[kWarpsPerBlock][3][36];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + w;
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t i = warp; i < n; i += nwarps) {
+        State<int> s;
+        unpack(load_packed(states, i), s);
+        Legal L;
+        legal_actions<int, true>(s, L, true);
+        __syncwarp();
+        for (int c = lane; c < 36; c += 32) {
+            heads[w][0][c] = log_p1[i * 36 + c]; heads[w][1][c] = log_p2[i * 36 + c]; heads[w][2][c] = log_pmc[i * 36 + c];
+        }
+        __syncwarp();
+        float logit[7], mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int a = lane + 32 * k;
+            float v = -INFINITY;
+            if (a < kActionDim && legal_test(L, a)) {
+                if (a < 36) v = heads[w][0][a];
+                else if (a < 180) {
+                    const int from = (a - 36) >> 2, d = (a - 36) & 3;
+                    v = heads[w][1][from] + heads[w][0][from + (d == 0 ? -6 : d == 1 ? 6 : d == 2 ? -1 : 1)];
+                } else if (a < 216) v = heads[w][2][a - 180];
+                else v = 0.0f;
+            }
+            logit[k] = v;
+            mx = fmaxf(mx, v);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        const bool ok = mx > -INFINITY && mx < INFINITY;
+        float e[7], sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { e[k] = (ok && logit[k] > -INFINITY) ? expf(logit[k] - mx) : 0.0f; sum += e[k]; }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int a = lane + 32 * k;
+            if (a < kActionDim) priors[i * kActionDim + a] = ok ? e[k] / sum : 0.0f;
+        }
+        // value = sum softmax(logits) * linspace(-1, 1, bins)
+        float vmx = -INFINITY;
+        for (int b = lane; b < bins; b += 32) vmx = fmaxf(vmx, value_logits[i * bins + b]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) vmx = fmaxf(vmx, __shfl_xor_sync(0xffffffffu, vmx, off));
+        float se = 0.0f, sc = 0.0f;
+        const float step = bins > 1 ? 2.0f / (float)(bins - 1) : 0.0f;
+        for (int b = lane; b < bins; b += 32) {
+            const float ev = expf(value_logits[i * bins + b] - vmx);
+            se += ev; sc += ev * (-1.0f + step * (float)b);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, off);
+            sc += __shfl_xor_sync(0xffffffffu, sc, off);
+        }
+        if (lane == 0) values[i] = sc / se;
+    }
+}
+
+}  // namespace
+}  // namespace lzb
+
+using namespace lzb;
+
+static int check_tree(const lzb_tree* t) {
+    LZB_REQUIRE(t && t->visit && t->value_sum && t->prior && t->info && t->first_child && t->parent && t->state &&
+                t->counters && t->root_value, "tree arena has null arrays");
+    LZB_REQUIRE(t->num_trees > 0 && t->capacity >= t->num_trees && t->capacity < (1LL << 31), "bad tree sizes");
+    return LZB_OK;
+}
+
+extern "C" int lzb_tree_init_roots(const lzb_tree* tree, const uint64_t* root_states, const uint8_t* active, void* stream) {
+    int rc = check_tree(tree);
+    if (rc) return rc;
+    LZB_REQUIRE(root_states, "null root states");
+    tree_init_kernel<<<thread_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(*tree, root_states, active);
+    return check_launch("tree_init_kernel");
+}
+
+extern "C" int lzb_tree_select(const lzb_tree* tree, int32_t K, double c_puct, double virtual_loss, int32_t* leaf_node,
+                               int32_t* leaf_status, uint64_t* leaf_states, void* stream) {
+    int rc = check_tree(tree);
+    if (rc) return rc;
+    LZB_REQUIRE(K >= 1 && K <= 64, "leaves per tree per wave must be in [1, 64]");
+    LZB_REQUIRE(c_puct >= 0.0 && c_puct == c_puct, "exploration_weight must be finite and non-negative");
+    LZB_REQUIRE(leaf_node && leaf_status && leaf_states, "null output");
+    tree_select_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(
+        *tree, K, c_puct, virtual_loss, leaf_node, leaf_status, leaf_states);
+    return check_launch("tree_select_kernel");
+}
+
+extern "C" int lzb_tree_expand_backup(const lzb_tree* tree, int32_t K, const int32_t* leaf_node,
+                                      const int32_t* leaf_status, const float* priors, const float* values,
+                                      int32_t do_backup, double virtual_loss, void* stream) {
+    int rc = check_tree(tree);
+    if (rc) return rc;
+    LZB_REQUIRE(K >= 1 && K <= 64, "leaves per tree per wave must be in [1, 64]");
+    LZB_REQUIRE(leaf_node && leaf_status && priors && values, "null input");
+    tree_expand_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(
+        *tree, K, leaf_node, leaf_status, priors, values, do_backup, virtual_loss);
+    return check_launch("tree_expand_kernel");
+}
+
+extern "C" int lzb_tree_root_outputs(const lzb_tree* tree, int32_t* visits, float* qvalues, float* root_values,
+                                     uint8_t* legal, uint8_t* terminal, float* priors, void* stream) {
+    int rc = check_tree(tree);
+    if (rc) return rc;
+    tree_root_outputs_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(
+        *tree, visits, qvalues, root_values, legal, terminal, priors);
+    return check_launch("tree_root_outputs_kernel");
+}
+
+extern "C" int lzb_tree_set_root_priors(const lzb_tree* tree, const float* priors, void* stream) {
+    int rc = check_tree(tree);
+    if (rc) return rc;
+    LZB_REQUIRE(priors, "null priors");
+    tree_set_root_priors_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(*tree, priors);
+    return check_launch("tree_set_root_priors_kernel");
+}
+
+extern "C" int lzb_encode_inputs_packed(const uint64_t* states, int64_t n, int32_t layout, void* out, void* stream) {
+    LZB_REQUIRE(n >= 0 && (layout == 0 || layout == 1), "bad arguments");
+    if (n == 0) return LZB_OK;
+    LZB_REQUIRE(states && out, "null pointer");
+    if (layout == 0) encode_inputs_kernel<0><<<warp_grid(n), kThreads, 0, (cudaStream_t)stream>>>(states, n, out);
+    else encode_inputs_kernel<1><<<warp_grid(n), kThreads, 0, (cudaStream_t)stream>>>(states, n, out);
+    return check_launch("encode_inputs_kernel");
+}
+
+extern "C" int lzb_heads_to_priors(const uint64_t* states, int64_t n, const float* log_p1, const float* log_p2,
+                                   const float* log_pmc, const float* value_logits, int32_t bins, float* priors,
+                                   float* values, void* stream) {
+    LZB_REQUIRE(n >= 0 && bins >= 1, "bad arguments");
+    if (n == 0) return LZB_OK;
+    LZB_REQUIRE(states && log_p1 && log_p2 && log_pmc && value_logits && priors && values, "null pointer");
+    heads_to_priors_kernel<<<warp_grid(n), kThreads, 0, (cudaStream_t)stream>>>(states, n, log_p1, log_p2, log_pmc,
+                                                                               value_logits, bins, priors, values);
+    return check_launch("heads_to_priors_kernel");
+}

@@ -1,0 +1,227 @@
+"""Policy / value network of the reference (``ChessNet``, /root/reference/src/neural_network.py:213-259) and the
+bf16 inference wrapper the search engines use.
+
+The architecture (11 -> 128-channel stem, 10 pre-activation residual blocks, three-head policy with global
+pooling, 101-bucket value head) and every parameter name are the reference's, so its checkpoints
+(``{"model_state_dict": ...}``, v1/train.py:2556) load unchanged.  north_star keeps this one dense contraction
+in PyTorch (cuDNN / cuBLAS on the tensor cores); what is ours is everything around it: inputs are written by our
+kernels directly as bf16 channels-last planes, outputs are consumed by our fused head kernel, and the whole
+forward is replayed from a CUDA graph at fixed batch sizes.
+
+FLOPs per evaluated state (forward, 2 x MAC): stem 0.91 M + 20 convs x 10.62 M + heads ~1.29 M = 214.5 MFLOP.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+NUM_INPUT_CHANNELS = 11
+VALUE_BUCKET_BINS = 101
+BOARD_SIZE = 6
+FLOPS_PER_STATE = 214.5e6
+
+
+class GlobalPool(nn.Module):
+    """mean / max / std over the board -> (N, 3C)   (neural_network.py:68-81)."""
+
+    def __init__(self, eps: float = 1e-6):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        flat = x.flatten(2)
+        mean = flat.mean(dim=2)
+        mx = flat.max(dim=2)[0]
+        std = torch.sqrt(flat.var(dim=2, unbiased=False) + self.eps)
+        return torch.cat([mean, mx, std], dim=1)
+
+
+class PreActResBlock(nn.Module):
+    """x + conv2(relu(bn2(conv1(relu(bn1(x))))))   (neural_network.py:83-96)."""
+
+    def __init__(self, channels: int):
+        super().__init__()
+        self.bn1 = nn.BatchNorm2d(channels)
+        self.act1 = nn.ReLU(inplace=True)
+        self.conv1 = nn.Conv2d(channels, channels, kernel_size=3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(channels)
+        self.act2 = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(channels, channels, kernel_size=3, padding=1, bias=False)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        out = self.conv1(self.act1(self.bn1(x)))
+        out = self.conv2(self.act2(self.bn2(out)))
+        return x + out
+
+
+class PolicyHead(nn.Module):
+    """Three 36-way log-softmax heads (placement / move-from / mark-capture)   (neural_network.py:98-126)."""
+
+    def __init__(self, in_channels: int, policy_channels: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_channels, policy_channels, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(policy_channels)
+        self.act1 = nn.ReLU(inplace=True)
+        self.gpool = GlobalPool()
+        self.gpool_linear = nn.Linear(3 * policy_channels, policy_channels, bias=False)
+        self.bn2 = nn.BatchNorm2d(policy_channels)
+        self.act2 = nn.ReLU(inplace=True)
+        self.out_pos1 = nn.Conv2d(policy_channels, 1, kernel_size=1, bias=False)
+        self.out_pos2 = nn.Conv2d(policy_channels, 1, kernel_size=1, bias=False)
+        self.out_mark = nn.Conv2d(policy_channels, 1, kernel_size=1, bias=False)
+
+    def forward(self, x: torch.Tensor):
+        p = self.act1(self.bn1(self.conv1(x)))
+        g = self.gpool_linear(self.gpool(p)).unsqueeze(-1).unsqueeze(-1)
+        p = self.act2(self.bn2(p + g))
+        return (F.log_softmax(self.out_pos1(p).flatten(1), dim=1),
+                F.log_softmax(self.out_pos2(p).flatten(1), dim=1),
+                F.log_softmax(self.out_mark(p).flatten(1), dim=1))
+
+
+class ValueHead(nn.Module):
+    """Bucketed value head -> raw logits (N, K)   (neural_network.py:128-151)."""
+
+    def __init__(self, in_channels: int, value_channels: int, mlp_channels: int, num_value_bins: int = VALUE_BUCKET_BINS):
+        super().__init__()
+        if int(num_value_bins) < 2:
+            raise ValueError("num_value_bins must be >= 2")
+        self.conv1 = nn.Conv2d(in_channels, value_channels, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(value_channels)
+        self.act1 = nn.ReLU(inplace=True)
+        self.gpool = GlobalPool()
+        self.fc1 = nn.Linear(3 * value_channels, mlp_channels, bias=True)
+        self.act2 = nn.ReLU(inplace=True)
+        self.fc2 = nn.Linear(mlp_channels, int(num_value_bins), bias=True)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        v = self.act1(self.bn1(self.conv1(x)))
+        return self.fc2(self.act2(self.fc1(self.gpool(v))))
+
+
+def bucket_logits_to_scalar(logits: torch.Tensor, num_bins: int = VALUE_BUCKET_BINS) -> torch.Tensor:
+    """Probability-weighted expectation over linspace(-1, 1, bins)   (neural_network.py:201-210)."""
+    bins = int(logits.size(-1))
+    probs = torch.softmax(logits, dim=-1)
+    centers = torch.linspace(-1.0, 1.0, steps=bins, device=logits.device, dtype=probs.dtype)
+    return (probs * centers).sum(dim=-1)
+
+
+class ChessNet(nn.Module):
+    def __init__(self, board_size: int = BOARD_SIZE, num_input_channels: int = NUM_INPUT_CHANNELS,
+                 hidden_conv_channels: Optional[int] = None, trunk_channels: int = 128, num_blocks: int = 10,
+                 policy_channels: int = 64, value_channels: int = 64, value_mlp_channels: int = 128,
+                 value_bucket_bins: int = VALUE_BUCKET_BINS):
+        super().__init__()
+        self.board_size = board_size
+        self.num_input_channels = num_input_channels
+        if hidden_conv_channels is not None:
+            trunk_channels = hidden_conv_channels
+        self.stem_conv = nn.Conv2d(num_input_channels, trunk_channels, kernel_size=3, padding=1, bias=False)
+        self.stem_bn = nn.BatchNorm2d(trunk_channels)
+        self.stem_act = nn.ReLU(inplace=True)
+        self.blocks = nn.ModuleList([PreActResBlock(trunk_channels) for _ in range(num_blocks)])
+        self.trunk_bn = nn.BatchNorm2d(trunk_channels)
+        self.trunk_act = nn.ReLU(inplace=True)
+        self.policy_head = PolicyHead(trunk_channels, policy_channels)
+        self.value_head = ValueHead(trunk_channels, value_channels, value_mlp_channels,
+                                    num_value_bins=int(value_bucket_bins))
+
+    def forward(self, x: torch.Tensor):
+        x = self.stem_act(self.stem_bn(self.stem_conv(x)))
+        for block in self.blocks:
+            x = block(x)
+        x = self.trunk_act(self.trunk_bn(x))
+        log_p1, log_p2, log_pmc = self.policy_head(x)
+        return log_p1, log_p2, log_pmc, self.value_head(x)
+
+
+def flops_per_state(model: ChessNet) -> float:
+    """Forward FLOPs (2 x MAC) per evaluated state for an arbitrary ChessNet instance."""
+    total = 0.0
+    cells = model.board_size * model.board_size
+    for m in model.modules():
+        if isinstance(m, nn.Conv2d):
+            total += 2.0 * m.in_channels * m.out_channels * m.kernel_size[0] * m.kernel_size[1] * cells
+        elif isinstance(m, nn.Linear):
+            total += 2.0 * m.in_features * m.out_features
+    return total
+
+
+class InferenceNet:
+    """bf16 / channels-last / CUDA-graph inference wrapper around a ChessNet on one GPU.
+
+    ``forward(inputs)`` takes bf16 channels-last planes [n,11,6,6] (as written by ``lzb_encode_inputs_packed``)
+    and returns fp32 (log_p1, log_p2, log_pmc, value_logits).  For batch sizes registered with ``capture``
+    the forward is a graph replay on static buffers (returned tensors alias those buffers)."""
+
+    def __init__(self, model: ChessNet, device, dtype: torch.dtype = torch.bfloat16):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("InferenceNet needs a CUDA device")
+        self.device = dev
+        self.dtype = dtype
+        self.model = self._clone_for_inference(model, dev, dtype)
+        self.flops_per_state = flops_per_state(self.model)
+        self._graphs: Dict[int, Tuple[torch.cuda.CUDAGraph, torch.Tensor, Tuple[torch.Tensor, ...]]] = {}
+
+    @staticmethod
+    def _clone_for_inference(model: ChessNet, dev, dtype):
+        import copy
+
+        m = copy.deepcopy(model).to(device=dev, dtype=dtype)
+        m = m.to(memory_format=torch.channels_last)
+        m.eval()
+        for p in m.parameters():
+            p.requires_grad_(False)
+        return m
+
+    def load_state_dict(self, state_dict) -> None:
+        """In-place weight refresh (e.g. after an NCCL broadcast); captured graphs stay valid."""
+        own = self.model.state_dict()
+        with torch.no_grad():
+            for k, v in state_dict.items():
+                if k in own:
+                    own[k].copy_(v.to(device=self.device, dtype=own[k].dtype))
+
+    @torch.no_grad()
+    def _forward_eager(self, x: torch.Tensor):
+        lp1, lp2, lpm, vl = self.model(x)
+        return lp1.float(), lp2.float(), lpm.float(), vl.float()
+
+    def new_input(self, n: int) -> torch.Tensor:
+        return torch.zeros((n, 11, 6, 6), dtype=self.dtype, device=self.device, memory_format=torch.channels_last)
+
+    def capture(self, n: int, static_input: Optional[torch.Tensor] = None):
+        """Capture a CUDA graph of the forward at batch size n. Returns (static_input, static_outputs)."""
+        if n in self._graphs and (static_input is None or static_input is self._graphs[n][1]):
+            return self._graphs[n][1], self._graphs[n][2]
+        x = static_input if static_input is not None else self.new_input(n)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._forward_eager(x)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            outs = self._forward_eager(x)
+        self._graphs[n] = (g, x, outs)
+        return x, outs
+
+    @torch.no_grad()
+    def forward(self, inputs: torch.Tensor):
+        n = inputs.size(0)
+        entry = self._graphs.get(n)
+        if entry is None:
+            x = inputs.to(device=self.device, dtype=self.dtype).contiguous(memory_format=torch.channels_last)
+            return self._forward_eager(x)
+        g, x, outs = entry
+        if inputs.data_ptr() != x.data_ptr():
+            x.copy_(inputs)
+        g.replay()
+        return outs

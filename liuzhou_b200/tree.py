@@ -1,0 +1,210 @@
+"""Device-resident full-tree MCTS (host-side mirror of the reference's ``PortableTreeBatch`` protocol,
+/root/reference/v1/cpp/portable_mcts.cpp:437-977 and its Python driver v1/python/portable_cpp_mcts.py:243-390).
+
+All tree state lives in HBM (node arena, structure of arrays); selection / expansion / backup are the
+hand-written kernels in csrc/lz_tree.cu.  Shapes are static (``num_trees * leaves_per_wave`` leaf slots per
+wave, each with a status), so one simulation wave -- select -> network -> expand+backup -- can be captured
+in a CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from ._lib import check, i64, lib, ptr, require_cuda, stream_ptr
+
+ACTION_DIM = 220
+LEAF_EVAL, LEAF_DONE, LEAF_DUPLICATE = 0, 1, 2
+
+
+class _TreeStruct(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("visit", "value_sum", "prior", "info", "first_child", "parent", "state",
+                                                "root_value", "counters")] + [("capacity", ctypes.c_int64),
+                                                                             ("num_trees", ctypes.c_int64)]
+
+
+class DeviceTreeBatch:
+    """``num_trees`` independent search trees in one node arena on one GPU."""
+
+    def __init__(self, num_trees: int, device="cuda", *, exploration_weight: float = 1.0, leaves_per_wave: int = 1,
+                 virtual_loss: float = 1.0, node_capacity: Optional[int] = None,
+                 nodes_per_tree_hint: int = 200 * 40) -> None:
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("DeviceTreeBatch needs a CUDA device (no CPU path)")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if not (exploration_weight >= 0.0):
+            raise RuntimeError("exploration_weight must be finite and non-negative")
+        self.device = dev
+        self.num_trees = int(num_trees)
+        self.k = int(leaves_per_wave)
+        self.exploration_weight = float(exploration_weight)
+        self.virtual_loss = float(virtual_loss)
+        cap = int(node_capacity) if node_capacity is not None else self.num_trees * (1 + int(nodes_per_tree_hint))
+        cap = min(cap, 2**31 - 2)
+        self.capacity = cap
+        t, slots = self.num_trees, self.num_trees * self.k
+        with torch.cuda.device(dev):
+            self.visit = torch.empty((cap,), dtype=torch.int32, device=dev)
+            self.value_sum = torch.empty((cap,), dtype=torch.float64, device=dev)
+            self.prior = torch.empty((cap,), dtype=torch.float64, device=dev)
+            self.info = torch.empty((cap,), dtype=torch.int32, device=dev)
+            self.first_child = torch.empty((cap,), dtype=torch.int32, device=dev)
+            self.parent = torch.empty((cap,), dtype=torch.int32, device=dev)
+            self.state = torch.empty((cap, 4), dtype=torch.int64, device=dev)
+            self.root_value = torch.zeros((t,), dtype=torch.float64, device=dev)
+            self.counters = torch.zeros((4,), dtype=torch.int32, device=dev)
+            self.leaf_node = torch.full((slots,), -1, dtype=torch.int32, device=dev)
+            self.leaf_status = torch.full((slots,), LEAF_DONE, dtype=torch.int32, device=dev)
+            self.leaf_states = torch.zeros((slots, 4), dtype=torch.int64, device=dev)
+        self._struct = _TreeStruct()
+        for name in ("visit", "value_sum", "prior", "info", "first_child", "parent", "state", "root_value", "counters"):
+            setattr(self._struct, name, getattr(self, name).data_ptr())
+        self._struct.capacity = cap
+        self._struct.num_trees = t
+        self._pending_is_root = False
+
+    # -- protocol ------------------------------------------------------------------------------------
+    def reset(self, root_states: torch.Tensor, active: Optional[torch.Tensor] = None) -> None:
+        """New search from packed root states int64[T,4] (drops every node of the previous search)."""
+        require_cuda(root_states, "root_states")
+        if tuple(root_states.shape) != (self.num_trees, 4):
+            raise RuntimeError(f"root_states must be int64[{self.num_trees}, 4]")
+        rs = root_states.contiguous()
+        act = None if active is None else active.to(device=self.device, dtype=torch.bool).contiguous()
+        with torch.cuda.device(self.device):
+            check(lib().lzb_tree_init_roots(ctypes.byref(self._struct), ptr(rs), ptr(act), stream_ptr(self.device)))
+
+    def _select(self, k: int) -> None:
+        with torch.cuda.device(self.device):
+            check(lib().lzb_tree_select(ctypes.byref(self._struct), ctypes.c_int32(k),
+                                        ctypes.c_double(self.exploration_weight), ctypes.c_double(self.virtual_loss),
+                                        ptr(self.leaf_node), ptr(self.leaf_status), ptr(self.leaf_states),
+                                        stream_ptr(self.device)))
+
+    def prepare_roots(self) -> None:
+        """Unexpanded, non-terminal roots become the pending leaves (slot t*K of each tree)."""
+        if self.k != 1:
+            self.leaf_status.fill_(LEAF_DONE)
+            self.leaf_node.fill_(-1)
+        # a root that is not expanded ends the descent immediately -> leaf == root; expanded roots (not used by
+        # reset-per-move searches) would descend, so prepare_roots is only valid right after reset().
+        self._select_roots()
+        self._pending_is_root = True
+
+    def _select_roots(self) -> None:
+        if self.k == 1:
+            self._select(1)
+            return
+        # K > 1: roots use slot t*K only
+        tmp_node = torch.empty((self.num_trees,), dtype=torch.int32, device=self.device)
+        tmp_status = torch.empty((self.num_trees,), dtype=torch.int32, device=self.device)
+        tmp_states = torch.empty((self.num_trees, 4), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().lzb_tree_select(ctypes.byref(self._struct), ctypes.c_int32(1),
+                                        ctypes.c_double(self.exploration_weight), ctypes.c_double(self.virtual_loss),
+                                        ptr(tmp_node), ptr(tmp_status), ptr(tmp_states), stream_ptr(self.device)))
+        self.leaf_node.view(self.num_trees, self.k)[:, 0] = tmp_node
+        self.leaf_status.view(self.num_trees, self.k)[:, 0] = tmp_status
+        self.leaf_states.view(self.num_trees, self.k, 4)[:, 0] = tmp_states
+
+    def select_leaves(self) -> None:
+        self._select(self.k)
+        self._pending_is_root = False
+
+    def complete_pending(self, priors: torch.Tensor, values: torch.Tensor) -> None:
+        """priors f32[T*K,220] dense over the action space, values f32[T*K]; rows of slots whose status is not
+        LEAF_EVAL are ignored.  Roots are expanded without a backup (portable_mcts.cpp:575)."""
+        slots = self.num_trees * self.k
+        if tuple(priors.shape) != (slots, ACTION_DIM) or values.numel() != slots:
+            raise RuntimeError(f"priors must be [{slots}, 220] and values [{slots}]")
+        require_cuda(priors, "priors")
+        p = priors.to(torch.float32).contiguous()
+        v = values.to(torch.float32).contiguous()
+        # K > 1 root preparation applied no virtual loss (K passed as 1 there), so revert none either
+        vl = 0.0 if self._pending_is_root else self.virtual_loss
+        k_eff = self.k
+        with torch.cuda.device(self.device):
+            check(lib().lzb_tree_expand_backup(ctypes.byref(self._struct), ctypes.c_int32(k_eff), ptr(self.leaf_node),
+                                               ptr(self.leaf_status), ptr(p), ptr(v),
+                                               ctypes.c_int32(0 if self._pending_is_root else 1),
+                                               ctypes.c_double(vl if self.k > 1 else 0.0), stream_ptr(self.device)))
+
+    def root_outputs(self, with_priors: bool = True) -> dict:
+        t, dev = self.num_trees, self.device
+        with torch.cuda.device(dev):
+            visits = torch.empty((t, ACTION_DIM), dtype=torch.int32, device=dev)
+            q = torch.empty((t, ACTION_DIM), dtype=torch.float32, device=dev)
+            rv = torch.empty((t,), dtype=torch.float32, device=dev)
+            legal = torch.empty((t, ACTION_DIM), dtype=torch.bool, device=dev)
+            term = torch.empty((t,), dtype=torch.bool, device=dev)
+            pri = torch.empty((t, ACTION_DIM), dtype=torch.float32, device=dev) if with_priors else None
+            check(lib().lzb_tree_root_outputs(ctypes.byref(self._struct), ptr(visits), ptr(q), ptr(rv), ptr(legal),
+                                              ptr(term), ptr(pri), stream_ptr(dev)))
+        return {"visit_counts": visits, "root_action_values": q, "root_values": rv, "legal_masks": legal,
+                "terminal": term, "root_priors": pri}
+
+    def set_root_priors(self, priors: torch.Tensor) -> None:
+        if tuple(priors.shape) != (self.num_trees, ACTION_DIM):
+            raise RuntimeError("root priors must have shape [trees, 220]")
+        p = priors.to(device=self.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            check(lib().lzb_tree_set_root_priors(ctypes.byref(self._struct), ptr(p), stream_ptr(self.device)))
+
+    # -- helpers -------------------------------------------------------------------------------------
+    def pending_inputs(self, layout: str = "f32_nchw", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Model-input planes of every leaf slot (rows of non-pending slots hold stale / zero states)."""
+        return encode_inputs(self.leaf_states, layout, out)
+
+    def stats(self) -> dict:
+        c = self.counters.tolist()
+        return {"nodes_used": int(c[0]), "overflow": bool(c[1]), "expansions": int(c[2]), "terminal_hits": int(c[3]),
+                "capacity": self.capacity}
+
+    def check_capacity(self) -> None:
+        if int(self.counters[1].item()):
+            raise RuntimeError(f"tree node arena exhausted (capacity {self.capacity}); raise node_capacity")
+
+
+def encode_inputs(packed: torch.Tensor, layout: str = "f32_nchw", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """packed int64[n,4] -> network input. 'f32_nchw': float32[n,11,6,6]; 'bf16_nhwc': bfloat16[n,11,6,6] in
+    channels_last memory format."""
+    require_cuda(packed, "packed")
+    dev = packed.device
+    packed = packed.contiguous()
+    n = packed.size(0)
+    with torch.cuda.device(dev):
+        if layout == "f32_nchw":
+            if out is None:
+                out = torch.empty((n, 11, 6, 6), dtype=torch.float32, device=dev)
+            code = 0
+        elif layout == "bf16_nhwc":
+            if out is None:
+                out = torch.empty((n, 11, 6, 6), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+            code = 1
+        else:
+            raise RuntimeError(f"unknown layout {layout}")
+        check(lib().lzb_encode_inputs_packed(ptr(packed), i64(n), ctypes.c_int32(code), ptr(out), stream_ptr(dev)))
+    return out
+
+
+def heads_to_priors(packed: torch.Tensor, log_p1: torch.Tensor, log_p2: torch.Tensor, log_pmc: torch.Tensor,
+                    value_logits: torch.Tensor, priors_out: Optional[torch.Tensor] = None,
+                    values_out: Optional[torch.Tensor] = None):
+    """Fused policy projection (masked softmax over the legal set of each packed state) + bucketed value decode."""
+    require_cuda(packed, "packed")
+    dev = packed.device
+    n = packed.size(0)
+    h = [x.reshape(n, 36).to(torch.float32).contiguous() for x in (log_p1, log_p2, log_pmc)]
+    vl = value_logits.reshape(n, -1).to(torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        if priors_out is None:
+            priors_out = torch.empty((n, ACTION_DIM), dtype=torch.float32, device=dev)
+        if values_out is None:
+            values_out = torch.empty((n,), dtype=torch.float32, device=dev)
+        check(lib().lzb_heads_to_priors(ptr(packed.contiguous()), i64(n), ptr(h[0]), ptr(h[1]), ptr(h[2]), ptr(vl),
+                                        ctypes.c_int32(vl.size(1)), ptr(priors_out), ptr(values_out), stream_ptr(dev)))
+    return priors_out, values_out
