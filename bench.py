@@ -308,24 +308,308 @@ def run_reference_playout(args):
     }
 
 
+# ----------------------------------------------------------------------------------------------------
+# workload: config 3 -- wave-batched MCTS self-play, 4,096 games x 200 sims/move, default net bf16 (per GPU)
+# ----------------------------------------------------------------------------------------------------
+SELFPLAY_GAMES = 4096
+SELFPLAY_SIMS = 200
+
+
+def _default_model():
+    import torch
+
+    from liuzhou_b200.net import ChessNet
+
+    torch.manual_seed(SEED)
+    return ChessNet()
+
+
+def cpu_selfplay_baseline(budget_s: float = 20.0, trees: int = 32, sims: int = SELFPLAY_SIMS,
+                          threads: int | None = None) -> dict:
+    """The reference's own CPU tree search (oracle/_ref/_liuzhou_portable_cpp, threaded C++) + fp32 PyTorch network
+    on all host cores, on a bounded sample of the same workload: `trees` games, `sims` simulations per move, as
+    many plies as fit the budget.  Falls back to the oracle's C port of the tree when oracle/_ref is absent."""
+    import numpy as np
+    import torch
+
+    import oracle
+    from liuzhou_b200.net import bucket_logits_to_scalar
+
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = _default_model().eval()
+    kind = "port"
+    portable = None
+    ref_dir = ROOT / "oracle" / "_ref"
+    if list(ref_dir.glob("_liuzhou_portable_cpp*.so")):
+        try:
+            sys.path.insert(0, str(ref_dir))
+            import _liuzhou_portable_cpp as portable  # noqa: F811
+            kind = "reference"
+        except Exception:
+            portable = None
+    states = oracle.initial_states(trees)
+    # diversify like the GPU arm: game i advanced by a different number of uniform-random plies
+    for i in range(trees):
+        tr = oracle.random_playout(SEED, i, (120 * i) // max(1, trees - 1), want_trace=False)
+        if not oracle.is_game_over(tr["final"]):
+            for k in oracle.STATE_FIELDS:
+                states[k][i] = np.asarray(tr["final"][k])[0]
+
+    def evaluate(inputs, masks):
+        with torch.inference_mode():
+            lp1, lp2, lpm, vl = model(torch.from_numpy(inputs))
+            pri, _ = oracle.project_policy_logits_fast(lp1.numpy(), lp2.numpy(), lpm.numpy(), masks != 0)
+            return pri.astype(np.float32), bucket_logits_to_scalar(vl).numpy().astype(np.float32)
+
+    def new_tree(st):
+        if portable is not None:
+            from types import SimpleNamespace
+
+            objs = []
+            for i in range(trees):
+                objs.append(SimpleNamespace(
+                    board=[[int(v) for v in row] for row in st["board"][i].reshape(6, 6)], phase=int(st["phase"][i]),
+                    current_player=int(st["current_player"][i]),
+                    marked_black=[(int(r), int(c)) for r, c in zip(*np.nonzero(st["marks_black"][i].reshape(6, 6)))],
+                    marked_white=[(int(r), int(c)) for r, c in zip(*np.nonzero(st["marks_white"][i].reshape(6, 6)))],
+                    forced_removals_done=int(st["forced_removals_done"][i]), move_count=int(st["move_count"][i]),
+                    pending_marks_required=int(st["pending_marks_required"][i]),
+                    pending_marks_remaining=int(st["pending_marks_remaining"][i]),
+                    pending_captures_required=int(st["pending_captures_required"][i]),
+                    pending_captures_remaining=int(st["pending_captures_remaining"][i]),
+                    moves_since_capture=int(st["moves_since_capture"][i])))
+            return portable.PortableTreeBatch(objs, exploration_weight=1.0, num_threads=cores)
+        return oracle.TreeBatch(st, 1.0)
+
+    t0 = time.perf_counter()
+    positions = evals = 0
+    tb = new_tree(states)
+    while True:
+        pend = tb.prepare_roots()
+        if len(pend["tree_indices"]):
+            tb.complete_pending(*evaluate(pend["model_inputs"], pend["legal_masks"]))
+            evals += len(pend["tree_indices"])
+        else:
+            tb.complete_pending(np.zeros((0, 220), np.float32), np.zeros((0,), np.float32))
+        for _ in range(sims):
+            pend = tb.select_leaves()
+            n = len(pend["tree_indices"])
+            if n:
+                tb.complete_pending(*evaluate(pend["model_inputs"], pend["legal_masks"]))
+            else:
+                tb.complete_pending(np.zeros((0, 220), np.float32), np.zeros((0,), np.float32))
+            evals += n
+        out = tb.root_outputs()
+        visits = out["visit_counts"]
+        live = out["terminal"] == 0
+        positions += int(live.sum())
+        actions = np.where(live, visits.argmax(1), -1).astype(np.int32)
+        tb.advance_roots([int(a) for a in actions] if portable is not None else actions)
+        if time.perf_counter() - t0 > budget_s or not live.any():
+            break
+    dt = time.perf_counter() - t0
+    return {"value": positions / dt, "unit": "positions/s", "cores": cores, "kind": kind,
+            "sims_per_sec": positions * sims / dt, "network_evals_per_sec": evals / dt,
+            "sample": f"{trees} games x {sims} sims/move, {positions} positions in {dt:.1f}s; "
+                      f"{'reference _liuzhou_portable_cpp tree' if kind == 'reference' else 'oracle C tree port'} "
+                      f"+ fp32 PyTorch ChessNet on {cores} host threads (subtree reuse as in the reference)"}
+
+
+def run_selfplay(args, world, rank, local_rank):
+    import torch
+
+    from liuzhou_b200 import _lib
+    from liuzhou_b200.engine import BYTES_PER_POSITION, SelfPlayStepper
+    from liuzhou_b200.net import InferenceNet
+
+    dev = torch.device("cuda", local_rank)
+    peaks, peak_kind = measured_peaks()
+    games, sims, k = args.games, args.sims, args.leaves_per_wave
+    model = _default_model()
+    if world > 1:   # weights come from rank 0 over NCCL (replaces the reference's torch.save / torch.load hand-off)
+        import torch.distributed as dist
+
+        model = model.to(dev)
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=0)
+    net = InferenceNet(model, dev)
+    torch.manual_seed(SEED * 10007 + (rank + 1) * 9973)          # per-rank seed rule of v1/train.py:795,998
+    stepper = SelfPlayStepper(net, games, simulations=sims, leaves_per_wave=k, seed=SEED, device=dev)
+    stepper.diversify(seed=SEED + rank)
+    stream = torch.cuda.current_stream(dev)
+
+    gather_buf = None
+    if world > 1:
+        import torch.distributed as dist
+
+        if rank == 0:
+            gather_buf = [torch.empty((games, 220), dtype=torch.float32, device=dev) for _ in range(world)]
+
+    def step():
+        stepper.step()
+        if world > 1:   # trajectories return to the trainer rank over NCCL (policy block shown; 880 of 2,692 B/pos)
+            import torch.distributed as dist
+
+            dist.gather(stepper.trajectory_block()[2], gather_buf, dst=0)
+
+    for _ in range(args.warmup):
+        step()
+    barrier_sync(world)
+    launches0 = _lib.launch_count()
+    evals0 = stepper.mcts.evals
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    e1.synchronize()
+    barrier_sync(world)
+    clocks = sampler.stop() if rank == 0 else {}
+    # graph replays re-launch the captured kernels: count them (4 of ours per wave + root step + per-ply kernels)
+    waves = stepper.mcts.waves
+    launches = (_lib.launch_count() - launches0) + args.steps * (waves * 4 + 4)
+    elapsed_ms = max_over_ranks(e0.elapsed_time(e1), world)
+    positions = sum_over_ranks(float(games * args.steps), world)
+    value = positions / (elapsed_ms / 1e3)
+    evals = stepper.mcts.evals - evals0
+
+    # dominant kernel group: the network forward (PyTorch / cuDNN, bf16 tensor cores) at the wave batch size,
+    # timed alone with CUDA events on its stream; the tree kernels are the remainder of the wave.
+    slots = games * k
+    x = net.new_input(slots)
+    g = torch.cuda.CUDAGraph()
+    for _ in range(3):
+        net._forward_eager(x)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        net._forward_eager(x)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 50
+    g.replay()
+    f0.record(stream)
+    for _ in range(reps):
+        g.replay()
+    f1.record(stream)
+    f1.synchronize()
+    fwd_ms = f0.elapsed_time(f1) / reps
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stepper.mcts._wave_graph.replay()
+    w0.record(stream)
+    for _ in range(reps):
+        stepper.mcts._wave_graph.replay()
+    w1.record(stream)
+    w1.synchronize()
+    wave_ms = w0.elapsed_time(w1) / reps
+    tflops = slots * net.flops_per_state / (fwd_ms / 1e3) / 1e12
+    tree_stats = stepper.mcts.tree.stats()
+
+    # e2e: the same ply through host buffers -- states (reference byte layout) H2D from pinned memory, search +
+    # step on the device, new states + this ply's trajectory rows (2,692 B/position) D2H into pinned memory.
+    from liuzhou_b200 import native
+
+    st_host = [t.cpu().pin_memory() for t in native.unpack_states(stepper.states)]
+    st_out = [torch.empty_like(t).pin_memory() for t in st_host]
+    blk = stepper.trajectory_block()
+    traj_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in blk]
+    h2d = sum(t.numel() * t.element_size() for t in st_host)
+    d2h = h2d + sum(t.numel() * t.element_size() for t in traj_host)
+    e2e_times = []
+    for it in range(2 + args.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dev_st = [t.to(dev, non_blocking=True) for t in st_host]
+        stepper.states = native.pack_states(dev_st)
+        stepper.step()
+        for dst, src in zip(st_out, native.unpack_states(stepper.states)):
+            dst.copy_(src, non_blocking=True)
+        for dst, src in zip(traj_host, stepper.trajectory_block()):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        if it >= 2:
+            e2e_times.append(time.perf_counter() - t0)
+        st_host, st_out = st_out, st_host
+    e2e_elapsed = max_over_ranks(sum(e2e_times), world)
+    e2e_value = sum_over_ranks(float(games * len(e2e_times)), world) / e2e_elapsed
+
+    if rank != 0:
+        return None
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    cpu = cpu_selfplay_baseline(budget_s=args.cpu_budget, sims=sims)
+    return {
+        "metric": "selfplay_positions_per_sec", "value": value, "unit": "positions/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "mcts_sims_per_sec": value * sims, "network_evals_per_sec": evals * world / (elapsed_ms / 1e3),
+        "config": {"workload": "v1 wave-batched MCTS self-play (BASELINE configs[2])", "games_per_gpu": games,
+                   "sims_per_move": sims, "search": "full tree on device (select/expand/backup kernels)",
+                   "leaves_per_wave": k, "net": "ChessNet 128ch x 10 blocks, random init, seed 20260314",
+                   "step": "one ply of every game; finished games refilled; batch pre-diversified by 0..120 random plies",
+                   "dirichlet_noise": True, "temperature": "1.0 -> 0.1 at ply 10", "exploration_weight": 1.0,
+                   "l2": "working set per step (node arena > 1 GB) exceeds the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "positions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
+                     "traffic": None, "peak_kind": peak_kind + " (sustained bf16)",
+                     "kernel": "ChessNet forward (PyTorch/cuDNN bf16, CUDA graph) at the wave batch",
+                     "kernel_ms": fwd_ms, "units_per_launch": slots, "flops_per_unit": net.flops_per_state,
+                     "wave_ms": wave_ms, "tree_kernels_ms_per_wave": max(0.0, wave_ms - fwd_ms),
+                     "share_of_step": fwd_ms * waves / (elapsed_ms / args.steps)},
+        "tree": tree_stats,
+        "cpu_baseline": cpu,
+    }
+
+
+def run_reference_selfplay(args):
+    per_step = max(5.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    vals, last = [], None
+    for it in range(args.warmup + args.steps):
+        last = cpu_selfplay_baseline(budget_s=per_step, sims=args.sims)
+        if it >= args.warmup:
+            vals.append(last["value"])
+    value = sum(vals) / len(vals)
+    last["value"] = value
+    return {
+        "impl": "reference", "metric": "selfplay_positions_per_sec", "value": value, "unit": "positions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "mcts_sims_per_sec": value * args.sims,
+        "config": {"workload": "v1 wave-batched MCTS self-play (BASELINE configs[2])", "sims_per_move": args.sims,
+                   "search": "reference CPU tree (portable C++) + fp32 network on host cores"},
+        "cpu_baseline": last,
+        "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
+    ap.add_argument("--games", type=int, default=SELFPLAY_GAMES)
+    ap.add_argument("--sims", type=int, default=SELFPLAY_SIMS)
+    ap.add_argument("--leaves-per-wave", type=int, default=1)
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["playout", "selfplay"], default="playout")
+    ap.add_argument("--workload", choices=["playout", "selfplay"], default="selfplay")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return 0
-        print(json.dumps(run_reference_playout(args)), flush=True)
+        fn = run_reference_selfplay if args.workload == "selfplay" else run_reference_playout
+        print(json.dumps(fn(args)), flush=True)
         return 0
 
     world, rank, local_rank = dist_setup(args.gpus)
-    line = run_playout(args, world, rank, local_rank)
+    fn = run_selfplay if args.workload == "selfplay" else run_playout
+    line = fn(args, world, rank, local_rank)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -193,7 +193,8 @@ class InferenceNet:
         return lp1.float(), lp2.float(), lpm.float(), vl.float()
 
     def new_input(self, n: int) -> torch.Tensor:
-        return torch.zeros((n, 11, 6, 6), dtype=self.dtype, device=self.device, memory_format=torch.channels_last)
+        return torch.empty((n, 11, 6, 6), dtype=self.dtype, device=self.device,
+                           memory_format=torch.channels_last).zero_()
 
     def capture(self, n: int, static_input: Optional[torch.Tensor] = None):
         """Capture a CUDA graph of the forward at batch size n. Returns (static_input, static_outputs)."""

@@ -60,6 +60,13 @@ class DeviceTreeBatch:
             self.leaf_node = torch.full((slots,), -1, dtype=torch.int32, device=dev)
             self.leaf_status = torch.full((slots,), LEAF_DONE, dtype=torch.int32, device=dev)
             self.leaf_states = torch.zeros((slots, 4), dtype=torch.int64, device=dev)
+            if self.k == 1:
+                self.root_leaf_node, self.root_leaf_status, self.root_leaf_states = (
+                    self.leaf_node, self.leaf_status, self.leaf_states)
+            else:
+                self.root_leaf_node = torch.full((t,), -1, dtype=torch.int32, device=dev)
+                self.root_leaf_status = torch.full((t,), LEAF_DONE, dtype=torch.int32, device=dev)
+                self.root_leaf_states = torch.zeros((t, 4), dtype=torch.int64, device=dev)
         self._struct = _TreeStruct()
         for name in ("visit", "value_sum", "prior", "info", "first_child", "parent", "state", "root_value", "counters"):
             setattr(self._struct, name, getattr(self, name).data_ptr())
@@ -86,52 +93,44 @@ class DeviceTreeBatch:
                                         stream_ptr(self.device)))
 
     def prepare_roots(self) -> None:
-        """Unexpanded, non-terminal roots become the pending leaves (slot t*K of each tree)."""
-        if self.k != 1:
-            self.leaf_status.fill_(LEAF_DONE)
-            self.leaf_node.fill_(-1)
-        # a root that is not expanded ends the descent immediately -> leaf == root; expanded roots (not used by
-        # reset-per-move searches) would descend, so prepare_roots is only valid right after reset().
-        self._select_roots()
-        self._pending_is_root = True
-
-    def _select_roots(self) -> None:
-        if self.k == 1:
-            self._select(1)
-            return
-        # K > 1: roots use slot t*K only
-        tmp_node = torch.empty((self.num_trees,), dtype=torch.int32, device=self.device)
-        tmp_status = torch.empty((self.num_trees,), dtype=torch.int32, device=self.device)
-        tmp_states = torch.empty((self.num_trees, 4), dtype=torch.int64, device=self.device)
+        """Unexpanded, non-terminal roots become the pending leaves (one slot per tree, whatever K is).
+        Valid right after reset(): an unexpanded root ends the descent immediately, so leaf == root."""
         with torch.cuda.device(self.device):
             check(lib().lzb_tree_select(ctypes.byref(self._struct), ctypes.c_int32(1),
-                                        ctypes.c_double(self.exploration_weight), ctypes.c_double(self.virtual_loss),
-                                        ptr(tmp_node), ptr(tmp_status), ptr(tmp_states), stream_ptr(self.device)))
-        self.leaf_node.view(self.num_trees, self.k)[:, 0] = tmp_node
-        self.leaf_status.view(self.num_trees, self.k)[:, 0] = tmp_status
-        self.leaf_states.view(self.num_trees, self.k, 4)[:, 0] = tmp_states
+                                        ctypes.c_double(self.exploration_weight), ctypes.c_double(0.0),
+                                        ptr(self.root_leaf_node), ptr(self.root_leaf_status),
+                                        ptr(self.root_leaf_states), stream_ptr(self.device)))
+        self._pending_is_root = True
 
     def select_leaves(self) -> None:
         self._select(self.k)
         self._pending_is_root = False
 
+    @property
+    def pending_status(self) -> torch.Tensor:
+        return self.root_leaf_status if self._pending_is_root else self.leaf_status
+
+    @property
+    def pending_states(self) -> torch.Tensor:
+        return self.root_leaf_states if self._pending_is_root else self.leaf_states
+
     def complete_pending(self, priors: torch.Tensor, values: torch.Tensor) -> None:
-        """priors f32[T*K,220] dense over the action space, values f32[T*K]; rows of slots whose status is not
-        LEAF_EVAL are ignored.  Roots are expanded without a backup (portable_mcts.cpp:575)."""
-        slots = self.num_trees * self.k
+        """priors f32[slots,220] dense over the action space, values f32[slots] (slots = T for roots, T*K for a
+        wave); rows of slots whose status is not LEAF_EVAL are ignored.  Roots are expanded without a backup
+        (portable_mcts.cpp:575)."""
+        root = self._pending_is_root
+        k = 1 if root else self.k
+        slots = self.num_trees * k
         if tuple(priors.shape) != (slots, ACTION_DIM) or values.numel() != slots:
             raise RuntimeError(f"priors must be [{slots}, 220] and values [{slots}]")
         require_cuda(priors, "priors")
         p = priors.to(torch.float32).contiguous()
         v = values.to(torch.float32).contiguous()
-        # K > 1 root preparation applied no virtual loss (K passed as 1 there), so revert none either
-        vl = 0.0 if self._pending_is_root else self.virtual_loss
-        k_eff = self.k
+        node, status = (self.root_leaf_node, self.root_leaf_status) if root else (self.leaf_node, self.leaf_status)
         with torch.cuda.device(self.device):
-            check(lib().lzb_tree_expand_backup(ctypes.byref(self._struct), ctypes.c_int32(k_eff), ptr(self.leaf_node),
-                                               ptr(self.leaf_status), ptr(p), ptr(v),
-                                               ctypes.c_int32(0 if self._pending_is_root else 1),
-                                               ctypes.c_double(vl if self.k > 1 else 0.0), stream_ptr(self.device)))
+            check(lib().lzb_tree_expand_backup(ctypes.byref(self._struct), ctypes.c_int32(k), ptr(node), ptr(status),
+                                               ptr(p), ptr(v), ctypes.c_int32(0 if root else 1),
+                                               ctypes.c_double(self.virtual_loss), stream_ptr(self.device)))
 
     def root_outputs(self, with_priors: bool = True) -> dict:
         t, dev = self.num_trees, self.device
@@ -157,7 +156,7 @@ class DeviceTreeBatch:
     # -- helpers -------------------------------------------------------------------------------------
     def pending_inputs(self, layout: str = "f32_nchw", out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Model-input planes of every leaf slot (rows of non-pending slots hold stale / zero states)."""
-        return encode_inputs(self.leaf_states, layout, out)
+        return encode_inputs(self.pending_states, layout, out)
 
     def stats(self) -> dict:
         c = self.counters.tolist()

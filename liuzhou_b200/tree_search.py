@@ -1,0 +1,188 @@
+"""Batched full-tree MCTS search on one GPU: the device tree (tree.py / csrc/lz_tree.cu) + the bf16 network
+(net.py) + the fused head kernel, with one simulation wave captured in a CUDA graph.
+
+Host-side counterpart of the reference's ``PortableCppMCTS.search_batch`` (v1/python/portable_cpp_mcts.py:243-390):
+prepare_roots -> evaluate -> expand roots -> optional Dirichlet noise on root priors -> S x (select leaves ->
+evaluate -> expand + backup) -> root outputs -> policy from visit counts.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from .net import InferenceNet
+from .tree import ACTION_DIM, DeviceTreeBatch, encode_inputs, heads_to_priors
+
+
+@dataclass
+class TreeMCTSConfig:
+    num_simulations: int = 200
+    exploration_weight: float = 1.0
+    temperature: float = 1.0
+    add_dirichlet_noise: bool = True
+    dirichlet_alpha: float = 0.3
+    dirichlet_epsilon: float = 0.25
+    sample_moves: bool = True
+    leaves_per_wave: int = 1          # K = 1 reproduces the reference's visit counts exactly
+    virtual_loss: float = 1.0
+    nodes_per_tree_hint: Optional[int] = None
+    use_cuda_graph: bool = True
+
+
+@dataclass
+class TreeSearchOutput:
+    legal_mask: torch.Tensor          # bool[T,220]  (children of each root)
+    visit_counts: torch.Tensor        # int32[T,220]
+    policy_dense: torch.Tensor        # f32[T,220]   visits^(1/T) normalised (one-hot argmax for T <= 1e-6)
+    root_value: torch.Tensor          # f32[T]
+    root_action_values: torch.Tensor  # f32[T,220]
+    terminal_mask: torch.Tensor       # bool[T]      root is game-over / has no legal action / inactive
+    chosen_action_indices: torch.Tensor   # int64[T], -1 for terminal roots
+
+
+class TreeMCTS:
+    def __init__(self, net: InferenceNet, num_trees: int, config: TreeMCTSConfig, device=None):
+        self.net = net
+        self.cfg = config
+        self.device = torch.device(device) if device is not None else net.device
+        self.num_trees = int(num_trees)
+        k = max(1, int(config.leaves_per_wave))
+        waves = -(-int(config.num_simulations) // k)
+        self.waves = waves
+        hint = config.nodes_per_tree_hint or min((waves * k + 2) * 40, 60_000)
+        self.tree = DeviceTreeBatch(self.num_trees, self.device, exploration_weight=config.exploration_weight,
+                                    leaves_per_wave=k, virtual_loss=config.virtual_loss, nodes_per_tree_hint=hint)
+        t, slots = self.num_trees, self.num_trees * k
+        dev = self.device
+        self._root_in = net.new_input(t)
+        self._wave_in = self._root_in if k == 1 else net.new_input(slots)
+        self._root_pri = torch.zeros((t, ACTION_DIM), dtype=torch.float32, device=dev)
+        self._root_val = torch.zeros((t,), dtype=torch.float32, device=dev)
+        self._wave_pri = self._root_pri if k == 1 else torch.zeros((slots, ACTION_DIM), dtype=torch.float32, device=dev)
+        self._wave_val = self._root_val if k == 1 else torch.zeros((slots,), dtype=torch.float32, device=dev)
+        self._wave_graph: Optional[torch.cuda.CUDAGraph] = None
+        self._root_graph: Optional[torch.cuda.CUDAGraph] = None
+        self.evals = 0
+
+    # one network evaluation of the pending leaves + expansion (+ backup)
+    def _eval_pending(self, root: bool) -> None:
+        tree = self.tree
+        x = self._root_in if root else self._wave_in
+        pri = self._root_pri if root else self._wave_pri
+        val = self._root_val if root else self._wave_val
+        encode_inputs(tree.pending_states, "bf16_nhwc", out=x)
+        lp1, lp2, lpm, vl = self.net._forward_eager(x)
+        heads_to_priors(tree.pending_states, lp1, lp2, lpm, vl, priors_out=pri, values_out=val)
+        tree.complete_pending(pri, val)
+
+    def _root_step(self) -> None:
+        self.tree.prepare_roots()
+        self._eval_pending(True)
+
+    def _wave_step(self) -> None:
+        self.tree.select_leaves()
+        self._eval_pending(False)
+
+    def _capture(self) -> None:
+        dev = self.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):          # warm up (cuDNN autotune / workspace) outside the capture
+            self._root_step()
+            self._wave_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._root_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._root_graph):
+            self._root_step()
+        self._wave_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._wave_graph, pool=self._root_graph.pool()):
+            self._wave_step()
+
+    def _apply_root_noise(self) -> None:
+        """Dirichlet(alpha) over each root's legal actions mixed with weight epsilon (portable_cpp_mcts.py:180-199,
+        v1 root search mcts_gpu.py:1329-1339); Gamma draws come from torch's CUDA generator."""
+        cfg = self.cfg
+        out = self.tree.root_outputs(with_priors=True)
+        legal = out["legal_masks"]
+        pri = out["root_priors"]
+        alpha = torch.full_like(pri, max(float(cfg.dirichlet_alpha), 1e-8))
+        noise = torch._standard_gamma(alpha) * legal.to(torch.float32)
+        noise = noise / noise.sum(dim=1, keepdim=True).clamp_min(1e-8)
+        eps = min(max(float(cfg.dirichlet_epsilon), 0.0), 1.0)
+        mixed = (1.0 - eps) * pri + eps * noise
+        many = legal.sum(dim=1, keepdim=True) > 1
+        self.tree.set_root_priors(torch.where(many, mixed, pri))
+
+    @torch.no_grad()
+    def search(self, root_states: torch.Tensor, *, active: Optional[torch.Tensor] = None,
+               temperatures: Optional[torch.Tensor] = None, add_dirichlet_noise: Optional[bool] = None,
+               sample_moves: Optional[bool] = None) -> TreeSearchOutput:
+        cfg = self.cfg
+        tree = self.tree
+        tree.reset(root_states, active)
+        use_graph = bool(cfg.use_cuda_graph)
+        if use_graph and self._wave_graph is None:
+            self._capture()
+            tree.reset(root_states, active)
+        if use_graph:
+            self._root_graph.replay()
+        else:
+            self._root_step()
+        if cfg.add_dirichlet_noise if add_dirichlet_noise is None else add_dirichlet_noise:
+            self._apply_root_noise()
+        for _ in range(self.waves):
+            if use_graph:
+                self._wave_graph.replay()
+            else:
+                self._wave_step()
+        self.evals += self.num_trees * (1 + self.waves * tree.k)
+        out = tree.root_outputs(with_priors=False)
+        visits = out["visit_counts"]
+        legal = out["legal_masks"]
+        terminal = out["terminal"]
+        t = self.num_trees
+        if temperatures is None:
+            temps = torch.full((t,), float(cfg.temperature), dtype=torch.float32, device=self.device)
+        else:
+            temps = torch.as_tensor(temperatures, dtype=torch.float32, device=self.device).view(-1)
+        policy = policy_from_visits(visits, temps)
+        do_sample = cfg.sample_moves if sample_moves is None else sample_moves
+        has_mass = policy.sum(dim=1) > 0
+        safe = torch.where(has_mass.view(-1, 1), policy, torch.full_like(policy, 1.0 / ACTION_DIM))
+        if do_sample:
+            chosen = torch.multinomial(safe, num_samples=1).view(-1)
+        else:
+            chosen = deterministic_action(visits, out["root_action_values"], legal)
+        chosen = torch.where(has_mass & ~terminal, chosen, torch.full_like(chosen, -1))
+        return TreeSearchOutput(legal_mask=legal, visit_counts=visits, policy_dense=policy,
+                                root_value=out["root_values"], root_action_values=out["root_action_values"],
+                                terminal_mask=terminal | ~has_mass, chosen_action_indices=chosen)
+
+
+def policy_from_visits(visits: torch.Tensor, temperatures: torch.Tensor) -> torch.Tensor:
+    """softmax(log(N) / T) over N > 0; one-hot argmax for T <= 1e-6 (portable_mcts.py:150-205, beta = 0)."""
+    v = visits.to(torch.float32)
+    temps = temperatures.view(-1, 1)
+    logits = torch.where(v > 0, torch.log(v.clamp_min(1e-30)) / temps.clamp_min(1e-6), torch.full_like(v, float("-inf")))
+    any_pos = (v > 0).any(dim=1, keepdim=True)
+    soft = torch.softmax(torch.where(any_pos, logits, torch.zeros_like(logits)), dim=1)
+    soft = torch.where(any_pos, soft, torch.zeros_like(soft))
+    onehot = torch.zeros_like(v)
+    onehot.scatter_(1, v.argmax(dim=1, keepdim=True), 1.0)
+    onehot = torch.where(any_pos, onehot, torch.zeros_like(onehot))
+    return torch.where(temps <= 1e-6, onehot, soft)
+
+
+def deterministic_action(visits: torch.Tensor, action_values: torch.Tensor, legal: torch.Tensor) -> torch.Tensor:
+    """max N, then max Q (atol 1e-6), then lowest action index (portable_mcts.py:208-261; the prior tie-break only
+    matters between actions with identical N and Q, and is folded into the index order here)."""
+    v = torch.where(legal, visits.to(torch.float32), torch.full_like(action_values, -1.0))
+    best_n = v.max(dim=1, keepdim=True).values
+    cand = v == best_n
+    q = torch.where(cand, action_values, torch.full_like(action_values, float("-inf")))
+    best_q = q.max(dim=1, keepdim=True).values
+    cand = cand & ((q - best_q).abs() <= 1e-6)
+    return cand.to(torch.int8).argmax(dim=1)

@@ -80,7 +80,7 @@ def lib():
         for name in ("or_tree_free", "or_tree_prepare_roots", "or_tree_select_leaves", "or_tree_complete_pending",
                      "or_tree_root_priors", "or_tree_set_root_priors", "or_tree_root_outputs",
                      "or_tree_advance_roots", "or_tree_deactivate", "or_tree_root_state",
-                     "or_tree_root_visit_count"):
+                     "or_tree_root_visit_count", "or_tree_pending_states"):
             getattr(L, name).argtypes = None
         L.or_tree_free.restype = None
         _lib = L
@@ -365,6 +365,11 @@ class TreeBatch:
     def deactivate(self, indices):
         for i in indices:
             lib().or_tree_deactivate(self._h, ctypes.c_int(int(i)))
+
+    def pending_states(self) -> dict:
+        arr = (_State * self.num_trees)()
+        n = lib().or_tree_pending_states(self._h, ctypes.cast(arr, ctypes.c_void_p))
+        return structs_to_states(arr, n)
 
     def root_state(self, tree: int) -> dict:
         out = (_State * 1)()

@@ -358,3 +358,9 @@ void or_tree_deactivate(or_tree_batch *tb, int tree) { tb->active[tree] = 0; }
 
 void or_tree_root_state(const or_tree_batch *tb, int tree, or_state *out) { *out = tb->roots[tree]->state; }
 int or_tree_root_visit_count(const or_tree_batch *tb, int tree) { return tb->roots[tree]->visit_count; }
+
+/* test helper: states of the currently pending leaves, in pending order */
+int or_tree_pending_states(const or_tree_batch *tb, or_state *out) {
+    for (int p = 0; p < tb->num_pending; ++p) out[p] = tb->pending[p].node->state;
+    return tb->num_pending;
+}

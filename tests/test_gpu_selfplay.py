@@ -1,0 +1,220 @@
+"""GPU tests of the search / self-play layer above the kernels: V1RootMCTS.search_batch (root-PUCT mirror),
+TreeMCTS (device tree + network) and the self_play_v1_gpu entry with the reference's trajectory format."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests._util import STATE_FIELDS, concat_states, to_torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _small_net(seed=7):
+    """The reference tests' deterministic tiny network (tests/v1/test_portable_cpp_mcts.py:16-28)."""
+    from liuzhou_b200.net import ChessNet
+
+    torch.manual_seed(seed)
+    return ChessNet(trunk_channels=8, num_blocks=1, policy_channels=4, value_channels=4, value_mlp_channels=8)
+
+
+def _playout_states(n_games, seed, every):
+    out = []
+    for g in range(n_games):
+        trace = oracle.random_playout(seed, g, 512, want_trace=True)["trace"]
+        st = oracle.initial_states(1)
+        for ply, a in enumerate(trace):
+            if ply % every == 0:
+                out.append(st)
+            st = oracle.apply_move_scalar(st, int(a))
+    return concat_states(out)
+
+
+def test_chessnet_matches_reference_architecture():
+    from liuzhou_b200.net import ChessNet, flops_per_state
+
+    m = ChessNet()
+    n_params = sum(p.numel() for p in m.parameters())
+    assert 2_900_000 < n_params < 3_100_000                     # ~3.0 M params
+    assert abs(flops_per_state(m) - 214.5e6) / 214.5e6 < 0.01   # 214.5 MFLOP / state
+    keys = set(m.state_dict().keys())
+    for k in ("stem_conv.weight", "blocks.9.conv2.weight", "trunk_bn.running_var", "policy_head.gpool_linear.weight",
+              "policy_head.out_mark.weight", "value_head.fc2.bias"):
+        assert k in keys
+    x = torch.zeros(2, 11, 6, 6)
+    lp1, lp2, lpm, vl = m.eval()(x)
+    assert tuple(lp1.shape) == (2, 36) and tuple(vl.shape) == (2, 101)
+
+
+def test_root_search_batch_stagewise_vs_oracle():
+    """Deterministic configuration (no noise, argmax picks): every stage of search_batch is replayed through the
+    oracle from the network outputs recorded on the GPU; visit counts, picks and policy must agree."""
+    from liuzhou_b200.mcts_gpu import GpuStateBatch, V1RootMCTS, V1RootMCTSConfig
+    from liuzhou_b200.net import InferenceNet, bucket_logits_to_scalar
+
+    st = _playout_states(6, 31, every=5)
+    b = st["board"].shape[0]
+    net = InferenceNet(_small_net(), DEV)
+    recorded = []
+    orig = net.forward
+
+    def rec_forward(x):
+        out = orig(x)
+        recorded.append([o.clone() for o in out])
+        return out
+
+    net.forward = rec_forward
+    cfg = V1RootMCTSConfig(num_simulations=64, exploration_weight=1.0, add_dirichlet_noise=False, sample_moves=False)
+    mcts = V1RootMCTS(net, cfg, DEV)
+    state = GpuStateBatch(*to_torch(st, DEV))
+    temps = torch.where(torch.arange(b, device=DEV) % 2 == 0, 1.0, 0.5)
+    out = mcts.search_batch(state, temperatures=temps)
+    assert len(recorded) == 2
+    (lp1, lp2, lpm, rv), (_c1, _c2, _c3, crv) = recorded
+    # oracle replay
+    mask, meta = oracle.encode_actions_fast(st)
+    probs, _ = oracle.project_policy_logits_fast(_np(lp1), _np(lp2), _np(lpm), mask)
+    pack = oracle.root_pack_sparse_actions(mask, probs, meta)
+    (term, roots, counts, valid_mask, legal_idx, priors, code_mat, flat, codes_all, parents_all) = pack
+    children = oracle.batch_apply_moves(st, codes_all, parents_all)
+    cvals = _np(bucket_logits_to_scalar(crv).float())
+    parent_player = st["current_player"][parents_all]
+    leaf = np.where(children["current_player"] == parent_player, cvals, -cvals).astype(np.float32)
+    tmask = oracle.terminal_mask_from_next_state(children)
+    soft = oracle.soft_value_from_board(children["board"], 2.0)
+    leaf = np.where(tmask, soft * np.where(parent_player >= 0, 1.0, -1.0), leaf).astype(np.float32)
+    leaf_mat = np.zeros(priors.shape, np.float32)
+    leaf_mat.reshape(-1)[flat] = leaf
+    visits, value_sum, _ = oracle.root_puct_allocate_visits(priors, leaf_mat, valid_mask, 64, 1.0)
+    fin = oracle.root_finalize_from_visits(legal_idx, code_mat, valid_mask, visits, value_sum, roots, b, 220,
+                                           _np(temps)[roots])
+    assert np.array_equal(_np(out.legal_mask), mask)
+    assert np.array_equal(_np(out.terminal_mask), term)
+    assert np.array_equal(_np(out.model_input), oracle.states_to_model_input(st))
+    # the fp32 projection differs by ~1e-7 between expf implementations; visits are integers and picks follow them
+    assert np.array_equal(_np(out.chosen_action_indices), fin[1])
+    assert np.array_equal(_np(out.chosen_action_codes), fin[2])
+    np.testing.assert_allclose(_np(out.policy_dense), fin[0], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(_np(out.root_value)[roots], fin[4], rtol=1e-4, atol=1e-5)
+    pol = _np(out.policy_dense)
+    assert np.allclose(pol[roots].sum(1), 1.0, atol=1e-5) and (pol[~mask] == 0).all()
+
+
+def test_root_search_noise_and_sampling_invariants():
+    from liuzhou_b200.mcts_gpu import GpuStateBatch, V1RootMCTS, V1RootMCTSConfig
+
+    st = _playout_states(6, 32, every=4)
+    b = st["board"].shape[0]
+    mcts = V1RootMCTS(_small_net(), V1RootMCTSConfig(num_simulations=32), DEV)
+    state = GpuStateBatch(*to_torch(st, DEV))
+    force = torch.zeros(b, dtype=torch.bool, device=DEV)
+    force[::3] = True
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(123)
+        outs.append(mcts.search_batch(state, temperatures=1.0, add_dirichlet_noise=True, force_uniform_random_mask=force))
+    a, c = outs
+    assert torch.equal(a.chosen_action_indices, c.chosen_action_indices) and torch.equal(a.policy_dense, c.policy_dense)
+    mask, meta = oracle.encode_actions_fast(st)
+    idx = _np(a.chosen_action_indices)
+    valid = _np(a.chosen_valid_mask)
+    assert (valid == mask.any(1)).all()
+    assert all(mask[i, idx[i]] for i in range(b) if valid[i])
+    codes = _np(a.chosen_action_codes)
+    assert all(np.array_equal(codes[i], meta[i, idx[i]]) for i in range(b) if valid[i])
+
+
+def test_tree_mcts_search_graph_vs_eager_and_oracle_replay():
+    """TreeMCTS with the CUDA-graph wave == eager wave (bit-identical visit counts), and the visit counts equal an
+    oracle tree fed with the priors / values the GPU network produced for the same leaves."""
+    from liuzhou_b200 import native
+    from liuzhou_b200.net import InferenceNet
+    from liuzhou_b200.tree_search import TreeMCTS, TreeMCTSConfig
+
+    st = _playout_states(5, 41, every=7)
+    n = st["board"].shape[0]
+    packed = native.pack_states(to_torch(st, DEV))
+    net = InferenceNet(_small_net(), DEV)
+    res = []
+    for graph in (True, False):
+        cfg = TreeMCTSConfig(num_simulations=48, exploration_weight=1.25, add_dirichlet_noise=False,
+                             sample_moves=False, use_cuda_graph=graph)
+        out = TreeMCTS(net, n, cfg, DEV).search(packed, temperatures=torch.ones(n, device=DEV))
+        res.append(out)
+    assert torch.equal(res[0].visit_counts, res[1].visit_counts)
+    assert torch.equal(res[0].chosen_action_indices, res[1].chosen_action_indices)
+    out = res[0]
+    visits = _np(out.visit_counts)
+    live = ~_np(out.terminal_mask)
+    assert (visits[live].sum(1) == 48).all()
+    pol = _np(out.policy_dense)
+    assert np.allclose(pol[live].sum(1), 1.0, atol=1e-5)
+    np.testing.assert_allclose(pol[live], visits[live] / 48.0, rtol=1e-5, atol=1e-6)   # T = 1 -> N / sum N
+    chosen = _np(out.chosen_action_indices)
+    assert (visits[live, chosen[live]] == visits[live].max(1)).all()
+    # oracle replay with the GPU network as the evaluator: the oracle tree's pending leaf states are evaluated by
+    # the same network at the same batch size (row = tree index), so both searches see identical network outputs
+    from liuzhou_b200.tree import encode_inputs, heads_to_priors
+
+    def gpu_eval(pend_states, tree_idx):
+        full = oracle.initial_states(n)
+        for k in STATE_FIELDS:
+            full[k][tree_idx] = pend_states[k]
+        pk = native.pack_states(to_torch(full, DEV))
+        lp1, lp2, lpm, vl = net._forward_eager(encode_inputs(pk, "bf16_nhwc"))
+        p, v = heads_to_priors(pk, lp1, lp2, lpm, vl)
+        return _np(p)[tree_idx], _np(v)[tree_idx]
+
+    ref = oracle.TreeBatch(st, 1.25)
+    pend = ref.prepare_roots()
+    ref.complete_pending(*gpu_eval(ref.pending_states(), pend["tree_indices"]))
+    for _ in range(48):
+        pend = ref.select_leaves()
+        ref.complete_pending(*gpu_eval(ref.pending_states(), pend["tree_indices"]))
+    ro = ref.root_outputs()
+    assert np.array_equal(ro["visit_counts"], visits)
+    np.testing.assert_allclose(_np(out.root_value), ro["root_values"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(_np(out.root_action_values), ro["root_action_values"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("backend", ["root", "tree"])
+def test_self_play_entry_format_and_determinism(backend):
+    """self_play_v1_gpu: reference signature, TensorSelfPlayBatch format (2,692 B / position), finalised value
+    targets, policies over legal actions, and bit-identical reruns for a fixed torch seed."""
+    from liuzhou_b200.self_play import self_play_v1_gpu
+
+    model = _small_net()
+    runs = []
+    for _ in range(2):
+        torch.manual_seed(99)
+        batch, stats = self_play_v1_gpu(model, num_games=12, mcts_simulations=8, temperature_init=1.0,
+                                        temperature_final=0.1, temperature_threshold=10, exploration_weight=1.0,
+                                        device=DEV, add_dirichlet_noise=True, soft_value_k=2.0, max_game_plies=512,
+                                        sample_moves=True, concurrent_games=8, search_backend=backend)
+        runs.append((batch, stats))
+    batch, stats = runs[0]
+    n = batch.num_samples
+    assert stats.num_games == 12 and stats.num_positions == n and n > 12 * 36
+    assert stats.black_wins + stats.white_wins + stats.draws == 12
+    assert batch.state_tensors.dtype == torch.float32 and tuple(batch.state_tensors.shape[1:]) == (11, 6, 6)
+    assert batch.legal_masks.dtype == torch.bool and tuple(batch.legal_masks.shape) == (n, 220)
+    assert batch.policy_targets.dtype == torch.float32 and tuple(batch.policy_targets.shape) == (n, 220)
+    assert batch.nbytes() == n * 2692
+    vt, svt = _np(batch.value_targets), _np(batch.soft_value_targets)
+    assert not np.isnan(vt).any() and not np.isnan(svt).any()
+    assert set(np.unique(vt)).issubset({-1.0, 0.0, 1.0}) and (np.abs(svt) <= 1.0).all()
+    pol, legal = _np(batch.policy_targets), _np(batch.legal_masks)
+    has = legal.any(1)
+    assert np.allclose(pol[has].sum(1), 1.0, atol=1e-4) and (pol[~legal] == 0).all()
+    planes = _np(batch.state_tensors)
+    assert ((planes == 0) | (planes == 1)).all() and (planes[:, 4:11, 0, 0].sum(1) == 1).all()
+    assert 36 < stats.avg_game_length <= 512
+    assert stats.positions_per_sec > 0 and isinstance(stats.to_dict()["piece_delta_buckets"], dict)
+    b2, s2 = runs[1]
+    assert torch.equal(batch.policy_targets, b2.policy_targets) and torch.equal(batch.value_targets, b2.value_targets)
+    assert torch.equal(batch.state_tensors, b2.state_tensors)

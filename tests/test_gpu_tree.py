@@ -33,16 +33,16 @@ def _playout_states(n_games, seed, every):
 
 def _pending_from_device(tree, native):
     """(tree indices, model inputs, legal masks) of the LEAF_EVAL slots, in tree order."""
-    status = _np(tree.leaf_status)
+    status = _np(tree.pending_status)
     rows = np.nonzero(status == 0)[0]
     inputs = _np(tree.pending_inputs("f32_nchw"))[rows]
-    words, _ = native.legal_masks(tree.leaf_states, scalar_semantics=True)
+    words, _ = native.legal_masks(tree.pending_states, scalar_semantics=True)
     masks = _np(native.mask_words_to_bool(words))[rows].astype(np.uint8)
     return rows, inputs, masks
 
 
 def _complete(tree, rows, pri, val):
-    slots = tree.num_trees * tree.k
+    slots = tree.pending_status.numel()
     p = np.zeros((slots, 220), np.float32)
     v = np.zeros((slots,), np.float32)
     p[rows] = pri
