@@ -247,6 +247,18 @@ LZB_API int lzb_heads_to_priors(const uint64_t *states, int64_t n, const float *
                                 const float *log_pmc, const float *value_logits, int32_t bins, float *priors,
                                 float *values, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (a17 glue) Fused elementwise epilogues around the network's cuDNN convolutions, bf16 channels-last
+ * (replaces PyTorch's separate eval-BatchNorm / ReLU / residual-add passes of
+ * src/neural_network.py:83-96,250-254):
+ *   v == NULL : out_act = relu(scale * u + shift)
+ *   v != NULL : sum = u + v (stored to out_sum if non-NULL) ; out_act = relu(scale * sum + shift)
+ * u, v, out_* bf16[rows, channels]; scale / shift f32[channels] (BatchNorm folded: scale = w / sqrt(var + eps),
+ * shift = b - mean * scale).
+ * ---------------------------------------------------------------------------------------------- */
+LZB_API int lzb_bn_relu_bf16(const void *u, const void *v, const float *scale, const float *shift, int64_t rows,
+                             int32_t channels, void *out_sum, void *out_act, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

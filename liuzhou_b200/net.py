@@ -151,6 +151,67 @@ def flops_per_state(model: ChessNet) -> float:
     return total
 
 
+def _fold_bn(bn: nn.BatchNorm2d):
+    """eval-mode BatchNorm as y = scale * x + shift (fp32 vectors)."""
+    scale = (bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)).contiguous()
+    shift = (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
+    return scale, shift
+
+
+class FusedTrunk:
+    """The ChessNet trunk with cuDNN convolutions (bf16 channels-last implicit GEMMs on the tensor cores) and OUR fused
+    epilogue kernel (csrc/lz_nn.cu) instead of PyTorch's separate BatchNorm / ReLU / add passes: one elementwise pass
+    per convolution.  Same math as ChessNet.forward up to `trunk_act` (src/neural_network.py:250-254)."""
+
+    def __init__(self, model: "ChessNet"):
+        self.model = model
+        self.refresh()
+
+    def refresh(self) -> None:
+        """(Re)fold the BatchNorm statistics; in place when already folded, so captured CUDA graphs stay valid."""
+        m = self.model
+        new = {"stem": _fold_bn(m.stem_bn), "bn1": [_fold_bn(b.bn1) for b in m.blocks],
+               "bn2": [_fold_bn(b.bn2) for b in m.blocks], "trunk": _fold_bn(m.trunk_bn)}
+        if not hasattr(self, "stem"):
+            self.stem, self.bn1, self.bn2, self.trunk = new["stem"], new["bn1"], new["bn2"], new["trunk"]
+            return
+        for dst, src in [(self.stem, new["stem"]), (self.trunk, new["trunk"])] + list(zip(self.bn1, new["bn1"])) + \
+                list(zip(self.bn2, new["bn2"])):
+            dst[0].copy_(src[0])
+            dst[1].copy_(src[1])
+
+    @staticmethod
+    def _bn_relu(u, v, scale_shift, want_sum: bool):
+        import ctypes
+
+        from ._lib import check, i64, lib, ptr, stream_ptr
+
+        n, c, h, w = u.shape
+        out_act = torch.empty_like(u)
+        out_sum = torch.empty_like(u) if (v is not None and want_sum) else None
+        check(lib().lzb_bn_relu_bf16(ptr(u), ptr(v), ptr(scale_shift[0]), ptr(scale_shift[1]), i64(n * h * w),
+                                     ctypes.c_int32(c), ptr(out_sum), ptr(out_act), stream_ptr(u.device)))
+        return out_sum, out_act
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        m = self.model
+        nb = len(m.blocks)
+        c = F.conv2d(x, m.stem_conv.weight, None, 1, 1)
+        _, xr = self._bn_relu(c, None, self.stem, False)                   # x0 = relu(stem_bn(conv))
+        if nb == 0:
+            _, a = self._bn_relu(xr, None, self.trunk, False)
+            return a
+        _, a = self._bn_relu(xr, None, self.bn1[0], False)                  # a0 = relu(bn1_0(x0))
+        for i, blk in enumerate(m.blocks):
+            h = F.conv2d(a, blk.conv1.weight, None, 1, 1)
+            _, h = self._bn_relu(h, None, self.bn2[i], False)
+            c2 = F.conv2d(h, blk.conv2.weight, None, 1, 1)
+            last = i == nb - 1
+            nxt = self.trunk if last else self.bn1[i + 1]
+            xr, a = self._bn_relu(xr, c2, nxt, not last)                   # x' = x + conv2 ; a = relu(bn_next(x'))
+        return a
+
+
 class InferenceNet:
     """bf16 / channels-last / CUDA-graph inference wrapper around a ChessNet on one GPU.
 
@@ -158,13 +219,18 @@ class InferenceNet:
     and returns fp32 (log_p1, log_p2, log_pmc, value_logits).  For batch sizes registered with ``capture``
     the forward is a graph replay on static buffers (returned tensors alias those buffers)."""
 
-    def __init__(self, model: ChessNet, device, dtype: torch.dtype = torch.bfloat16):
+    def __init__(self, model: ChessNet, device, dtype: torch.dtype = torch.bfloat16, fused: bool = True):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("InferenceNet needs a CUDA device")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         self.dtype = dtype
         self.model = self._clone_for_inference(model, dev, dtype)
+        # fused epilogue kernels need bf16 and a channel count that is a multiple of 8
+        self.fused = bool(fused) and dtype == torch.bfloat16 and self.model.stem_conv.out_channels % 8 == 0
+        self.trunk = FusedTrunk(self.model) if self.fused else None
         self.flops_per_state = flops_per_state(self.model)
         self._graphs: Dict[int, Tuple[torch.cuda.CUDAGraph, torch.Tensor, Tuple[torch.Tensor, ...]]] = {}
 
@@ -186,10 +252,18 @@ class InferenceNet:
             for k, v in state_dict.items():
                 if k in own:
                     own[k].copy_(v.to(device=self.device, dtype=own[k].dtype))
+        if self.trunk is not None:
+            self.trunk.refresh()
 
     @torch.no_grad()
     def _forward_eager(self, x: torch.Tensor):
-        lp1, lp2, lpm, vl = self.model(x)
+        if self.trunk is not None:
+            with torch.cuda.device(self.device):
+                a = self.trunk(x)
+                lp1, lp2, lpm = self.model.policy_head(a)
+                vl = self.model.value_head(a)
+        else:
+            lp1, lp2, lpm, vl = self.model(x)
         return lp1.float(), lp2.float(), lpm.float(), vl.float()
 
     def new_input(self, n: int) -> torch.Tensor:

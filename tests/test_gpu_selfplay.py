@@ -218,3 +218,34 @@ def test_self_play_entry_format_and_determinism(backend):
     b2, s2 = runs[1]
     assert torch.equal(batch.policy_targets, b2.policy_targets) and torch.equal(batch.value_targets, b2.value_targets)
     assert torch.equal(batch.state_tensors, b2.state_tensors)
+
+
+def test_fused_trunk_matches_pytorch_forward():
+    """Our fused BatchNorm+ReLU(+residual add) epilogue kernels around the cuDNN convolutions reproduce the plain
+    PyTorch bf16 forward (bf16 rounding tolerance), with non-trivial BatchNorm statistics."""
+    from liuzhou_b200.net import ChessNet, InferenceNet
+
+    torch.manual_seed(3)
+    model = ChessNet(trunk_channels=32, num_blocks=3, policy_channels=16, value_channels=16, value_mlp_channels=32)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0.0, 0.3)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0.0, 0.2)
+    fused = InferenceNet(model, DEV, fused=True)
+    plain = InferenceNet(model, DEV, fused=False)
+    assert fused.trunk is not None and plain.trunk is None
+    x = fused.new_input(257)
+    x.copy_((torch.rand(257, 11, 6, 6, device=DEV) > 0.6).to(torch.bfloat16))
+    a, b = fused._forward_eager(x), plain._forward_eager(x)
+    for u, v in zip(a, b):
+        torch.testing.assert_close(u, v, rtol=5e-2, atol=5e-2)
+    # policy heads are log-probabilities: compare the distributions
+    for u, v in zip(a[:3], b[:3]):
+        assert float((u.exp() - v.exp()).abs().max()) < 2e-2
+    # graph replay == eager
+    xin, outs = fused.capture(257, x)
+    got = [o.clone() for o in fused.forward(x)]
+    for u, v in zip(got, a):
+        assert torch.equal(u, v)
