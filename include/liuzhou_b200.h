@@ -259,6 +259,19 @@ LZB_API int lzb_heads_to_priors(const uint64_t *states, int64_t n, const float *
 LZB_API int lzb_bn_relu_bf16(const void *u, const void *v, const float *scale, const float *shift, int64_t rows,
                              int32_t channels, void *out_sum, void *out_act, void *stream);
 
+/* Fused network heads: everything of PolicyHead / ValueHead after their 1x1 convolutions
+ * (src/neural_network.py:98-151: global pooling, gpool_linear, bn2 + relu, the three output convs,
+ * log-softmax, value MLP) + bucket expectation (:201-210) + masked softmax over the legal actions of the
+ * packed state (project_policy_logits_fast.cpp:16-164) in one kernel.
+ * pv bf16[n,36,pc+vc] = relu(bn1(conv1x1)) of both heads (policy channels first); weights fp32, transposed:
+ * wgl_t[3pc][pc], wout[3][pc], wfc1_t[3vc][mlp], wfc2_t[mlp][bins]. Any output may be NULL:
+ * priors f32[n,220] (needs states), values f32[n], log_heads f32[n,3,36], value_logits f32[n,bins]. */
+LZB_API int lzb_heads_tail(const void *pv, int64_t n, int32_t pc, int32_t vc, int32_t mlp, int32_t bins,
+                           const float *wgl_t, const float *bn2_scale, const float *bn2_shift, const float *wout,
+                           const float *wfc1_t, const float *bfc1, const float *wfc2_t, const float *bfc2,
+                           const uint64_t *states, float *priors, float *values, float *log_heads,
+                           float *value_logits, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

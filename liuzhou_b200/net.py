@@ -212,6 +212,85 @@ class FusedTrunk:
         return a
 
 
+class FusedHeads:
+    """PolicyHead + ValueHead as ONE cuDNN 1x1 convolution (both heads' conv1 stacked) + our bn_relu epilogue + ONE
+    fused kernel for everything after it (csrc/lz_nn.cu: heads_tail_kernel), optionally fused with the masked
+    softmax over legal actions and the bucket expectation."""
+
+    def __init__(self, model: "ChessNet"):
+        self.model = model
+        ph, vh = model.policy_head, model.value_head
+        self.pc, self.vc = ph.conv1.out_channels, vh.conv1.out_channels
+        self.mlp, self.bins = vh.fc1.out_features, vh.fc2.out_features
+        self.supported = (self.pc <= 64 and self.vc <= 64 and self.mlp <= 128 and 2 <= self.bins <= 128
+                          and (self.pc + self.vc) % 8 == 0)
+        self._t = {}
+        if self.supported:
+            self.refresh()
+
+    def _set(self, name: str, value: torch.Tensor) -> None:
+        if name in self._t:
+            self._t[name].copy_(value)
+        else:
+            self._t[name] = value.contiguous().clone()
+
+    def refresh(self) -> None:
+        ph, vh = self.model.policy_head, self.model.value_head
+        f = lambda x: x.detach().float()  # noqa: E731
+        self._set("conv_w", torch.cat([ph.conv1.weight.detach(), vh.conv1.weight.detach()], 0).contiguous(
+            memory_format=torch.channels_last))
+        s1, t1 = _fold_bn(ph.bn1)
+        s2, t2 = _fold_bn(vh.bn1)
+        self._set("bn1_scale", torch.cat([s1, s2]))
+        self._set("bn1_shift", torch.cat([t1, t2]))
+        self._set("wgl_t", f(ph.gpool_linear.weight).t())
+        sb, tb = _fold_bn(ph.bn2)
+        self._set("bn2_scale", sb)
+        self._set("bn2_shift", tb)
+        self._set("wout", torch.stack([f(ph.out_pos1.weight).view(-1), f(ph.out_pos2.weight).view(-1),
+                                       f(ph.out_mark.weight).view(-1)]))
+        self._set("wfc1_t", f(vh.fc1.weight).t())
+        self._set("bfc1", f(vh.fc1.bias))
+        self._set("wfc2_t", f(vh.fc2.weight).t())
+        self._set("bfc2", f(vh.fc2.bias))
+
+    def __call__(self, a: torch.Tensor, states: Optional[torch.Tensor] = None, *, priors_out=None, values_out=None,
+                 want_raw: bool = False):
+        """a: trunk output bf16 [n,C,6,6] channels-last.  With `states` (packed int64[n,4]) returns
+        (priors f32[n,220], values f32[n]); with want_raw returns (log_p1, log_p2, log_pmc, value_logits) fp32."""
+        import ctypes
+
+        from ._lib import check, i64, lib, ptr, stream_ptr
+
+        t = self._t
+        n = a.size(0)
+        dev = a.device
+        c = F.conv2d(a, t["conv_w"], None, 1, 0)
+        pv = torch.empty_like(c)
+        check(lib().lzb_bn_relu_bf16(ptr(c), ptr(None), ptr(t["bn1_scale"]), ptr(t["bn1_shift"]), i64(n * 36),
+                                     ctypes.c_int32(self.pc + self.vc), ptr(None), ptr(pv), stream_ptr(dev)))
+        log_heads = value_logits = None
+        if want_raw:
+            log_heads = torch.empty((n, 3, 36), dtype=torch.float32, device=dev)
+            value_logits = torch.empty((n, self.bins), dtype=torch.float32, device=dev)
+        if states is not None:
+            if priors_out is None:
+                priors_out = torch.empty((n, 220), dtype=torch.float32, device=dev)
+            if values_out is None:
+                values_out = torch.empty((n,), dtype=torch.float32, device=dev)
+        check(lib().lzb_heads_tail(ptr(pv), i64(n), ctypes.c_int32(self.pc), ctypes.c_int32(self.vc),
+                                   ctypes.c_int32(self.mlp), ctypes.c_int32(self.bins), ptr(t["wgl_t"]),
+                                   ptr(t["bn2_scale"]), ptr(t["bn2_shift"]), ptr(t["wout"]), ptr(t["wfc1_t"]),
+                                   ptr(t["bfc1"]), ptr(t["wfc2_t"]), ptr(t["bfc2"]),
+                                   ptr(states if states is not None else None),
+                                   ptr(priors_out if states is not None else None),
+                                   ptr(values_out if states is not None else None), ptr(log_heads), ptr(value_logits),
+                                   stream_ptr(dev)))
+        if want_raw:
+            return log_heads[:, 0], log_heads[:, 1], log_heads[:, 2], value_logits
+        return priors_out, values_out
+
+
 class InferenceNet:
     """bf16 / channels-last / CUDA-graph inference wrapper around a ChessNet on one GPU.
 
@@ -231,6 +310,9 @@ class InferenceNet:
         # fused epilogue kernels need bf16 and a channel count that is a multiple of 8
         self.fused = bool(fused) and dtype == torch.bfloat16 and self.model.stem_conv.out_channels % 8 == 0
         self.trunk = FusedTrunk(self.model) if self.fused else None
+        self.heads = FusedHeads(self.model) if self.fused else None
+        if self.heads is not None and not self.heads.supported:
+            self.heads = None
         self.flops_per_state = flops_per_state(self.model)
         self._graphs: Dict[int, Tuple[torch.cuda.CUDAGraph, torch.Tensor, Tuple[torch.Tensor, ...]]] = {}
 
@@ -254,17 +336,34 @@ class InferenceNet:
                     own[k].copy_(v.to(device=self.device, dtype=own[k].dtype))
         if self.trunk is not None:
             self.trunk.refresh()
+        if self.heads is not None:
+            self.heads.refresh()
 
     @torch.no_grad()
     def _forward_eager(self, x: torch.Tensor):
+        """-> fp32 (log_p1 [n,36], log_p2, log_pmc, value_logits [n,bins])."""
         if self.trunk is not None:
             with torch.cuda.device(self.device):
                 a = self.trunk(x)
+                if self.heads is not None:
+                    return self.heads(a, want_raw=True)
                 lp1, lp2, lpm = self.model.policy_head(a)
                 vl = self.model.value_head(a)
         else:
             lp1, lp2, lpm, vl = self.model(x)
         return lp1.float(), lp2.float(), lpm.float(), vl.float()
+
+    @torch.no_grad()
+    def forward_priors(self, x: torch.Tensor, states: torch.Tensor, priors_out=None, values_out=None):
+        """Network + head post-processing for the tree search: bf16 planes [n,11,6,6] + packed states int64[n,4] ->
+        (priors f32[n,220] = softmax over each state's legal actions, values f32[n] = bucket expectation)."""
+        with torch.cuda.device(self.device):
+            if self.trunk is not None and self.heads is not None:
+                return self.heads(self.trunk(x), states, priors_out=priors_out, values_out=values_out)
+            from .tree import heads_to_priors
+
+            lp1, lp2, lpm, vl = self._forward_eager(x)
+            return heads_to_priors(states, lp1, lp2, lpm, vl, priors_out=priors_out, values_out=values_out)
 
     def new_input(self, n: int) -> torch.Tensor:
         return torch.empty((n, 11, 6, 6), dtype=self.dtype, device=self.device,

@@ -73,8 +73,7 @@ class TreeMCTS:
         pri = self._root_pri if root else self._wave_pri
         val = self._root_val if root else self._wave_val
         encode_inputs(tree.pending_states, "bf16_nhwc", out=x)
-        lp1, lp2, lpm, vl = self.net._forward_eager(x)
-        heads_to_priors(tree.pending_states, lp1, lp2, lpm, vl, priors_out=pri, values_out=val)
+        self.net.forward_priors(x, tree.pending_states, priors_out=pri, values_out=val)
         tree.complete_pending(pri, val)
 
     def _root_step(self) -> None:

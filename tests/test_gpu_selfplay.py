@@ -249,3 +249,54 @@ def test_fused_trunk_matches_pytorch_forward():
     got = [o.clone() for o in fused.forward(x)]
     for u, v in zip(got, a):
         assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("dims", [(32, 16, 16, 32, 101), (128, 64, 64, 128, 101), (8, 4, 4, 8, 101)])
+def test_fused_heads_kernel_vs_fp32_pytorch_heads(dims):
+    """heads_tail_kernel (fp32 math on the bf16 trunk output) vs the PyTorch head modules evaluated in fp32 on the
+    same trunk activations, and forward_priors == heads_to_priors(raw heads)."""
+    from liuzhou_b200 import native
+    from liuzhou_b200.net import ChessNet, InferenceNet
+    from liuzhou_b200.tree import heads_to_priors
+
+    trunk, pc, vc, mlp, bins = dims
+    torch.manual_seed(11)
+    model = ChessNet(trunk_channels=trunk, num_blocks=1, policy_channels=pc, value_channels=vc,
+                     value_mlp_channels=mlp, value_bucket_bins=bins)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0.0, 0.3)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0.0, 0.2)
+    net = InferenceNet(model, DEV)
+    if (pc + vc) % 8 != 0:
+        assert net.heads is None
+        return
+    assert net.heads is not None
+    st = _playout_states(3, 5, every=2)
+    n = st["board"].shape[0]
+    packed = native.pack_states(to_torch(st, DEV))
+    from liuzhou_b200.tree import encode_inputs
+
+    x = encode_inputs(packed, "bf16_nhwc")
+    a = net.trunk(x)
+    raw = net.heads(a, want_raw=True)
+    # fp32 reference heads on the same (bf16) trunk activations
+    ref_model = model.to(DEV).float().eval()
+    with torch.no_grad():
+        af = a.float()
+        r1, r2, r3 = ref_model.policy_head(af)
+        rv = ref_model.value_head(af)
+    # weights were rounded to bf16 for the 1x1 conv and its output is stored in bf16: ~1e-2 abs on log-probs
+    for u, v in zip(raw, (r1, r2, r3, rv)):
+        torch.testing.assert_close(u, v, rtol=3e-2, atol=3e-2)
+    pri, val = net.forward_priors(x, packed)
+    pri2, val2 = heads_to_priors(packed, *raw)
+    torch.testing.assert_close(pri, pri2, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(val, val2, rtol=1e-5, atol=1e-6)
+    legal = np.zeros((n, 220), bool)
+    for i in range(n):
+        legal[i, oracle.legal_actions(st, i)[0]] = True
+    p = _np(pri)
+    assert (p[~legal] == 0).all() and np.allclose(p[legal.any(1)].sum(1), 1.0, atol=1e-5)
