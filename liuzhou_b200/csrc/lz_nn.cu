@@ -84,13 +84,17 @@ extern "C" int lzb_bn_relu_bf16(const void* u, const void* v, const float* scale
 // the two heads' 1x1 convolutions run as ONE cuDNN conv; everything after it -- global pooling (mean / max /
 // std), gpool_linear, bn2 + relu, the three 1-channel output convs, log-softmax, the value MLP, the bucket
 // expectation and the masked softmax over the legal actions of the packed state -- is this one kernel
-// (~30 PyTorch launches in the unfused path).  One 128-thread block per state (grid-strided), fp32 math,
-// weights pre-transposed so that consecutive threads read consecutive addresses.
+// (~30 PyTorch launches in the unfused path).
+//
+// A 128-thread block processes a TILE of kTile = 16 states per iteration so that every weight element
+// (pre-transposed: consecutive threads read consecutive addresses) is loaded once per tile and used for 16
+// states from registers; pooled features / hidden activations live in shared memory (fp32 math throughout).
 // ------------------------------------------------------------------------------------------------------
 namespace lzb {
 namespace {
 
 constexpr int kHeadsThreads = 128;
+constexpr int kTile = 16;
 constexpr int kMaxHeadCh = 64;     // policy_channels, value_channels <= 64
 constexpr int kMaxMlp = 128;       // value_mlp_channels <= 128
 constexpr int kMaxBins = 128;      // value buckets <= 128
@@ -103,63 +107,102 @@ struct HeadsParams {
 
 __global__ void __launch_bounds__(kHeadsThreads)
 heads_tail_kernel(HeadsParams P) {
-    __shared__ float act[36][2 * kMaxHeadCh + 1];
-    __shared__ float pooled_p[3 * kMaxHeadCh], pooled_v[3 * kMaxHeadCh];
-    __shared__ float g[kMaxHeadCh], hid[kMaxMlp], vlog[kMaxBins];
-    __shared__ float logit3[3][36], lp[3][36];
+    __shared__ float pooled_p[kTile][3 * kMaxHeadCh];
+    __shared__ float pooled_v[kTile][3 * kMaxHeadCh];
+    __shared__ float g[kTile][kMaxHeadCh];
+    __shared__ float hid[kTile][kMaxMlp];
+    // value logits reuse pooled_v's storage (dead after the fc1 phase; a __syncthreads separates the two uses)
+    float (*vlog)[kMaxBins + 1] = reinterpret_cast<float (*)[kMaxBins + 1]>(&pooled_v[0][0]);
+    static_assert(sizeof(float) * kTile * (kMaxBins + 1) <= sizeof(float) * kTile * 3 * kMaxHeadCh, "vlog alias too big");
+    __shared__ float lp[kTile][3][36];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int pc = P.pc, vc = P.vc, c2 = pc + vc;
-    for (int64_t i = blockIdx.x; i < P.n; i += gridDim.x) {
+    const int pc = P.pc, vc = P.vc, c2 = pc + vc, mlp = P.mlp, bins = P.bins;
+    const int64_t num_tiles = (P.n + kTile - 1) / kTile;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t base = tile * kTile;
+        const int ns = (int)min((int64_t)kTile, P.n - base);
         __syncthreads();
-        // 1. load + global pooling (mean / max / std, biased variance + 1e-6)   neural_network.py:68-81
-        if (t < c2) {
-            const __nv_bfloat16* src = P.pv + i * 36 * c2 + t;
-            float s = 0.0f, mx = -INFINITY;
-#pragma unroll 4
-            for (int cell = 0; cell < 36; ++cell) {
-                const float x = __bfloat162float(src[cell * c2]);
-                act[cell][t] = x; s += x; mx = fmaxf(mx, x);
-            }
-            const float mean = s * (1.0f / 36.0f);
+        // 1. global pooling per (state, channel): mean / max / std (biased variance + 1e-6)  neural_network.py:68-81
+        for (int idx = t; idx < ns * c2; idx += kHeadsThreads) {
+            const int s = idx / c2, c = idx - s * c2;
+            const __nv_bfloat16* src = P.pv + (base + s) * 36 * c2 + c;
+            float x[36], sum = 0.0f, mx = -INFINITY;
+#pragma unroll
+            for (int cell = 0; cell < 36; ++cell) { x[cell] = __bfloat162float(src[cell * c2]); sum += x[cell]; mx = fmaxf(mx, x[cell]); }
+            const float mean = sum * (1.0f / 36.0f);
             float var = 0.0f;
-#pragma unroll 4
-            for (int cell = 0; cell < 36; ++cell) { const float d = act[cell][t] - mean; var += d * d; }
+#pragma unroll
+            for (int cell = 0; cell < 36; ++cell) { const float d = x[cell] - mean; var = fmaf(d, d, var); }
             const float sd = sqrtf(var * (1.0f / 36.0f) + 1e-6f);
-            if (t < pc) { pooled_p[t] = mean; pooled_p[pc + t] = mx; pooled_p[2 * pc + t] = sd; }
-            else { const int c = t - pc; pooled_v[c] = mean; pooled_v[vc + c] = mx; pooled_v[2 * vc + c] = sd; }
+            if (c < pc) { pooled_p[s][c] = mean; pooled_p[s][pc + c] = mx; pooled_p[s][2 * pc + c] = sd; }
+            else { const int cv = c - pc; pooled_v[s][cv] = mean; pooled_v[s][vc + cv] = mx; pooled_v[s][2 * vc + cv] = sd; }
         }
         __syncthreads();
-        // 2. policy gpool_linear (no bias) and value fc1 + relu
-        if (t < pc) {
-            float a = 0.0f;
-            for (int k = 0; k < 3 * pc; ++k) a = fmaf(P.wgl_t[k * pc + t], pooled_p[k], a);
-            g[t] = a;
-        }
-        for (int m = t; m < P.mlp; m += kHeadsThreads) {
-            float a = P.bfc1[m];
-            for (int k = 0; k < 3 * vc; ++k) a = fmaf(P.wfc1_t[k * P.mlp + m], pooled_v[k], a);
-            hid[m] = fmaxf(a, 0.0f);
-        }
-        __syncthreads();
-        // 3. p2 = relu(bn2(p + g)); three 1-channel output convs; value fc2
-        if (t < 108) {
-            const int cell = t % 36, h = t / 36;
-            float a = 0.0f;
-            for (int ch = 0; ch < pc; ++ch) {
-                const float p2 = fmaxf(fmaf(P.bn2_scale[ch], act[cell][ch] + g[ch], P.bn2_shift[ch]), 0.0f);
-                a = fmaf(P.wout[h * pc + ch], p2, a);
+        // 2a. g = gpool_linear(pooled_p) (no bias): thread -> (output j, half of the tile)
+        {
+            const int halves = kHeadsThreads / kMaxHeadCh;            // 2
+            const int j = t % kMaxHeadCh, hsel = t / kMaxHeadCh;
+            if (j < pc) {
+                float acc[kTile / 2];
+#pragma unroll
+                for (int q = 0; q < kTile / 2; ++q) acc[q] = 0.0f;
+                for (int k = 0; k < 3 * pc; ++k) {
+                    const float w = __ldg(P.wgl_t + k * pc + j);
+#pragma unroll
+                    for (int q = 0; q < kTile / 2; ++q) acc[q] = fmaf(w, pooled_p[hsel * (kTile / halves) + q][k], acc[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < kTile / 2; ++q) g[hsel * (kTile / halves) + q][j] = acc[q];
             }
-            logit3[h][cell] = a;
         }
-        for (int k = t; k < P.bins; k += kHeadsThreads) {
-            float a = P.bfc2[k];
-            for (int m = 0; m < P.mlp; ++m) a = fmaf(P.wfc2_t[m * P.bins + k], hid[m], a);
-            vlog[k] = a;
+        // 2b. hid = relu(fc1(pooled_v)): thread -> output m
+        for (int m = t; m < mlp; m += kHeadsThreads) {
+            float acc[kTile];
+            const float b = __ldg(P.bfc1 + m);
+#pragma unroll
+            for (int q = 0; q < kTile; ++q) acc[q] = b;
+            for (int k = 0; k < 3 * vc; ++k) {
+                const float w = __ldg(P.wfc1_t + k * mlp + m);
+#pragma unroll
+                for (int q = 0; q < kTile; ++q) acc[q] = fmaf(w, pooled_v[q][k], acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < kTile; ++q) hid[q][m] = fmaxf(acc[q], 0.0f);
         }
         __syncthreads();
-        // 4. log-softmax of each policy head over the 36 cells (warps 0..2); value expectation (warp 3)
-        if (warp < 3) {
-            const float x0 = logit3[warp][lane], x1 = lane < 4 ? logit3[warp][32 + lane] : -INFINITY;
+        // 3a. value logits = fc2(hid): thread -> bucket k
+        for (int k = t; k < bins; k += kHeadsThreads) {
+            float acc[kTile];
+            const float b = __ldg(P.bfc2 + k);
+#pragma unroll
+            for (int q = 0; q < kTile; ++q) acc[q] = b;
+            for (int m = 0; m < mlp; ++m) {
+                const float w = __ldg(P.wfc2_t + m * bins + k);
+#pragma unroll
+                for (int q = 0; q < kTile; ++q) acc[q] = fmaf(w, hid[q][m], acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < kTile; ++q) vlog[q][k] = acc[q];
+        }
+        // 3b. policy: p2 = relu(bn2(p + g)); three 1-channel output convs -> raw logits (stored in lp)
+        for (int idx = t; idx < ns * 36; idx += kHeadsThreads) {
+            const int s = idx / 36, cell = idx - s * 36;
+            const __nv_bfloat16* src = P.pv + ((base + s) * 36 + cell) * c2;
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+            for (int ch = 0; ch < pc; ++ch) {
+                const float p2 = fmaxf(fmaf(__ldg(P.bn2_scale + ch), __bfloat162float(src[ch]) + g[s][ch],
+                                            __ldg(P.bn2_shift + ch)), 0.0f);
+                a0 = fmaf(__ldg(P.wout + ch), p2, a0);
+                a1 = fmaf(__ldg(P.wout + pc + ch), p2, a1);
+                a2 = fmaf(__ldg(P.wout + 2 * pc + ch), p2, a2);
+            }
+            lp[s][0][cell] = a0; lp[s][1][cell] = a1; lp[s][2][cell] = a2;
+        }
+        __syncthreads();
+        // 4. log-softmax of each (state, head) row over the 36 cells; value expectation per state
+        for (int row = warp; row < ns * 3; row += kHeadsThreads / 32) {
+            const int s = row / 3, h = row - s * 3;
+            const float x0 = lp[s][h][lane], x1 = lane < 4 ? lp[s][h][32 + lane] : -INFINITY;
             float mx = fmaxf(x0, x1);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
@@ -167,69 +210,74 @@ heads_tail_kernel(HeadsParams P) {
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) se += __shfl_xor_sync(0xffffffffu, se, off);
             const float lse = mx + logf(se);
-            lp[warp][lane] = x0 - lse;
-            if (lane < 4) lp[warp][32 + lane] = x1 - lse;
+            lp[s][h][lane] = x0 - lse;
+            if (lane < 4) lp[s][h][32 + lane] = x1 - lse;
             if (P.log_heads) {
-                P.log_heads[(i * 3 + warp) * 36 + lane] = x0 - lse;
-                if (lane < 4) P.log_heads[(i * 3 + warp) * 36 + 32 + lane] = x1 - lse;
+                float* dst = P.log_heads + ((base + s) * 3 + h) * 36;
+                dst[lane] = x0 - lse;
+                if (lane < 4) dst[32 + lane] = x1 - lse;
             }
-        } else {
+        }
+        for (int s = warp; s < ns; s += kHeadsThreads / 32) {
             float mx = -INFINITY;
-            for (int k = lane; k < P.bins; k += 32) mx = fmaxf(mx, vlog[k]);
+            for (int k = lane; k < bins; k += 32) mx = fmaxf(mx, vlog[s][k]);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
             float se = 0.0f, sc = 0.0f;
-            const float step = P.bins > 1 ? 2.0f / (float)(P.bins - 1) : 0.0f;
-            for (int k = lane; k < P.bins; k += 32) {
-                const float e = expf(vlog[k] - mx);
+            const float step = bins > 1 ? 2.0f / (float)(bins - 1) : 0.0f;
+            for (int k = lane; k < bins; k += 32) {
+                const float e = expf(vlog[s][k] - mx);
                 se += e; sc += e * (-1.0f + step * (float)k);
-                if (P.value_logits) P.value_logits[i * P.bins + k] = vlog[k];
+                if (P.value_logits) P.value_logits[(base + s) * bins + k] = vlog[s][k];
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 se += __shfl_xor_sync(0xffffffffu, se, off);
                 sc += __shfl_xor_sync(0xffffffffu, sc, off);
             }
-            if (lane == 0 && P.values) P.values[i] = sc / se;
+            if (lane == 0 && P.values) P.values[base + s] = sc / se;
         }
         __syncthreads();
-        // 5. priors = softmax of the combined logits over the legal actions of the packed state (warp 0)
-        if (warp == 0 && P.priors && P.states) {
-            lz::State<int> s;
-            lz::Packed pk;
-            const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(P.states + 4 * i);
-            const ulonglong2 a = sp[0], b = sp[1];
-            pk.w[0] = a.x; pk.w[1] = a.y; pk.w[2] = b.x; pk.w[3] = b.y;
-            lz::unpack(pk, s);
-            lz::Legal L;
-            lz::legal_actions<int, true>(s, L, true);
-            float logit[7], mx = -INFINITY;
+        // 5. priors = softmax of the combined logits over the legal actions of the packed state (warp per state)
+        if (P.priors && P.states) {
+            for (int s = warp; s < ns; s += kHeadsThreads / 32) {
+                const int64_t i = base + s;
+                lz::State<int> st;
+                lz::Packed pk;
+                const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(P.states + 4 * i);
+                const ulonglong2 a = sp[0], b = sp[1];
+                pk.w[0] = a.x; pk.w[1] = a.y; pk.w[2] = b.x; pk.w[3] = b.y;
+                lz::unpack(pk, st);
+                lz::Legal L;
+                lz::legal_actions<int, true>(st, L, true);
+                float logit[7], mx = -INFINITY;
 #pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const int ac = lane + 32 * k;
-                float v = -INFINITY;
-                if (ac < lz::kActionDim && lz::legal_test(L, ac)) {
-                    if (ac < 36) v = lp[0][ac];
-                    else if (ac < 180) {
-                        const int from = (ac - 36) >> 2, d = (ac - 36) & 3;
-                        v = lp[1][from] + lp[0][from + (d == 0 ? -6 : d == 1 ? 6 : d == 2 ? -1 : 1)];
-                    } else if (ac < 216) v = lp[2][ac - 180];
-                    else v = 0.0f;
+                for (int k = 0; k < 7; ++k) {
+                    const int ac = lane + 32 * k;
+                    float v = -INFINITY;
+                    if (ac < lz::kActionDim && lz::legal_test(L, ac)) {
+                        if (ac < 36) v = lp[s][0][ac];
+                        else if (ac < 180) {
+                            const int from = (ac - 36) >> 2, d = (ac - 36) & 3;
+                            v = lp[s][1][from] + lp[s][0][from + (d == 0 ? -6 : d == 1 ? 6 : d == 2 ? -1 : 1)];
+                        } else if (ac < 216) v = lp[s][2][ac - 180];
+                        else v = 0.0f;
+                    }
+                    logit[k] = v; mx = fmaxf(mx, v);
                 }
-                logit[k] = v; mx = fmaxf(mx, v);
-            }
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-            const bool ok = mx > -INFINITY && mx < INFINITY;
-            float e[7], sum = 0.0f;
+                for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+                const bool ok = mx > -INFINITY && mx < INFINITY;
+                float e[7], sum = 0.0f;
 #pragma unroll
-            for (int k = 0; k < 7; ++k) { e[k] = (ok && logit[k] > -INFINITY) ? expf(logit[k] - mx) : 0.0f; sum += e[k]; }
+                for (int k = 0; k < 7; ++k) { e[k] = (ok && logit[k] > -INFINITY) ? expf(logit[k] - mx) : 0.0f; sum += e[k]; }
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
 #pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const int ac = lane + 32 * k;
-                if (ac < lz::kActionDim) P.priors[i * lz::kActionDim + ac] = ok ? e[k] / sum : 0.0f;
+                for (int k = 0; k < 7; ++k) {
+                    const int ac = lane + 32 * k;
+                    if (ac < lz::kActionDim) P.priors[i * lz::kActionDim + ac] = ok ? e[k] / sum : 0.0f;
+                }
             }
         }
     }
@@ -254,7 +302,8 @@ extern "C" int lzb_heads_tail(const void* pv, int64_t n, int32_t pc, int32_t vc,
     P.wgl_t = wgl_t; P.bn2_scale = bn2_scale; P.bn2_shift = bn2_shift; P.wout = wout; P.wfc1_t = wfc1_t; P.bfc1 = bfc1;
     P.wfc2_t = wfc2_t; P.bfc2 = bfc2; P.states = states; P.priors = priors; P.values = values;
     P.log_heads = log_heads; P.value_logits = value_logits;
-    int64_t blocks = n < (int64_t)lzb::kNumSMs * 8 ? n : (int64_t)lzb::kNumSMs * 8;
+    const int64_t tiles = (n + lzb::kTile - 1) / lzb::kTile;
+    const int64_t blocks = tiles < (int64_t)lzb::kNumSMs * 4 ? tiles : (int64_t)lzb::kNumSMs * 4;
     lzb::heads_tail_kernel<<<(int)blocks, lzb::kHeadsThreads, 0, (cudaStream_t)stream>>>(P);
     return lzb::check_launch("heads_tail_kernel");
 }

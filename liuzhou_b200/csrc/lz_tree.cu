@@ -218,7 +218,16 @@ tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, con
                 double prior_sum = 0.0;
                 int fc = 0;
                 if (lane == 0) {
-                    for (int i = 0; i < n; ++i) prior_sum = __dadd_rn(prior_sum, (double)s_pri[w][legal_kth(L, i)]);
+                    // one ascending pass over the legal set: placement cells, then (from, dir) moves, then selections
+                    for (uint64_t m = L.place; m; m &= m - 1) prior_sum = __dadd_rn(prior_sum, (double)s_pri[w][ctz64(m)]);
+                    for (uint64_t u = L.mv[0] | L.mv[1] | L.mv[2] | L.mv[3]; u; u &= u - 1) {
+                        const int from = ctz64(u);
+#pragma unroll
+                        for (int d = 0; d < 4; ++d)
+                            if ((L.mv[d] >> from) & 1) prior_sum = __dadd_rn(prior_sum, (double)s_pri[w][36 + from * 4 + d]);
+                    }
+                    for (uint64_t m = L.sel; m; m &= m - 1) prior_sum = __dadd_rn(prior_sum, (double)s_pri[w][180 + ctz64(m)]);
+                    if (L.process) prior_sum = __dadd_rn(prior_sum, (double)s_pri[w][216]);
                     fc = atomicAdd(&A.counters[0], n);
                     if ((int64_t)fc + n > A.capacity) { A.counters[1] = 1; fc = -1; }
                     else atomicAdd(&A.counters[2], 1);
@@ -227,9 +236,10 @@ tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, con
                 fc = __shfl_sync(0xffffffffu, fc, 0);
                 if (fc >= 0) {
                     const bool uniform = !(prior_sum > 0.0) || isinf(prior_sum);      // :919
-                    for (int a = lane; a < 224; a += 32) {
-                        if (a < kActionDim && legal_test(L, a)) {
-                            const int c = fc + legal_rank(L, a);
+                    for (int i = lane; i < n; i += 32) {      // child i <-> i-th legal action in ascending index order
+                        {
+                            const int a = legal_kth(L, i);
+                            const int c = fc + i;
                             State<int> cs = s;
                             apply_index(cs, a);
                             store_packed(A.state, c, pack(cs));

@@ -159,29 +159,72 @@ def _fold_bn(bn: nn.BatchNorm2d):
 
 
 class FusedTrunk:
-    """The ChessNet trunk with cuDNN convolutions (bf16 channels-last implicit GEMMs on the tensor cores) and OUR fused
-    epilogue kernel (csrc/lz_nn.cu) instead of PyTorch's separate BatchNorm / ReLU / add passes: one elementwise pass
-    per convolution.  Same math as ChessNet.forward up to `trunk_act` (src/neural_network.py:250-254)."""
+    """The ChessNet trunk (src/neural_network.py:250-254) with
+      * cuDNN convolutions (bf16 channels-last implicit GEMMs on the tensor cores, cutlass sm100 kernels),
+      * BatchNorm folded INTO the convolution wherever a BN directly follows a conv (stem_bn -> stem_conv, bn2 ->
+        conv1 of each block) and applied by cuDNN's fused conv + bias + ReLU epilogue (free on B200: same time as
+        the bare conv),
+      * OUR fused kernel (csrc/lz_nn.cu) for the one pass cuDNN cannot absorb: residual add + next block's
+        BatchNorm + ReLU with both the sum and the activation written.
+    Per residual block: 2 tensor-core kernels + 1 HBM-bound pass (PyTorch eager: 2 + ~7)."""
 
     def __init__(self, model: "ChessNet"):
         self.model = model
+        self._t = {}
+        self.use_cudnn_fused = True
         self.refresh()
+        self._probe()
 
-    def refresh(self) -> None:
-        """(Re)fold the BatchNorm statistics; in place when already folded, so captured CUDA graphs stay valid."""
-        m = self.model
-        new = {"stem": _fold_bn(m.stem_bn), "bn1": [_fold_bn(b.bn1) for b in m.blocks],
-               "bn2": [_fold_bn(b.bn2) for b in m.blocks], "trunk": _fold_bn(m.trunk_bn)}
-        if not hasattr(self, "stem"):
-            self.stem, self.bn1, self.bn2, self.trunk = new["stem"], new["bn1"], new["bn2"], new["trunk"]
-            return
-        for dst, src in [(self.stem, new["stem"]), (self.trunk, new["trunk"])] + list(zip(self.bn1, new["bn1"])) + \
-                list(zip(self.bn2, new["bn2"])):
-            dst[0].copy_(src[0])
-            dst[1].copy_(src[1])
+    def _set(self, name: str, value: torch.Tensor) -> None:
+        if name in self._t:
+            self._t[name].copy_(value)          # in place: captured CUDA graphs stay valid
+        else:
+            self._t[name] = value.clone()
 
     @staticmethod
-    def _bn_relu(u, v, scale_shift, want_sum: bool):
+    def _fold_into_conv(conv: nn.Conv2d, bn: nn.BatchNorm2d):
+        scale, shift = _fold_bn(bn)
+        w = (conv.weight.detach().float() * scale.view(-1, 1, 1, 1)).to(conv.weight.dtype)
+        return w.contiguous(memory_format=torch.channels_last), shift.to(conv.weight.dtype).contiguous()
+
+    def refresh(self) -> None:
+        m = self.model
+        w, b = self._fold_into_conv(m.stem_conv, m.stem_bn)
+        self._set("stem_w", w)
+        self._set("stem_b", b)
+        for i, blk in enumerate(m.blocks):
+            w, b = self._fold_into_conv(blk.conv1, blk.bn2)
+            self._set(f"w1_{i}", w)
+            self._set(f"b1_{i}", b)
+            s, t = _fold_bn(blk.bn1)
+            self._set(f"s1_{i}", s)
+            self._set(f"t1_{i}", t)
+            s, t = _fold_bn(blk.bn2)
+            self._set(f"s2_{i}", s)
+            self._set(f"t2_{i}", t)
+        s, t = _fold_bn(m.stem_bn)
+        self._set("stem_s", s)
+        self._set("stem_t", t)
+        s, t = _fold_bn(m.trunk_bn)
+        self._set("trunk_s", s)
+        self._set("trunk_t", t)
+
+    def _probe(self) -> None:
+        """cuDNN's fused conv+bias+ReLU needs engine support for this shape / dtype; fall back to conv + our
+        bn_relu pass if it is not available."""
+        m = self.model
+        try:
+            dev = m.stem_conv.weight.device
+            x = torch.zeros((2, m.stem_conv.in_channels, 6, 6), dtype=m.stem_conv.weight.dtype, device=dev).contiguous(
+                memory_format=torch.channels_last)
+            y = torch.cudnn_convolution_relu(x, self._t["stem_w"], self._t["stem_b"], [1, 1], [1, 1], [1, 1], 1)
+            if len(m.blocks):
+                torch.cudnn_convolution_relu(y, self._t["w1_0"], self._t["b1_0"], [1, 1], [1, 1], [1, 1], 1)
+        except Exception:
+            self.use_cudnn_fused = False
+
+    @staticmethod
+    def _bn_relu(u, v, scale, shift, want_sum: bool):
         import ctypes
 
         from ._lib import check, i64, lib, ptr, stream_ptr
@@ -189,26 +232,30 @@ class FusedTrunk:
         n, c, h, w = u.shape
         out_act = torch.empty_like(u)
         out_sum = torch.empty_like(u) if (v is not None and want_sum) else None
-        check(lib().lzb_bn_relu_bf16(ptr(u), ptr(v), ptr(scale_shift[0]), ptr(scale_shift[1]), i64(n * h * w),
-                                     ctypes.c_int32(c), ptr(out_sum), ptr(out_act), stream_ptr(u.device)))
+        check(lib().lzb_bn_relu_bf16(ptr(u), ptr(v), ptr(scale), ptr(shift), i64(n * h * w), ctypes.c_int32(c),
+                                     ptr(out_sum), ptr(out_act), stream_ptr(u.device)))
         return out_sum, out_act
 
+    def _conv_bn_relu(self, x, conv: nn.Conv2d, wname: str, bname: str, sname: str, tname: str):
+        t = self._t
+        if self.use_cudnn_fused:
+            return torch.cudnn_convolution_relu(x, t[wname], t[bname], [1, 1], [1, 1], [1, 1], 1)
+        c = F.conv2d(x, conv.weight, None, 1, 1)
+        return self._bn_relu(c, None, t[sname], t[tname], False)[1]
+
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
-        m = self.model
+        m, t = self.model, self._t
         nb = len(m.blocks)
-        c = F.conv2d(x, m.stem_conv.weight, None, 1, 1)
-        _, xr = self._bn_relu(c, None, self.stem, False)                   # x0 = relu(stem_bn(conv))
+        xr = self._conv_bn_relu(x, m.stem_conv, "stem_w", "stem_b", "stem_s", "stem_t")     # x0 = relu(stem_bn(conv))
         if nb == 0:
-            _, a = self._bn_relu(xr, None, self.trunk, False)
-            return a
-        _, a = self._bn_relu(xr, None, self.bn1[0], False)                  # a0 = relu(bn1_0(x0))
+            return self._bn_relu(xr, None, t["trunk_s"], t["trunk_t"], False)[1]
+        _, a = self._bn_relu(xr, None, t["s1_0"], t["t1_0"], False)                           # a0 = relu(bn1_0(x0))
         for i, blk in enumerate(m.blocks):
-            h = F.conv2d(a, blk.conv1.weight, None, 1, 1)
-            _, h = self._bn_relu(h, None, self.bn2[i], False)
+            h = self._conv_bn_relu(a, blk.conv1, f"w1_{i}", f"b1_{i}", f"s2_{i}", f"t2_{i}")  # relu(bn2(conv1(a)))
             c2 = F.conv2d(h, blk.conv2.weight, None, 1, 1)
             last = i == nb - 1
-            nxt = self.trunk if last else self.bn1[i + 1]
-            xr, a = self._bn_relu(xr, c2, nxt, not last)                   # x' = x + conv2 ; a = relu(bn_next(x'))
+            sn, tn = ("trunk_s", "trunk_t") if last else (f"s1_{i + 1}", f"t1_{i + 1}")
+            xr, a = self._bn_relu(xr, c2, t[sn], t[tn], not last)       # x' = x + conv2 ; a = relu(bn_next(x'))
         return a
 
 
