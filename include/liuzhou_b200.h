@@ -259,6 +259,20 @@ LZB_API int lzb_heads_to_priors(const uint64_t *states, int64_t n, const float *
 LZB_API int lzb_bn_relu_bf16(const void *u, const void *v, const float *scale, const float *shift, int64_t rows,
                              int32_t channels, void *out_sum, void *out_act, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (a17) The network's convolutions as hand-written tcgen05 implicit GEMMs with the pre-activation-ResNet
+ * epilogue fused in (replaces F.conv2d + eval BatchNorm + ReLU + residual add of PreActResBlock,
+ * src/neural_network.py:83-96,250-254; csrc/lz_conv.cu).
+ *   x bf16 [n,6,6,cin] channels-last, w bf16 [taps][128][cin] (tap = ky*3+kx; BatchNorm that follows the conv
+ *   folded into w / bias), cin = 128, taps = 9 (3x3, pad 1) or 1 (1x1), n a multiple of 64.
+ *   v    = conv(x, w) + bias (+ residual) ; optional ReLU (relu1)
+ *   out1 = bf16(v)                                   (may be NULL)
+ *   out2 = bf16(relu(scale * float(out1) + shift))   (may be NULL)
+ * ---------------------------------------------------------------------------------------------- */
+LZB_API int lzb_conv_bf16(const void *x, const void *w, int64_t n, int32_t cin, int32_t taps, const float *bias,
+                          const void *residual, const float *scale, const float *shift, int32_t relu1, void *out1,
+                          void *out2, void *stream);
+
 /* Fused network heads: everything of PolicyHead / ValueHead after their 1x1 convolutions
  * (src/neural_network.py:98-151: global pooling, gpool_linear, bn2 + relu, the three output convs,
  * log-softmax, value MLP) + bucket expectation (:201-210) + masked softmax over the legal actions of the

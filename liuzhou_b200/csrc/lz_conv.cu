@@ -1,0 +1,418 @@
+// lz_conv.cu -- the network's 3x3 / 1x1 convolutions as hand-written tcgen05 implicit GEMMs (sm_100a) with the
+// whole pre-activation-ResNet epilogue fused in (replaces cuDNN conv + our bn_relu pass; src/neural_network.py:83-96).
+//
+// One launch = one convolution layer over the whole wave batch:
+//     D[rows = n*36, 128] = sum over taps (ky,kx) of  A_tap[rows, Cin] * W_tap[Cin, 128]        (bf16 x bf16 -> fp32)
+// * A operand: activations bf16 NHWC [n,6,6,Cin]; each tap's shifted, zero-padded [128 rows x 64 ch] tile is fetched
+//   by ONE TMA im2col load (cp.async.bulk.tensor.4d.im2col, SWIZZLE_128B) -- the hardware does the halo.
+// * B operand: the layer's weights [tap][cout][cin] stay RESIDENT in shared memory for the whole launch: a CTA
+//   pair (cta_group::2, cluster of 2) splits Cout, so each CTA holds 9 x 64 x 128 bf16 = 147 KB.  Only A streams.
+// * MMA: tcgen05.mma.cta_group::2.kind::f16, M = 256 (128 rows per CTA), N = 128, K = 16; fp32 accumulators in
+//   TMEM, double buffered (2 x 128 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// * Persistent: 74 clusters walk the 256-row tiles round-robin.  Warp roles per CTA: warp 0 = TMA producer,
+//   warp 1 = TMEM allocator + (leader CTA) MMA issuer, warps 2-5 = epilogue (one TMEM lane quarter each).
+// * Epilogue (per row, fp32): v = acc + bias[c] (+ residual[row][c]); optional ReLU; out1 = bf16(v);
+//   out2 = bf16(relu(scale[c] * float(out1) + shift[c])).  With BatchNorm folded this covers
+//       conv1 of a block : out1 = relu(bn2(conv1(a)))                      (bias, relu)
+//       conv2 of a block : out1 = x + conv2(h) ; out2 = relu(bn1_next(out1)) (residual, both outputs)
+//       stem             : out1 = relu(stem_bn(conv(x))) ; out2 = relu(bn1_0(out1)).
+// Algorithmic work per launch (C = 128): 2 * rows * 128 * 1152 FLOP; bytes: rows * 256 B read (x9 from L2) +
+// rows * 256 B per output (+ residual).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "lz_common.cuh"
+
+namespace lzb {
+namespace {
+
+constexpr int kConvThreads = 192;
+constexpr int kStages = 4;                       // A-operand pipeline depth
+constexpr int kTileM = 128;                      // rows per CTA (256 per CTA pair)
+constexpr int kCout = 128;
+constexpr int kKC = 64;                          // channels per pipeline stage: 64 bf16 = one 128 B swizzle row
+constexpr uint32_t kStageBytes = kTileM * kKC * 2;        // 16 KB
+constexpr uint32_t kWSlotBytes = (kCout / 2) * kKC * 2;   // 8 KB: 64 couts (this CTA's half) x 64 cin
+constexpr int kAccStages = 2;
+constexpr uint32_t kTmemCols = kAccStages * kCout;        // 256 fp32 columns
+constexpr uint64_t kWatchdogCycles = 4000000000ull;       // ~2 s: a lost arrival traps instead of hanging the GPU
+
+struct ConvParams {
+    const float* bias;                 // [128] or null
+    const __nv_bfloat16* residual;     // [rows,128] or null
+    const float* scale;                // [128] (out2) or null
+    const float* shift;
+    __nv_bfloat16* out1;               // [rows,128] or null
+    __nv_bfloat16* out2;               // [rows,128] or null
+    int64_t rows;                      // n * 36, multiple of 256
+    int relu1;
+    int images;                        // n
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) break;
+        if ((uint64_t)(clock64() - t0) > kWatchdogCycles) {
+            printf("lz_conv: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+                   (int)threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+constexpr uint64_t kL2Default = 0x1000000000000000ull;   // the default L2 cache-hint descriptor
+
+// im2col load of [128 pixels x 64 ch] starting at base pixel (w, h, n) with filter offsets (off_w, off_h); the
+// transaction bytes are signalled on `bar` (an address in the LEADER CTA's window: cta_group::2).
+__device__ __forceinline__ void tma_im2col_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h, int n,
+                                               uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h),
+          "l"(kL2Default)
+        : "memory");
+}
+__device__ __forceinline__ void tma_tile2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(kL2Default)
+        : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, N = 128, M = 256 (cta_group::2).
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kCout >> 3) << 17) | ((256u >> 4) << 24);
+
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kInstrDesc), "r"(accumulate)
+        : "memory");
+}
+// all MMAs issued so far by this thread -> one arrival on `bar` in every CTA of `mask` when they complete
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------------
+// TAPS = 9 (3x3, pad 1) or 1 (1x1); KCH = Cin / 64.
+template <int TAPS, int KCH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvParams P) {
+    constexpr int kWSlots = TAPS * KCH;
+    constexpr uint32_t kWBytes = kWSlots * kWSlotBytes;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B atoms need 1024 B alignment
+    const uint32_t w_smem = base;
+    const uint32_t a_smem = base + kWBytes;
+    const uint32_t bar0 = a_smem + kStages * kStageBytes;
+    // barriers (8 B each)
+    const uint32_t full_bar = bar0;                         // [kStages]    leader: A stage landed (both CTAs' bytes)
+    const uint32_t empty_bar = full_bar + 8 * kStages;      // [kStages]    both  : MMAs that read the stage are done
+    const uint32_t w_bar = empty_bar + 8 * kStages;         // [TAPS]       leader: weights of a tap landed (both CTAs)
+    const uint32_t tfull_bar = w_bar + 8 * TAPS;            // [kAccStages] both  : accumulator complete
+    const uint32_t tempty_bar = tfull_bar + 8 * kAccStages; // [kAccStages] leader: epilogue of both CTAs drained it
+    const uint32_t tmem_slot = tempty_bar + 8 * kAccStages; // u32
+    const uint32_t vec_smem = tmem_slot + 16;               // bias | scale | shift : 3 x 128 f32
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    float* vec = reinterpret_cast<float*>(gen + (vec_smem - base));
+    volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int64_t pair_tiles = P.rows / (2 * kTileM);
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmW);
+        for (int i = 0; i < kStages; ++i) { mbar_init(full_bar + 8 * i, 1); mbar_init(empty_bar + 8 * i, 1); }
+        for (int i = 0; i < TAPS; ++i) mbar_init(w_bar + 8 * i, 1);
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {   // TMEM: one warp per CTA, the pair allocates together
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < kCout; i += kConvThreads) {
+        vec[i] = P.bias ? P.bias[i] : 0.0f;
+        vec[kCout + i] = P.scale ? P.scale[i] : 1.0f;
+        vec[2 * kCout + i] = P.shift ? P.shift[i] : 0.0f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();            // the peer's barriers exist before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_p;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one lane; both CTAs) =====================
+        if (lane == 0) {
+            const uint32_t full_leader = mapa_rank(full_bar, 0), w_leader = mapa_rank(w_bar, 0);
+            uint32_t stage = 0, phase = 0;
+            bool first = true;
+            for (int64_t pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
+                const int64_t p0 = (2 * pt + rank) * kTileM;
+                const int n0 = (int)(p0 / 36), rem = (int)(p0 - (int64_t)n0 * 36), h0 = rem / 6, w0 = rem - h0 * 6;
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    if (first) {   // this tap's weights: our half of Cout, all of Cin -> resident slots
+                        if (leader) mbar_arrive_expect_tx(w_bar + 8 * tap, 2 * KCH * kWSlotBytes);
+                        for (int kc = 0; kc < KCH; ++kc)
+                            tma_tile2d_2sm(w_smem + (tap * KCH + kc) * kWSlotBytes, &tmW, w_leader + 8 * tap, kc * kKC,
+                                           tap * kCout + (int)rank * (kCout / 2));
+                    }
+                    const int off_w = TAPS == 9 ? tap % 3 : 0, off_h = TAPS == 9 ? tap / 3 : 0;
+                    const int lo = TAPS == 9 ? -1 : 0;
+                    for (int kc = 0; kc < KCH; ++kc) {
+                        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                        if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * kStageBytes);
+                        tma_im2col_2sm(a_smem + stage * kStageBytes, &tmA, full_leader + 8 * stage, kc * kKC, w0 + lo, h0 + lo,
+                                       n0, (uint16_t)off_w, (uint16_t)off_h);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                first = false;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA, one lane) =====================
+        if (leader && lane == 0) {
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            bool first = true;
+            for (int64_t pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
+                mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kCout;
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    if (first) { mbar_wait(w_bar + 8 * tap, 0); tc_fence_after(); }
+                    for (int kc = 0; kc < KCH; ++kc) {
+                        mbar_wait(full_bar + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint64_t adesc = umma_desc_sw128(a_smem + stage * kStageBytes);
+                        const uint64_t bdesc = umma_desc_sw128(w_smem + (tap * KCH + kc) * kWSlotBytes);
+#pragma unroll
+                        for (int k = 0; k < kKC / 16; ++k)   // +32 B per K = 16 step inside the 128 B swizzle row
+                            umma_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, (uint32_t)((tap | kc | k) != 0));
+                        umma_commit_2sm(empty_bar + 8 * stage, 3);          // frees the stage in both CTAs
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                umma_commit_2sm(tfull_bar + 8 * acc, 3);                    // accumulator ready in both CTAs
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+                first = false;
+            }
+        }
+    } else {
+        // ===================== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====================
+        const int q = warp & 3;
+        const uint32_t tempty_leader = mapa_rank(tempty_bar, 0);
+        uint32_t acc = 0, acc_phase = 0;
+        const float* bias_s = vec;
+        const float* scale_s = vec + kCout;
+        const float* shift_s = vec + 2 * kCout;
+        for (int64_t pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
+            const int64_t row = (2 * pt + rank) * kTileM + q * 32 + lane;
+            mbar_wait(tfull_bar + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kCout;
+            const uint4* res = P.residual ? reinterpret_cast<const uint4*>(P.residual + row * kCout) : nullptr;
+            uint4* o1 = P.out1 ? reinterpret_cast<uint4*>(P.out1 + row * kCout) : nullptr;
+            uint4* o2 = P.out2 ? reinterpret_cast<uint4*>(P.out2 + row * kCout) : nullptr;
+#pragma unroll 1
+            for (int j = 0; j < kCout / 32; ++j) {
+                uint32_t v[32];
+                tmem_ld32(taddr + j * 32, v);
+                uint4 r[4];
+                if (res) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) r[i] = __ldg(res + j * 4 + i);
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {      // 8 channels per 16-byte store
+                    uint32_t p1[4], p2[4];
+                    const uint32_t* rw = reinterpret_cast<const uint32_t*>(&r[i]);
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const int c = j * 32 + i * 8 + h * 2;
+                        float f0 = __uint_as_float(v[i * 8 + h * 2]) + bias_s[c];
+                        float f1 = __uint_as_float(v[i * 8 + h * 2 + 1]) + bias_s[c + 1];
+                        if (res) {
+                            const float2 rr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[h]));
+                            f0 += rr.x; f1 += rr.y;
+                        }
+                        if (P.relu1) { f0 = fmaxf(f0, 0.0f); f1 = fmaxf(f1, 0.0f); }
+                        const __nv_bfloat162 hb = __floats2bfloat162_rn(f0, f1);
+                        p1[h] = *reinterpret_cast<const uint32_t*>(&hb);
+                        const float2 s = __bfloat1622float2(hb);       // BN reads the stored (bf16) value
+                        p2[h] = pack_bf16(fmaxf(fmaf(scale_s[c], s.x, shift_s[c]), 0.0f),
+                                          fmaxf(fmaf(scale_s[c + 1], s.y, shift_s[c + 1]), 0.0f));
+                    }
+                    if (o1) o1[j * 4 + i] = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+                    if (o2) o2[j * 4 + i] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * acc);
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    // teardown: every MMA / TMEM read of the pair is done before the pair frees TMEM
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool driver_entry(const char* name, void** fn) {
+    cudaDriverEntryPointQueryResult st;
+    return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess &&
+           *fn != nullptr;
+}
+
+template <int TAPS, int KCH>
+int launch_conv(const void* x, const void* w, const ConvParams& P, cudaStream_t stream) {
+    static EncodeTiledFn encode_tiled = nullptr;
+    static EncodeIm2colFn encode_im2col = nullptr;
+    if (!encode_tiled && !driver_entry("cuTensorMapEncodeTiled", reinterpret_cast<void**>(&encode_tiled))) {
+        set_error("lzb_conv: cuTensorMapEncodeTiled unavailable");
+        return LZB_ERR_CUDA;
+    }
+    if (!encode_im2col && !driver_entry("cuTensorMapEncodeIm2col", reinterpret_cast<void**>(&encode_im2col))) {
+        set_error("lzb_conv: cuTensorMapEncodeIm2col unavailable");
+        return LZB_ERR_CUDA;
+    }
+    constexpr int cin = KCH * kKC;
+    alignas(64) CUtensorMap tmA, tmW;
+    {   // activations: (C, W, H, N) bf16, NHWC
+        const cuuint64_t dim[4] = {(cuuint64_t)cin, 6, 6, (cuuint64_t)P.images};
+        const cuuint64_t stride[3] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * 2 * 6, (cuuint64_t)cin * 2 * 36};
+        const int pad = TAPS == 9 ? 1 : 0;
+        const int lower[2] = {-pad, -pad}, upper[2] = {-pad, -pad};   // pad - (filter - 1) * dilation = -pad for 3x3 / 1x1
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult rc = encode_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dim, stride, lower,
+                                          upper, kKC, kTileM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) { set_error("lzb_conv: cuTensorMapEncodeIm2col failed (%d)", (int)rc); return LZB_ERR_CUDA; }
+    }
+    {   // weights: [tap * 128 + cout][cin] bf16
+        const cuuint64_t dim[2] = {(cuuint64_t)cin, (cuuint64_t)TAPS * kCout};
+        const cuuint64_t stride[1] = {(cuuint64_t)cin * 2};
+        const cuuint32_t box[2] = {kKC, kCout / 2};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult rc = encode_tiled(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dim, stride, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (rc != CUDA_SUCCESS) { set_error("lzb_conv: cuTensorMapEncodeTiled failed (%d)", (int)rc); return LZB_ERR_CUDA; }
+    }
+    constexpr size_t smem = 1024 + (size_t)TAPS * KCH * kWSlotBytes + (size_t)kStages * kStageBytes +
+                            8 * (2 * kStages + TAPS + 2 * kAccStages) + 16 + 3 * kCout * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(conv_tc_kernel<TAPS, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            set_error("lzb_conv: cannot raise dynamic shared memory to %zu", smem);
+            return LZB_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int64_t pair_tiles = P.rows / (2 * kTileM);
+    const int clusters = (int)(pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2);
+    conv_tc_kernel<TAPS, KCH><<<2 * clusters, kConvThreads, smem, stream>>>(tmA, tmW, P);
+    return check_launch("conv_tc_kernel");
+}
+
+}  // namespace
+}  // namespace lzb
+
+// x bf16 [n,6,6,cin] (NHWC), w bf16 [taps][128][cin], outputs bf16 [n,6,6,128]; n must be a multiple of 64.
+extern "C" int lzb_conv_bf16(const void* x, const void* w, int64_t n, int32_t cin, int32_t taps, const float* bias,
+                             const void* residual, const float* scale, const float* shift, int32_t relu1, void* out1,
+                             void* out2, void* stream) {
+    LZB_REQUIRE(n > 0 && n % 64 == 0, "batch must be a positive multiple of 64 (256-row tile pairs)");
+    LZB_REQUIRE(cin == 128 && (taps == 9 || taps == 1), "supported: cin = 128, taps = 9 (3x3, pad 1) or 1 (1x1)");
+    LZB_REQUIRE(x && w && (out1 || out2), "null pointer");
+    LZB_REQUIRE(!out2 || (scale && shift), "out2 needs scale / shift");
+    LZB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(residual) |
+                  reinterpret_cast<uintptr_t>(out1) | reinterpret_cast<uintptr_t>(out2)) & 15) == 0, "pointers must be 16-byte aligned");
+    lzb::ConvParams P;
+    P.bias = bias; P.residual = reinterpret_cast<const __nv_bfloat16*>(residual); P.scale = scale; P.shift = shift;
+    P.out1 = reinterpret_cast<__nv_bfloat16*>(out1); P.out2 = reinterpret_cast<__nv_bfloat16*>(out2);
+    P.rows = n * 36; P.relu1 = relu1; P.images = (int)n;
+    if (taps == 9) return lzb::launch_conv<9, 2>(x, w, P, (cudaStream_t)stream);
+    return lzb::launch_conv<1, 2>(x, w, P, (cudaStream_t)stream);
+}

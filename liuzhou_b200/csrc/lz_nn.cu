@@ -81,20 +81,22 @@ extern "C" int lzb_bn_relu_bf16(const void* u, const void* v, const float* scale
 // ------------------------------------------------------------------------------------------------------
 // Fused network heads (src/neural_network.py:98-151 + project_policy_logits_fast + bucket_logits_to_scalar).
 // Input: pv = relu(bn(conv1x1([policy.conv1 ; value.conv1])(trunk)))  bf16 [n, 36, pc + vc] channels-last, i.e.
-// the two heads' 1x1 convolutions run as ONE cuDNN conv; everything after it -- global pooling (mean / max /
+// the two heads' 1x1 convolutions run as ONE convolution; everything after it -- global pooling (mean / max /
 // std), gpool_linear, bn2 + relu, the three 1-channel output convs, log-softmax, the value MLP, the bucket
 // expectation and the masked softmax over the legal actions of the packed state -- is this one kernel
 // (~30 PyTorch launches in the unfused path).
 //
-// A 128-thread block processes a TILE of kTile = 16 states per iteration so that every weight element
-// (pre-transposed: consecutive threads read consecutive addresses) is loaded once per tile and used for 16
-// states from registers; pooled features / hidden activations live in shared memory (fp32 math throughout).
+// A 256-thread block processes a TILE of kTile = 8 states: 512 blocks for a 4,096-leaf wave, all resident at once
+// (3-4 per SM), so the latency of the small dense layers is hidden by other blocks.  Pooled features / hidden
+// activations live in shared memory TRANSPOSED ([feature][state]) so that one broadcast 8/16-byte shared load
+// feeds 2/4 FMAs; weights are pre-transposed (consecutive threads read consecutive addresses) and every weight
+// element is used for kTile/groups states from a register.  fp32 math throughout.
 // ------------------------------------------------------------------------------------------------------
 namespace lzb {
 namespace {
 
-constexpr int kHeadsThreads = 128;
-constexpr int kTile = 16;
+constexpr int kHeadsThreads = 256;
+constexpr int kTile = 8;
 constexpr int kMaxHeadCh = 64;     // policy_channels, value_channels <= 64
 constexpr int kMaxMlp = 128;       // value_mlp_channels <= 128
 constexpr int kMaxBins = 128;      // value buckets <= 128
@@ -105,98 +107,144 @@ struct HeadsParams {
     const uint64_t* states; float *priors, *values, *log_heads, *value_logits;
 };
 
-__global__ void __launch_bounds__(kHeadsThreads)
+__global__ void __launch_bounds__(kHeadsThreads, 4)
 heads_tail_kernel(HeadsParams P) {
-    __shared__ float pooled_p[kTile][3 * kMaxHeadCh];
-    __shared__ float pooled_v[kTile][3 * kMaxHeadCh];
-    __shared__ float g[kTile][kMaxHeadCh];
-    __shared__ float hid[kTile][kMaxMlp];
-    // value logits reuse pooled_v's storage (dead after the fc1 phase; a __syncthreads separates the two uses)
-    float (*vlog)[kMaxBins + 1] = reinterpret_cast<float (*)[kMaxBins + 1]>(&pooled_v[0][0]);
-    static_assert(sizeof(float) * kTile * (kMaxBins + 1) <= sizeof(float) * kTile * 3 * kMaxHeadCh, "vlog alias too big");
+    __shared__ __align__(16) float poolT_p[3 * kMaxHeadCh][kTile];   // [feature][state]
+    __shared__ __align__(16) float poolT_v[3 * kMaxHeadCh][kTile];
+    __shared__ __align__(16) float g[kTile][kMaxHeadCh];
+    __shared__ __align__(16) float hidT[kMaxMlp][kTile];
+    __shared__ float vlog[kTile][kMaxBins + 1];
     __shared__ float lp[kTile][3][36];
+    __shared__ __align__(16) float wpol[5][kMaxHeadCh];               // bn2 scale, bn2 shift, out_pos1, out_pos2, out_mark
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int pc = P.pc, vc = P.vc, c2 = pc + vc, mlp = P.mlp, bins = P.bins;
+    for (int i = t; i < pc; i += kHeadsThreads) {
+        wpol[0][i] = P.bn2_scale[i]; wpol[1][i] = P.bn2_shift[i];
+        wpol[2][i] = P.wout[i]; wpol[3][i] = P.wout[pc + i]; wpol[4][i] = P.wout[2 * pc + i];
+    }
     const int64_t num_tiles = (P.n + kTile - 1) / kTile;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int64_t base = tile * kTile;
         const int ns = (int)min((int64_t)kTile, P.n - base);
         __syncthreads();
         // 1. global pooling per (state, channel): mean / max / std (biased variance + 1e-6)  neural_network.py:68-81
-        for (int idx = t; idx < ns * c2; idx += kHeadsThreads) {
-            const int s = idx / c2, c = idx - s * c2;
-            const __nv_bfloat16* src = P.pv + (base + s) * 36 * c2 + c;
-            float x[36], sum = 0.0f, mx = -INFINITY;
+        //    thread -> (state, channel): 36 independent loads in flight, consecutive channels across the warp
+        for (int idx = t; idx < kTile * c2; idx += kHeadsThreads) {
+            const int s = idx / c2, ch = idx - s * c2;
+            float r0 = 0.0f, r1 = 0.0f, r2 = 1e-3f;
+            if (s < ns) {
+                const __nv_bfloat16* src = P.pv + (base + s) * 36 * c2 + ch;
+                float x[36], sum = 0.0f, mx = -INFINITY;
 #pragma unroll
-            for (int cell = 0; cell < 36; ++cell) { x[cell] = __bfloat162float(src[cell * c2]); sum += x[cell]; mx = fmaxf(mx, x[cell]); }
-            const float mean = sum * (1.0f / 36.0f);
-            float var = 0.0f;
+                for (int cell = 0; cell < 36; ++cell) { x[cell] = __bfloat162float(src[cell * c2]); sum += x[cell]; mx = fmaxf(mx, x[cell]); }
+                const float mean = sum * (1.0f / 36.0f);
+                float var = 0.0f;
 #pragma unroll
-            for (int cell = 0; cell < 36; ++cell) { const float d = x[cell] - mean; var = fmaf(d, d, var); }
-            const float sd = sqrtf(var * (1.0f / 36.0f) + 1e-6f);
-            if (c < pc) { pooled_p[s][c] = mean; pooled_p[s][pc + c] = mx; pooled_p[s][2 * pc + c] = sd; }
-            else { const int cv = c - pc; pooled_v[s][cv] = mean; pooled_v[s][vc + cv] = mx; pooled_v[s][2 * vc + cv] = sd; }
+                for (int cell = 0; cell < 36; ++cell) { const float d = x[cell] - mean; var = fmaf(d, d, var); }
+                r0 = mean; r1 = mx; r2 = sqrtf(var * (1.0f / 36.0f) + 1e-6f);
+            }
+            if (ch < pc) { poolT_p[ch][s] = r0; poolT_p[pc + ch][s] = r1; poolT_p[2 * pc + ch][s] = r2; }
+            else { const int cv = ch - pc; poolT_v[cv][s] = r0; poolT_v[vc + cv][s] = r1; poolT_v[2 * vc + cv][s] = r2; }
         }
         __syncthreads();
-        // 2a. g = gpool_linear(pooled_p) (no bias): thread -> (output j, half of the tile)
+        // 2a. g = gpool_linear(pooled_p) (no bias): thread -> (output j, group of 2 states)
         {
-            const int halves = kHeadsThreads / kMaxHeadCh;            // 2
-            const int j = t % kMaxHeadCh, hsel = t / kMaxHeadCh;
+            const int j = t & (kMaxHeadCh - 1), sg = t >> 6;          // 4 groups x 2 states
             if (j < pc) {
-                float acc[kTile / 2];
-#pragma unroll
-                for (int q = 0; q < kTile / 2; ++q) acc[q] = 0.0f;
+                float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll 4
                 for (int k = 0; k < 3 * pc; ++k) {
                     const float w = __ldg(P.wgl_t + k * pc + j);
-#pragma unroll
-                    for (int q = 0; q < kTile / 2; ++q) acc[q] = fmaf(w, pooled_p[hsel * (kTile / halves) + q][k], acc[q]);
+                    const float2 p = *reinterpret_cast<const float2*>(&poolT_p[k][2 * sg]);
+                    a0 = fmaf(w, p.x, a0); a1 = fmaf(w, p.y, a1);
                 }
-#pragma unroll
-                for (int q = 0; q < kTile / 2; ++q) g[hsel * (kTile / halves) + q][j] = acc[q];
+                g[2 * sg][j] = a0; g[2 * sg + 1][j] = a1;
             }
         }
-        // 2b. hid = relu(fc1(pooled_v)): thread -> output m
-        for (int m = t; m < mlp; m += kHeadsThreads) {
-            float acc[kTile];
-            const float b = __ldg(P.bfc1 + m);
-#pragma unroll
-            for (int q = 0; q < kTile; ++q) acc[q] = b;
-            for (int k = 0; k < 3 * vc; ++k) {
-                const float w = __ldg(P.wfc1_t + k * mlp + m);
-#pragma unroll
-                for (int q = 0; q < kTile; ++q) acc[q] = fmaf(w, pooled_v[q][k], acc[q]);
+        // 2b. hid = relu(fc1(pooled_v)): thread -> (output m, group of 4 states)
+        {
+            const int m = t & (kMaxMlp - 1), sg = t >> 7;             // 2 groups x 4 states
+            if (m < mlp) {
+                const float b = __ldg(P.bfc1 + m);
+                float a0 = b, a1 = b, a2 = b, a3 = b;
+#pragma unroll 4
+                for (int k = 0; k < 3 * vc; ++k) {
+                    const float w = __ldg(P.wfc1_t + k * mlp + m);
+                    const float4 p = *reinterpret_cast<const float4*>(&poolT_v[k][4 * sg]);
+                    a0 = fmaf(w, p.x, a0); a1 = fmaf(w, p.y, a1); a2 = fmaf(w, p.z, a2); a3 = fmaf(w, p.w, a3);
+                }
+                *reinterpret_cast<float4*>(&hidT[m][4 * sg]) =
+                    make_float4(fmaxf(a0, 0.0f), fmaxf(a1, 0.0f), fmaxf(a2, 0.0f), fmaxf(a3, 0.0f));
             }
-#pragma unroll
-            for (int q = 0; q < kTile; ++q) hid[q][m] = fmaxf(acc[q], 0.0f);
         }
         __syncthreads();
-        // 3a. value logits = fc2(hid): thread -> bucket k
-        for (int k = t; k < bins; k += kHeadsThreads) {
-            float acc[kTile];
-            const float b = __ldg(P.bfc2 + k);
-#pragma unroll
-            for (int q = 0; q < kTile; ++q) acc[q] = b;
-            for (int m = 0; m < mlp; ++m) {
-                const float w = __ldg(P.wfc2_t + m * bins + k);
-#pragma unroll
-                for (int q = 0; q < kTile; ++q) acc[q] = fmaf(w, hid[q][m], acc[q]);
+        // 3a. value logits = fc2(hid): thread -> (bucket k, group of 4 states)
+        {
+            const int k = t & (kMaxBins - 1), sg = t >> 7;
+            if (k < bins) {
+                const float b = __ldg(P.bfc2 + k);
+                float a0 = b, a1 = b, a2 = b, a3 = b;
+#pragma unroll 4
+                for (int m = 0; m < mlp; ++m) {
+                    const float w = __ldg(P.wfc2_t + m * bins + k);
+                    const float4 h = *reinterpret_cast<const float4*>(&hidT[m][4 * sg]);
+                    a0 = fmaf(w, h.x, a0); a1 = fmaf(w, h.y, a1); a2 = fmaf(w, h.z, a2); a3 = fmaf(w, h.w, a3);
+                }
+                vlog[4 * sg][k] = a0; vlog[4 * sg + 1][k] = a1; vlog[4 * sg + 2][k] = a2; vlog[4 * sg + 3][k] = a3;
             }
-#pragma unroll
-            for (int q = 0; q < kTile; ++q) vlog[q][k] = acc[q];
         }
-        // 3b. policy: p2 = relu(bn2(p + g)); three 1-channel output convs -> raw logits (stored in lp)
-        for (int idx = t; idx < ns * 36; idx += kHeadsThreads) {
-            const int s = idx / 36, cell = idx - s * 36;
-            const __nv_bfloat16* src = P.pv + ((base + s) * 36 + cell) * c2;
-            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-            for (int ch = 0; ch < pc; ++ch) {
-                const float p2 = fmaxf(fmaf(__ldg(P.bn2_scale + ch), __bfloat162float(src[ch]) + g[s][ch],
-                                            __ldg(P.bn2_shift + ch)), 0.0f);
-                a0 = fmaf(__ldg(P.wout + ch), p2, a0);
-                a1 = fmaf(__ldg(P.wout + pc + ch), p2, a1);
-                a2 = fmaf(__ldg(P.wout + 2 * pc + ch), p2, a2);
+        // 3b. policy: p2 = relu(bn2(p + g)); three 1-channel output convs -> raw logits (stored in lp).
+        //     thread -> (state, cell, channel half); the two halves sit in adjacent lanes and meet by shuffle
+        {
+            const int half_ch = (pc + 1) >> 1;
+            const bool vec = (pc % 16 == 0) && (c2 % 8 == 0);
+            for (int idx0 = 0; idx0 < ns * 72; idx0 += kHeadsThreads) {
+                const int idx = idx0 + t;
+                const bool valid = idx < ns * 72;
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+                int s = 0, cell = 0;
+                if (valid) {
+                    const int item = idx >> 1, half = idx & 1;
+                    s = item / 36; cell = item - s * 36;
+                    const int ch0 = half * half_ch, ch1 = half ? pc : half_ch;
+                    const __nv_bfloat16* src = P.pv + ((base + s) * 36 + cell) * c2;
+                    if (vec) {
+                        for (int ch = ch0; ch < ch1; ch += 8) {
+                            const uint4 raw = *reinterpret_cast<const uint4*>(src + ch);
+                            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+                            float x[8];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h2[q]); x[2 * q] = f.x; x[2 * q + 1] = f.y; }
+#pragma unroll
+                            for (int q4 = 0; q4 < 2; ++q4) {
+                                const float4 gg = *reinterpret_cast<const float4*>(&g[s][ch + 4 * q4]);
+                                const float4 sc = *reinterpret_cast<const float4*>(&wpol[0][ch + 4 * q4]);
+                                const float4 sh = *reinterpret_cast<const float4*>(&wpol[1][ch + 4 * q4]);
+                                const float4 w0 = *reinterpret_cast<const float4*>(&wpol[2][ch + 4 * q4]);
+                                const float4 w1 = *reinterpret_cast<const float4*>(&wpol[3][ch + 4 * q4]);
+                                const float4 w2 = *reinterpret_cast<const float4*>(&wpol[4][ch + 4 * q4]);
+                                const float gv[4] = {gg.x, gg.y, gg.z, gg.w}, scv[4] = {sc.x, sc.y, sc.z, sc.w};
+                                const float shv[4] = {sh.x, sh.y, sh.z, sh.w}, w0v[4] = {w0.x, w0.y, w0.z, w0.w};
+                                const float w1v[4] = {w1.x, w1.y, w1.z, w1.w}, w2v[4] = {w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float p2 = fmaxf(fmaf(scv[q], x[4 * q4 + q] + gv[q], shv[q]), 0.0f);
+                                    a0 = fmaf(w0v[q], p2, a0); a1 = fmaf(w1v[q], p2, a1); a2 = fmaf(w2v[q], p2, a2);
+                                }
+                            }
+                        }
+                    } else {
+                        for (int ch = ch0; ch < ch1; ++ch) {
+                            const float p2 = fmaxf(fmaf(wpol[0][ch], __bfloat162float(src[ch]) + g[s][ch], wpol[1][ch]), 0.0f);
+                            a0 = fmaf(wpol[2][ch], p2, a0); a1 = fmaf(wpol[3][ch], p2, a1); a2 = fmaf(wpol[4][ch], p2, a2);
+                        }
+                    }
+                }
+                // channel order of the sum: low half first, then the high half (fixed -> run-to-run deterministic)
+                const float b0 = __shfl_xor_sync(0xffffffffu, a0, 1), b1 = __shfl_xor_sync(0xffffffffu, a1, 1);
+                const float b2 = __shfl_xor_sync(0xffffffffu, a2, 1);
+                if (valid && !(idx & 1)) { lp[s][0][cell] = a0 + b0; lp[s][1][cell] = a1 + b1; lp[s][2][cell] = a2 + b2; }
             }
-            lp[s][0][cell] = a0; lp[s][1][cell] = a1; lp[s][2][cell] = a2;
         }
         __syncthreads();
         // 4. log-softmax of each (state, head) row over the 36 cells; value expectation per state
@@ -297,6 +345,7 @@ extern "C" int lzb_heads_tail(const void* pv, int64_t n, int32_t pc, int32_t vc,
     if (n == 0) return LZB_OK;
     LZB_REQUIRE(pv && wgl_t && bn2_scale && bn2_shift && wout && wfc1_t && bfc1 && wfc2_t && bfc2, "null weights");
     LZB_REQUIRE(!priors || states, "priors need the packed states");
+    LZB_REQUIRE((pc + vc) % 2 == 0 && (reinterpret_cast<uintptr_t>(pv) & 15) == 0, "pv: even channel count, 16-byte aligned");
     lzb::HeadsParams P;
     P.pv = reinterpret_cast<const __nv_bfloat16*>(pv); P.n = n; P.pc = pc; P.vc = vc; P.mlp = mlp; P.bins = bins;
     P.wgl_t = wgl_t; P.bn2_scale = bn2_scale; P.bn2_shift = bn2_shift; P.wout = wout; P.wfc1_t = wfc1_t; P.bfc1 = bfc1;

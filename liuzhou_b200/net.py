@@ -158,6 +158,40 @@ def _fold_bn(bn: nn.BatchNorm2d):
     return scale, shift
 
 
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """Conv2d weight [cout, cin, kh, kw] -> the layout csrc/lz_conv.cu keeps resident in shared memory:
+    bf16 [kh*kw][cout][cin] (tap-major, K-major rows)."""
+    cout, cin, kh, kw = w.shape
+    return w.detach().permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).to(torch.bfloat16).contiguous()
+
+
+def conv_bf16(x: torch.Tensor, w_packed: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
+              residual: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
+              shift: Optional[torch.Tensor] = None, relu1: bool = False, want_out1: bool = True,
+              want_out2: bool = False, out1: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None):
+    """Our tcgen05 implicit-GEMM convolution with the fused residual / BatchNorm / ReLU epilogue (lzb_conv_bf16).
+    x bf16 [n,128,6,6] channels-last with n % 64 == 0; returns (out1, out2) (None where not requested)."""
+    import ctypes
+
+    from ._lib import check, i64, lib, ptr, require_cuda, stream_ptr
+
+    require_cuda(x, "x")
+    n, cin, h, w = x.shape
+    if (h, w) != (6, 6) or x.dtype != torch.bfloat16 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise RuntimeError("conv_bf16: x must be bf16 [n,C,6,6] in channels_last memory format")
+    taps = int(w_packed.size(0))
+    dev = x.device
+    with torch.cuda.device(dev):
+        if want_out1 and out1 is None:
+            out1 = torch.empty((n, 128, 6, 6), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+        if want_out2 and out2 is None:
+            out2 = torch.empty((n, 128, 6, 6), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+        check(lib().lzb_conv_bf16(ptr(x), ptr(w_packed), i64(n), ctypes.c_int32(cin), ctypes.c_int32(taps), ptr(bias),
+                                  ptr(residual), ptr(scale), ptr(shift), ctypes.c_int32(1 if relu1 else 0),
+                                  ptr(out1 if want_out1 else None), ptr(out2 if want_out2 else None), stream_ptr(dev)))
+    return (out1 if want_out1 else None), (out2 if want_out2 else None)
+
+
 class FusedTrunk:
     """The ChessNet trunk (src/neural_network.py:250-254) with
       * cuDNN convolutions (bf16 channels-last implicit GEMMs on the tensor cores, cutlass sm100 kernels),

@@ -1,0 +1,69 @@
+"""Our tcgen05 implicit-GEMM convolution (csrc/lz_conv.cu) vs a plain PyTorch fp32 reference of the same op on the
+same bf16 inputs.  Tolerance: the kernel accumulates bf16 x bf16 products in fp32 and rounds the outputs to bf16
+once, so |err| <= 2^-8 relative to the output magnitude (+ summation-order noise): rtol = atol = 2e-2."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _mk(n, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn((n, 128, 6, 6), generator=g).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn((128, 128, 3, 3), generator=g) * 0.03).to(DEV).to(torch.bfloat16)
+    bias = (torch.randn((128,), generator=g) * 0.5).to(DEV)
+    res = torch.randn((n, 128, 6, 6), generator=g).to(DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    scale = (torch.rand((128,), generator=g) + 0.5).to(DEV)
+    shift = (torch.randn((128,), generator=g) * 0.3).to(DEV)
+    return x, w, bias, res, scale, shift
+
+
+@pytest.mark.parametrize("n", [64, 192, 4096])
+def test_conv3x3_bias_relu(n):
+    from liuzhou_b200.net import conv_bf16, pack_conv_weight
+
+    x, w, bias, _, _, _ = _mk(n, 1)
+    y, _ = conv_bf16(x, pack_conv_weight(w), bias=bias, relu1=True)
+    ref = torch.relu(F.conv2d(x.float(), w.float(), bias, 1, 1))
+    torch.testing.assert_close(y.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("n", [64, 1024])
+def test_conv3x3_residual_dual_output(n):
+    from liuzhou_b200.net import conv_bf16, pack_conv_weight
+
+    x, w, _, res, scale, shift = _mk(n, 2)
+    s, a = conv_bf16(x, pack_conv_weight(w), residual=res, scale=scale, shift=shift, want_out2=True)
+    ref_s = F.conv2d(x.float(), w.float(), None, 1, 1) + res.float()
+    torch.testing.assert_close(s.float(), ref_s, rtol=2e-2, atol=2e-2)
+    ref_a = torch.relu(s.float() * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))     # BN reads the stored sum
+    torch.testing.assert_close(a.float(), ref_a, rtol=1e-2, atol=1e-2)
+    only_a = conv_bf16(x, pack_conv_weight(w), residual=res, scale=scale, shift=shift, want_out1=False, want_out2=True)[1]
+    assert torch.equal(only_a, a)
+
+
+def test_conv1x1():
+    from liuzhou_b200.net import conv_bf16, pack_conv_weight
+
+    x, w, bias, _, _, _ = _mk(128, 3)
+    w1 = w[:, :, 1:2, 1:2].contiguous()
+    y, _ = conv_bf16(x, pack_conv_weight(w1), bias=bias, relu1=True)
+    ref = torch.relu(F.conv2d(x.float(), w1.float(), bias))
+    torch.testing.assert_close(y.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+def test_conv_is_deterministic_and_border_exact():
+    """Zero padding: an all-ones input with all-ones centre-tap-only weights reproduces the input exactly; with
+    all nine taps = 1/128 the output counts the in-board neighbours (4 / 6 / 9)."""
+    from liuzhou_b200.net import conv_bf16, pack_conv_weight
+
+    n = 64
+    x = torch.ones((n, 128, 6, 6), device=DEV, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = torch.full((128, 128, 3, 3), 1.0 / 128.0, device=DEV, dtype=torch.bfloat16)
+    y, _ = conv_bf16(x, pack_conv_weight(w))
+    cnt = F.conv2d(torch.ones((1, 1, 6, 6), device=DEV), torch.ones((1, 1, 3, 3), device=DEV), None, 1, 1)
+    assert torch.equal(y.float(), cnt.expand(n, 128, 6, 6))
+    y2, _ = conv_bf16(x, pack_conv_weight(w))
+    assert torch.equal(y, y2)
