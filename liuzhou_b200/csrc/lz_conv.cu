@@ -19,6 +19,7 @@
 // Algorithmic work per launch (C = 128): 2 * rows * 128 * 1152 FLOP; bytes: rows * 256 B read (x9 from L2) +
 // rows * 256 B per output (+ residual).
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 #include "lz_common.cuh"
@@ -47,6 +48,8 @@ struct ConvParams {
     int64_t rows;                      // n * 36, multiple of 256
     int relu1;
     int images;                        // n
+    unsigned long long* trace;         // debug: clock64 stamps of cluster 0's leader (MMA thread: [0,4096), producer: [4096,8192))
+    int debug;                         // bit 0: epilogue drains TMEM but skips global loads / stores (timing experiments)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -74,19 +77,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
-    while (true) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) break;
+    while (!mbar_try_wait(bar, parity)) {
         if ((uint64_t)(clock64() - t0) > kWatchdogCycles) {
             printf("lz_conv: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
                    (int)threadIdx.x, bar, parity);
             __trap();
         }
     }
+}
+// fast path: one try_wait (which itself suspends the thread for a while); the watchdog only starts after it fails
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -174,7 +183,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tfull_bar = w_bar + 8 * TAPS;            // [kAccStages] both  : accumulator complete
     const uint32_t tempty_bar = tfull_bar + 8 * kAccStages; // [kAccStages] leader: epilogue of both CTAs drained it
     const uint32_t tmem_slot = tempty_bar + 8 * kAccStages; // u32
-    const uint32_t vec_smem = tmem_slot + 16;               // bias | scale | shift : 3 x 128 f32
+    const uint32_t vec_smem = (tmem_slot + 16 + 15u) & ~15u; // bias | scale | shift : 3 x 128 f32
+    const uint32_t stage_smem = vec_smem + 3 * kCout * 4;   // epilogue staging: 4 warps x 32 rows x 128 B (fp32)
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     float* vec = reinterpret_cast<float*>(gen + (vec_smem - base));
     volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
@@ -214,6 +224,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t full_leader = mapa_rank(full_bar, 0), w_leader = mapa_rank(w_bar, 0);
             uint32_t stage = 0, phase = 0;
             bool first = true;
+            int tr_p = 0;
             for (int64_t pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
                 const int64_t p0 = (2 * pt + rank) * kTileM;
                 const int n0 = (int)(p0 / 36), rem = (int)(p0 - (int64_t)n0 * 36), h0 = rem / 6, w0 = rem - h0 * 6;
@@ -228,6 +239,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int lo = TAPS == 9 ? -1 : 0;
                     for (int kc = 0; kc < KCH; ++kc) {
                         mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                        if (P.trace && blockIdx.x == 0 && tr_p < 4096) P.trace[4096 + tr_p++] = clock64();
+                        if (P.debug & 2) {   // timing experiment: no loads, the MMAs chew on whatever is in smem
+                            if (leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_bar + 8 * stage) : "memory");
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * kStageBytes);
                         tma_im2col_2sm(a_smem + stage * kStageBytes, &tmA, full_leader + 8 * stage, kc * kKC, w0 + lo, h0 + lo,
                                        n0, (uint16_t)off_w, (uint16_t)off_h);
@@ -242,21 +259,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (leader && lane == 0) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             bool first = true;
+            int tr_m = 0;
+            if (P.trace && blockIdx.x == 0) P.trace[tr_m++] = clock64();
             for (int64_t pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
                 mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+                if (P.trace && blockIdx.x == 0 && tr_m < 4000) P.trace[tr_m++] = clock64();
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kCout;
                 for (int tap = 0; tap < TAPS; ++tap) {
                     if (first) { mbar_wait(w_bar + 8 * tap, 0); tc_fence_after(); }
                     for (int kc = 0; kc < KCH; ++kc) {
                         mbar_wait(full_bar + 8 * stage, phase);
+                        if (P.trace && blockIdx.x == 0 && tr_m < 4000) P.trace[tr_m++] = clock64();
                         tc_fence_after();
                         const uint64_t adesc = umma_desc_sw128(a_smem + stage * kStageBytes);
                         const uint64_t bdesc = umma_desc_sw128(w_smem + (tap * KCH + kc) * kWSlotBytes);
 #pragma unroll
                         for (int k = 0; k < kKC / 16; ++k)   // +32 B per K = 16 step inside the 128 B swizzle row
-                            umma_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, (uint32_t)((tap | kc | k) != 0));
+                            if (!(P.debug & 4)) umma_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, (uint32_t)((tap | kc | k) != 0));
                         umma_commit_2sm(empty_bar + 8 * stage, 3);          // frees the stage in both CTAs
+                        if (P.trace && blockIdx.x == 0 && tr_m < 4000) P.trace[tr_m++] = clock64();
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -267,52 +289,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ===================== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====================
+        // Per 32-column chunk: TMEM -> registers (lane = row) -> fp32 staging tile in shared memory (XOR-swizzled
+        // 16 B slots, conflict-free both ways) -> re-read so that 4 consecutive lanes own 32 consecutive channels
+        // of one row: residual loads and both output stores are then full 32 B sectors, 8 rows per instruction.
         const int q = warp & 3;
         const uint32_t tempty_leader = mapa_rank(tempty_bar, 0);
         uint32_t acc = 0, acc_phase = 0;
-        const float* bias_s = vec;
-        const float* scale_s = vec + kCout;
-        const float* shift_s = vec + 2 * kCout;
+        float4* stg = reinterpret_cast<float4*>(gen + (stage_smem - base)) + q * (32 * 8);   // [32 rows][8 x 16 B]
+        const int sub = lane & 3, rsub = lane >> 2;          // channel octet within the chunk, row within a group of 8
+        const bool relu1 = P.relu1 != 0;
+        const bool no_io = (P.debug & 1) != 0;
         for (int64_t pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
-            const int64_t row = (2 * pt + rank) * kTileM + q * 32 + lane;
+            const int64_t row0 = (2 * pt + rank) * kTileM + q * 32;
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kCout;
-            const uint4* res = P.residual ? reinterpret_cast<const uint4*>(P.residual + row * kCout) : nullptr;
-            uint4* o1 = P.out1 ? reinterpret_cast<uint4*>(P.out1 + row * kCout) : nullptr;
-            uint4* o2 = P.out2 ? reinterpret_cast<uint4*>(P.out2 + row * kCout) : nullptr;
 #pragma unroll 1
             for (int j = 0; j < kCout / 32; ++j) {
                 uint32_t v[32];
                 tmem_ld32(taddr + j * 32, v);
-                uint4 r[4];
-                if (res) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) r[i] = __ldg(res + j * 4 + i);
-                }
+                const int c0 = j * 32 + sub * 8;
+                const float4 b0 = *reinterpret_cast<const float4*>(vec + c0), b1 = *reinterpret_cast<const float4*>(vec + c0 + 4);
+                const float4 s0 = *reinterpret_cast<const float4*>(vec + kCout + c0), s1 = *reinterpret_cast<const float4*>(vec + kCout + c0 + 4);
+                const float4 t0 = *reinterpret_cast<const float4*>(vec + 2 * kCout + c0), t1 = *reinterpret_cast<const float4*>(vec + 2 * kCout + c0 + 4);
+                const float bias8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float scale8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float shift8[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
                 tmem_ld_wait();
+                if (no_io) continue;
+                __syncwarp();                                   // previous chunk's readers are done with the staging tile
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {      // 8 channels per 16-byte store
+                for (int f = 0; f < 8; ++f)
+                    stg[lane * 8 + (f ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * f]), __uint_as_float(v[4 * f + 1]),
+                                                                   __uint_as_float(v[4 * f + 2]), __uint_as_float(v[4 * f + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int r = rsub + 8 * k;
+                    const float4 x0 = stg[r * 8 + ((2 * sub) ^ (r & 7))], x1 = stg[r * 8 + ((2 * sub + 1) ^ (r & 7))];
+                    float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                    const int64_t off = ((row0 + r) * kCout + c0) >> 3;            // in 16-byte units
+                    if (P.residual) {
+                        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(P.residual) + off);
+                        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) { const float2 f2 = __bfloat1622float2(r2[h]); x[2 * h] += f2.x; x[2 * h + 1] += f2.y; }
+                    }
                     uint32_t p1[4], p2[4];
-                    const uint32_t* rw = reinterpret_cast<const uint32_t*>(&r[i]);
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
-                        const int c = j * 32 + i * 8 + h * 2;
-                        float f0 = __uint_as_float(v[i * 8 + h * 2]) + bias_s[c];
-                        float f1 = __uint_as_float(v[i * 8 + h * 2 + 1]) + bias_s[c + 1];
-                        if (res) {
-                            const float2 rr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[h]));
-                            f0 += rr.x; f1 += rr.y;
-                        }
-                        if (P.relu1) { f0 = fmaxf(f0, 0.0f); f1 = fmaxf(f1, 0.0f); }
+                        float f0 = x[2 * h] + bias8[2 * h], f1 = x[2 * h + 1] + bias8[2 * h + 1];
+                        if (relu1) { f0 = fmaxf(f0, 0.0f); f1 = fmaxf(f1, 0.0f); }
                         const __nv_bfloat162 hb = __floats2bfloat162_rn(f0, f1);
                         p1[h] = *reinterpret_cast<const uint32_t*>(&hb);
-                        const float2 s = __bfloat1622float2(hb);       // BN reads the stored (bf16) value
-                        p2[h] = pack_bf16(fmaxf(fmaf(scale_s[c], s.x, shift_s[c]), 0.0f),
-                                          fmaxf(fmaf(scale_s[c + 1], s.y, shift_s[c + 1]), 0.0f));
+                        const float2 sv = __bfloat1622float2(hb);      // BN reads the stored (bf16) value
+                        p2[h] = pack_bf16(fmaxf(fmaf(scale8[2 * h], sv.x, shift8[2 * h]), 0.0f),
+                                          fmaxf(fmaf(scale8[2 * h + 1], sv.y, shift8[2 * h + 1]), 0.0f));
                     }
-                    if (o1) o1[j * 4 + i] = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-                    if (o2) o2[j * 4 + i] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+                    if (P.out1) reinterpret_cast<uint4*>(P.out1)[off] = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+                    if (P.out2) reinterpret_cast<uint4*>(P.out2)[off] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
                 }
             }
             tc_fence_before();
@@ -381,7 +416,7 @@ int launch_conv(const void* x, const void* w, const ConvParams& P, cudaStream_t 
         if (rc != CUDA_SUCCESS) { set_error("lzb_conv: cuTensorMapEncodeTiled failed (%d)", (int)rc); return LZB_ERR_CUDA; }
     }
     constexpr size_t smem = 1024 + (size_t)TAPS * KCH * kWSlotBytes + (size_t)kStages * kStageBytes +
-                            8 * (2 * kStages + TAPS + 2 * kAccStages) + 16 + 3 * kCout * sizeof(float);
+                            8 * (2 * kStages + TAPS + 2 * kAccStages) + 32 + 3 * kCout * sizeof(float) + 4 * 32 * 128;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(conv_tc_kernel<TAPS, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -400,6 +435,13 @@ int launch_conv(const void* x, const void* w, const ConvParams& P, cudaStream_t 
 }  // namespace lzb
 
 // x bf16 [n,6,6,cin] (NHWC), w bf16 [taps][128][cin], outputs bf16 [n,6,6,128]; n must be a multiple of 64.
+// debug: copy the clock64 trace of the last launches (LZB_CONV_DEBUG & 8) to host memory (8192 u64)
+static unsigned long long* g_trace_buf = nullptr;
+extern "C" __attribute__((visibility("default"))) int lzb_conv_debug_trace(unsigned long long* host_out) {
+    if (!g_trace_buf) return LZB_ERR_INVALID_ARGUMENT;
+    return cudaMemcpy(host_out, g_trace_buf, 8192 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? LZB_OK : LZB_ERR_CUDA;
+}
+
 extern "C" int lzb_conv_bf16(const void* x, const void* w, int64_t n, int32_t cin, int32_t taps, const float* bias,
                              const void* residual, const float* scale, const float* shift, int32_t relu1, void* out1,
                              void* out2, void* stream) {
@@ -413,6 +455,10 @@ extern "C" int lzb_conv_bf16(const void* x, const void* w, int64_t n, int32_t ci
     P.bias = bias; P.residual = reinterpret_cast<const __nv_bfloat16*>(residual); P.scale = scale; P.shift = shift;
     P.out1 = reinterpret_cast<__nv_bfloat16*>(out1); P.out2 = reinterpret_cast<__nv_bfloat16*>(out2);
     P.rows = n * 36; P.relu1 = relu1; P.images = (int)n;
+    static const int debug = getenv("LZB_CONV_DEBUG") ? atoi(getenv("LZB_CONV_DEBUG")) : 0;
+    P.debug = debug;
+    if ((debug & 8) && !g_trace_buf) { cudaMalloc(&g_trace_buf, 8192 * 8); cudaMemset(g_trace_buf, 0, 8192 * 8); }
+    P.trace = g_trace_buf;
     if (taps == 9) return lzb::launch_conv<9, 2>(x, w, P, (cudaStream_t)stream);
     return lzb::launch_conv<1, 2>(x, w, P, (cudaStream_t)stream);
 }

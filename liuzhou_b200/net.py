@@ -14,6 +14,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Tuple
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -206,6 +208,9 @@ class FusedTrunk:
         self.model = model
         self._t = {}
         self.use_cudnn_fused = True
+        # our tcgen05 implicit-GEMM conv covers the 128-channel trunk; other widths keep the cuDNN path
+        self.use_tc = (model.stem_conv.out_channels == 128 and model.stem_conv.weight.dtype == torch.bfloat16
+                       and os.environ.get("LZB_DISABLE_TC_CONV", "0") != "1")
         self.refresh()
         self._probe()
 
@@ -230,6 +235,10 @@ class FusedTrunk:
             w, b = self._fold_into_conv(blk.conv1, blk.bn2)
             self._set(f"w1_{i}", w)
             self._set(f"b1_{i}", b)
+            if self.use_tc:      # layouts of our tcgen05 convolution (csrc/lz_conv.cu)
+                self._set(f"wp1_{i}", pack_conv_weight(w))
+                self._set(f"bf1_{i}", b.float())
+                self._set(f"wp2_{i}", pack_conv_weight(blk.conv2.weight))
             s, t = _fold_bn(blk.bn1)
             self._set(f"s1_{i}", s)
             self._set(f"t1_{i}", t)
@@ -284,6 +293,16 @@ class FusedTrunk:
         if nb == 0:
             return self._bn_relu(xr, None, t["trunk_s"], t["trunk_t"], False)[1]
         _, a = self._bn_relu(xr, None, t["s1_0"], t["t1_0"], False)                           # a0 = relu(bn1_0(x0))
+        if self.use_tc and x.size(0) % 64 == 0:
+            # 2 launches per residual block, no elementwise pass: the residual add, the next BatchNorm and the
+            # ReLU are the epilogue of conv2; BatchNorm + ReLU after conv1 are folded weights + the epilogue of conv1
+            for i in range(nb):
+                h, _ = conv_bf16(a, t[f"wp1_{i}"], bias=t[f"bf1_{i}"], relu1=True)
+                last = i == nb - 1
+                sn, tn = ("trunk_s", "trunk_t") if last else (f"s1_{i + 1}", f"t1_{i + 1}")
+                xr, a = conv_bf16(h, t[f"wp2_{i}"], residual=xr, scale=t[sn], shift=t[tn], want_out1=not last,
+                                  want_out2=True)
+            return a
         for i, blk in enumerate(m.blocks):
             h = self._conv_bn_relu(a, blk.conv1, f"w1_{i}", f"b1_{i}", f"s2_{i}", f"t2_{i}")  # relu(bn2(conv1(a)))
             c2 = F.conv2d(h, blk.conv2.weight, None, 1, 1)
@@ -324,6 +343,12 @@ class FusedHeads:
         s2, t2 = _fold_bn(vh.bn1)
         self._set("bn1_scale", torch.cat([s1, s2]))
         self._set("bn1_shift", torch.cat([t1, t2]))
+        self.use_tc = (self.pc + self.vc == 128 and ph.conv1.in_channels == 128
+                       and ph.conv1.weight.dtype == torch.bfloat16 and os.environ.get("LZB_DISABLE_TC_CONV", "0") != "1")
+        if self.use_tc:     # both heads' 1x1 convs + their BatchNorm + ReLU as ONE launch of our tcgen05 conv
+            wf = torch.cat([ph.conv1.weight.detach(), vh.conv1.weight.detach()], 0).float()
+            self._set("conv_wp", pack_conv_weight(wf * torch.cat([s1, s2]).view(-1, 1, 1, 1)))
+            self._set("conv_bias", torch.cat([t1, t2]).float())
         self._set("wgl_t", f(ph.gpool_linear.weight).t())
         sb, tb = _fold_bn(ph.bn2)
         self._set("bn2_scale", sb)
@@ -346,10 +371,13 @@ class FusedHeads:
         t = self._t
         n = a.size(0)
         dev = a.device
-        c = F.conv2d(a, t["conv_w"], None, 1, 0)
-        pv = torch.empty_like(c)
-        check(lib().lzb_bn_relu_bf16(ptr(c), ptr(None), ptr(t["bn1_scale"]), ptr(t["bn1_shift"]), i64(n * 36),
-                                     ctypes.c_int32(self.pc + self.vc), ptr(None), ptr(pv), stream_ptr(dev)))
+        if self.use_tc and n % 64 == 0:
+            pv, _ = conv_bf16(a, t["conv_wp"], bias=t["conv_bias"], relu1=True)
+        else:
+            c = F.conv2d(a, t["conv_w"], None, 1, 0)
+            pv = torch.empty_like(c)
+            check(lib().lzb_bn_relu_bf16(ptr(c), ptr(None), ptr(t["bn1_scale"]), ptr(t["bn1_shift"]), i64(n * 36),
+                                         ctypes.c_int32(self.pc + self.vc), ptr(None), ptr(pv), stream_ptr(dev)))
         log_heads = value_logits = None
         if want_raw:
             log_heads = torch.empty((n, 3, 36), dtype=torch.float32, device=dev)

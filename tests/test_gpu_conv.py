@@ -67,3 +67,32 @@ def test_conv_is_deterministic_and_border_exact():
     assert torch.equal(y.float(), cnt.expand(n, 128, 6, 6))
     y2, _ = conv_bf16(x, pack_conv_weight(w))
     assert torch.equal(y, y2)
+
+
+def test_trunk_and_heads_tc_path_matches_cudnn_path():
+    """The whole default ChessNet forward through our tcgen05 convs (20 trunk convs + the heads' 1x1 conv) vs the
+    cuDNN conv + bn_relu path on the same inputs: same folded weights, bf16 activations -> agreement to bf16 noise,
+    and both agree with the fp32 PyTorch module."""
+    from liuzhou_b200.net import ChessNet, InferenceNet
+
+    torch.manual_seed(5)
+    model = ChessNet()
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0.0, 0.2)
+            m.running_var.uniform_(0.6, 1.4)
+            m.weight.data.uniform_(0.7, 1.3)
+            m.bias.data.normal_(0.0, 0.1)
+    net = InferenceNet(model, DEV)
+    assert net.trunk.use_tc and net.heads.use_tc
+    x = net.new_input(128)
+    x.copy_((torch.rand((128, 11, 6, 6), device=DEV) > 0.6).to(x.dtype))
+    out_tc = [o.clone() for o in net._forward_eager(x)]
+    net.trunk.use_tc = net.heads.use_tc = False
+    out_cudnn = [o.clone() for o in net._forward_eager(x)]
+    ref = model.to(DEV).float().eval()
+    with torch.no_grad():
+        out_ref = ref(x.float())
+    for a, b, r in zip(out_tc, out_cudnn, out_ref):
+        torch.testing.assert_close(a, b, rtol=5e-2, atol=5e-2)
+        torch.testing.assert_close(a, r.float().reshape(a.shape), rtol=8e-2, atol=8e-2)
