@@ -10,7 +10,7 @@
 // * MMA: tcgen05.mma.cta_group::2.kind::f16, M = 256 (128 rows per CTA), N = 128, K = 16; fp32 accumulators in
 //   TMEM, double buffered (2 x 128 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 // * Persistent: 74 clusters walk the 256-row tiles round-robin.  Warp roles per CTA: warp 0 = TMA producer,
-//   warp 1 = TMEM allocator + (leader CTA) MMA issuer, warps 2-5 = epilogue (one TMEM lane quarter each).
+//   warp 1 = TMEM allocator + (leader CTA) MMA issuer, warps 2-9 = epilogue (TMEM lane quarter x column half).
 // * Epilogue (per row, fp32): v = acc + bias[c] (+ residual[row][c]); optional ReLU; out1 = bf16(v);
 //   out2 = bf16(relu(scale[c] * float(out1) + shift[c])).  With BatchNorm folded this covers
 //       conv1 of a block : out1 = relu(bn2(conv1(a)))                      (bias, relu)
@@ -27,12 +27,12 @@
 namespace lzb {
 namespace {
 
-constexpr int kConvThreads = 192;
-constexpr int kStages = 4;                       // A-operand pipeline depth
+constexpr int kConvThreads = 320;                // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
+constexpr int kStages = 4;                       // pipeline depth (one stage = one tap: A [128 x Cin] + this CTA's half of W_tap)
 constexpr int kTileM = 128;                      // rows per CTA (256 per CTA pair)
 constexpr int kCout = 128;
 constexpr int kKC = 64;                          // channels per pipeline stage: 64 bf16 = one 128 B swizzle row
-constexpr uint32_t kStageBytes = kTileM * kKC * 2;        // 16 KB
+constexpr uint32_t kChunkBytes = kTileM * kKC * 2;        // 16 KB: [128 rows x 64 ch], one TMA im2col load
 constexpr uint32_t kWSlotBytes = (kCout / 2) * kKC * 2;   // 8 KB: 64 couts (this CTA's half) x 64 cin
 constexpr int kAccStages = 2;
 constexpr uint32_t kTmemCols = kAccStages * kCout;        // 256 fp32 columns
@@ -96,6 +96,14 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
 // fast path: one try_wait (which itself suspends the thread for a while); the watchdog only starts after it fails
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+}
+// One lane of the (converged) warp; the compiler then knows the guarded region runs single-threaded and keeps the
+// tcgen05 / TMA operands in uniform registers (a plain `lane == 0` test makes it wrap every UTCHMMA / UTMALDG in a
+// divergence "waterfall" loop: ~80 cycles per instruction instead of ~10).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -169,22 +177,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int TAPS, int KCH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvParams P) {
-    constexpr int kWSlots = TAPS * KCH;
-    constexpr uint32_t kWBytes = kWSlots * kWSlotBytes;
+    constexpr uint32_t kABytes = KCH * kChunkBytes;         // 32 KB
+    constexpr uint32_t kStageBytes = kABytes + KCH * kWSlotBytes;   // + 16 KB of weights = 48 KB
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B atoms need 1024 B alignment
-    const uint32_t w_smem = base;
-    const uint32_t a_smem = base + kWBytes;
+    const uint32_t a_smem = base;
     const uint32_t bar0 = a_smem + kStages * kStageBytes;
     // barriers (8 B each)
     const uint32_t full_bar = bar0;                         // [kStages]    leader: A stage landed (both CTAs' bytes)
     const uint32_t empty_bar = full_bar + 8 * kStages;      // [kStages]    both  : MMAs that read the stage are done
-    const uint32_t w_bar = empty_bar + 8 * kStages;         // [TAPS]       leader: weights of a tap landed (both CTAs)
-    const uint32_t tfull_bar = w_bar + 8 * TAPS;            // [kAccStages] both  : accumulator complete
+    const uint32_t tfull_bar = empty_bar + 8 * kStages;     // [kAccStages] both  : accumulator complete
     const uint32_t tempty_bar = tfull_bar + 8 * kAccStages; // [kAccStages] leader: epilogue of both CTAs drained it
     const uint32_t tmem_slot = tempty_bar + 8 * kAccStages; // u32
     const uint32_t vec_smem = (tmem_slot + 16 + 15u) & ~15u; // bias | scale | shift : 3 x 128 f32
-    const uint32_t stage_smem = vec_smem + 3 * kCout * 4;   // epilogue staging: 4 warps x 32 rows x 128 B (fp32)
+    const uint32_t stage_smem = vec_smem + 3 * kCout * 4;   // epilogue staging: 8 warps x 32 rows x 128 B (fp32)
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     float* vec = reinterpret_cast<float*>(gen + (vec_smem - base));
     volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
@@ -199,8 +205,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmW);
         for (int i = 0; i < kStages; ++i) { mbar_init(full_bar + 8 * i, 1); mbar_init(empty_bar + 8 * i, 1); }
-        for (int i = 0; i < TAPS; ++i) mbar_init(w_bar + 8 * i, 1);
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, 8); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(tfull_bar + 8 * i, 1); mbar_init(tempty_bar + 8 * i, 16); }
         fence_barrier_init();
     }
     if (warp == 1) {   // TMEM: one warp per CTA, the pair allocates together
@@ -219,109 +224,123 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot_p;
 
     if (warp == 0) {
-        // ===================== TMA producer (one lane; both CTAs) =====================
-        if (lane == 0) {
-            const uint32_t full_leader = mapa_rank(full_bar, 0), w_leader = mapa_rank(w_bar, 0);
-            uint32_t stage = 0, phase = 0;
-            bool first = true;
-            int tr_p = 0;
-            for (int64_t pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
-                const int64_t p0 = (2 * pt + rank) * kTileM;
-                const int n0 = (int)(p0 / 36), rem = (int)(p0 - (int64_t)n0 * 36), h0 = rem / 6, w0 = rem - h0 * 6;
-                for (int tap = 0; tap < TAPS; ++tap) {
-                    if (first) {   // this tap's weights: our half of Cout, all of Cin -> resident slots
-                        if (leader) mbar_arrive_expect_tx(w_bar + 8 * tap, 2 * KCH * kWSlotBytes);
-                        for (int kc = 0; kc < KCH; ++kc)
-                            tma_tile2d_2sm(w_smem + (tap * KCH + kc) * kWSlotBytes, &tmW, w_leader + 8 * tap, kc * kKC,
-                                           tap * kCout + (int)rank * (kCout / 2));
-                    }
-                    const int off_w = TAPS == 9 ? tap % 3 : 0, off_h = TAPS == 9 ? tap / 3 : 0;
-                    const int lo = TAPS == 9 ? -1 : 0;
-                    for (int kc = 0; kc < KCH; ++kc) {
-                        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-                        if (P.trace && blockIdx.x == 0 && tr_p < 4096) P.trace[4096 + tr_p++] = clock64();
-                        if (P.debug & 2) {   // timing experiment: no loads, the MMAs chew on whatever is in smem
-                            if (leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_bar + 8 * stage) : "memory");
-                            if (++stage == kStages) { stage = 0; phase ^= 1; }
-                            continue;
-                        }
+        // ===================== TMA producer (whole warp loops, one elected lane issues; both CTAs) ============
+        const uint32_t full_leader = mapa_rank(full_bar, 0);
+        uint32_t stage = 0, phase = 0;
+        int tr_p = 0;
+        for (int64_t pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
+            const int64_t p0 = (2 * pt + rank) * kTileM;
+            const int n0 = (int)(p0 / 36), rem = (int)(p0 - (int64_t)n0 * 36), h0 = rem / 6, w0 = rem - h0 * 6;
+            for (int tap = 0; tap < TAPS; ++tap) {
+                const int off_w = TAPS == 9 ? tap % 3 : 0, off_h = TAPS == 9 ? tap / 3 : 0;
+                const int lo = TAPS == 9 ? -1 : 0;
+                mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                if (elect_one()) {
+                    if (P.trace && blockIdx.x == 0 && tr_p < 4096) P.trace[4096 + tr_p++] = clock64();
+                    if (P.debug & 2) {   // timing experiment: no loads, the MMAs chew on whatever is in smem
+                        if (leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_bar + 8 * stage) : "memory");
+                    } else {
                         if (leader) mbar_arrive_expect_tx(full_bar + 8 * stage, 2 * kStageBytes);
-                        tma_im2col_2sm(a_smem + stage * kStageBytes, &tmA, full_leader + 8 * stage, kc * kKC, w0 + lo, h0 + lo,
-                                       n0, (uint16_t)off_w, (uint16_t)off_h);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+#pragma unroll
+                        for (int kc = 0; kc < KCH; ++kc) {
+                            tma_im2col_2sm(a_smem + stage * kStageBytes + kc * kChunkBytes, &tmA, full_leader + 8 * stage,
+                                           kc * kKC, w0 + lo, h0 + lo, n0, (uint16_t)off_w, (uint16_t)off_h);
+                            // this tap's weights: our half of Cout (the pair's MMA reads the other half from the peer)
+                            tma_tile2d_2sm(a_smem + stage * kStageBytes + kABytes + kc * kWSlotBytes, &tmW,
+                                           full_leader + 8 * stage, kc * kKC, tap * kCout + (int)rank * (kCout / 2));
+                        }
                     }
                 }
-                first = false;
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (leader CTA, one lane) =====================
-        if (leader && lane == 0) {
+        // ===================== MMA issuer (leader CTA; whole warp loops, one elected lane issues) =============
+        if (leader) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            bool first = true;
             int tr_m = 0;
-            if (P.trace && blockIdx.x == 0) P.trace[tr_m++] = clock64();
             for (int64_t pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
                 mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
-                if (P.trace && blockIdx.x == 0 && tr_m < 4000) P.trace[tr_m++] = clock64();
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kCout;
                 for (int tap = 0; tap < TAPS; ++tap) {
-                    if (first) { mbar_wait(w_bar + 8 * tap, 0); tc_fence_after(); }
-                    for (int kc = 0; kc < KCH; ++kc) {
-                        mbar_wait(full_bar + 8 * stage, phase);
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    tc_fence_after();
+                    if (elect_one()) {
                         if (P.trace && blockIdx.x == 0 && tr_m < 4000) P.trace[tr_m++] = clock64();
-                        tc_fence_after();
-                        const uint64_t adesc = umma_desc_sw128(a_smem + stage * kStageBytes);
-                        const uint64_t bdesc = umma_desc_sw128(w_smem + (tap * KCH + kc) * kWSlotBytes);
 #pragma unroll
-                        for (int k = 0; k < kKC / 16; ++k)   // +32 B per K = 16 step inside the 128 B swizzle row
-                            if (!(P.debug & 4)) umma_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, (uint32_t)((tap | kc | k) != 0));
-                        umma_commit_2sm(empty_bar + 8 * stage, 3);          // frees the stage in both CTAs
+                        for (int kc = 0; kc < KCH; ++kc) {
+                            const uint64_t adesc = umma_desc_sw128(a_smem + stage * kStageBytes + kc * kChunkBytes);
+                            const uint64_t bdesc = umma_desc_sw128(a_smem + stage * kStageBytes + kABytes + kc * kWSlotBytes);
+#pragma unroll
+                            for (int k = 0; k < kKC / 16; ++k)   // +32 B per K = 16 step inside the 128 B swizzle row
+                                if (!(P.debug & 4)) umma_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, (uint32_t)((tap | kc | k) != 0));
+                        }
+                        umma_commit_2sm(empty_bar + 8 * stage, 3);              // frees the stage in both CTAs
+                        if (tap == TAPS - 1) umma_commit_2sm(tfull_bar + 8 * acc, 3);   // accumulator ready in both CTAs
                         if (P.trace && blockIdx.x == 0 && tr_m < 4000) P.trace[tr_m++] = clock64();
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_2sm(tfull_bar + 8 * acc, 3);                    // accumulator ready in both CTAs
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
-                first = false;
             }
         }
     } else {
-        // ===================== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====================
-        // Per 32-column chunk: TMEM -> registers (lane = row) -> fp32 staging tile in shared memory (XOR-swizzled
-        // 16 B slots, conflict-free both ways) -> re-read so that 4 consecutive lanes own 32 consecutive channels
-        // of one row: residual loads and both output stores are then full 32 B sectors, 8 rows per instruction.
-        const int q = warp & 3;
+        // ===================== epilogue: warps 2..9 =====================
+        // TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4: each warp owns 32 rows x 64
+        // channels of the tile.  Per 32-column chunk: TMEM -> registers (lane = row) -> fp32 staging tile in shared
+        // memory (XOR-swizzled 16 B slots, conflict-free both ways) -> re-read so that 4 consecutive lanes own 32
+        // consecutive channels of one row: residual loads and both output stores are then full 32 B sectors,
+        // 8 rows per instruction.  The residual is prefetched into registers BEFORE waiting for the accumulator.
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const uint32_t tempty_leader = mapa_rank(tempty_bar, 0);
         uint32_t acc = 0, acc_phase = 0;
-        float4* stg = reinterpret_cast<float4*>(gen + (stage_smem - base)) + q * (32 * 8);   // [32 rows][8 x 16 B]
+        float4* stg = reinterpret_cast<float4*>(gen + (stage_smem - base)) + (warp - 2) * (32 * 8);   // [32 rows][8 x 16 B]
         const int sub = lane & 3, rsub = lane >> 2;          // channel octet within the chunk, row within a group of 8
         const bool relu1 = P.relu1 != 0;
         const bool no_io = (P.debug & 1) != 0;
+        int tr_e = 0;
         for (int64_t pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
             const int64_t row0 = (2 * pt + rank) * kTileM + q * 32;
+            uint4 resv[2][4];
+            if (P.residual) {
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        resv[jj][k] = __ldg(reinterpret_cast<const uint4*>(P.residual) +
+                                            (((row0 + rsub + 8 * k) * kCout + half * 64 + jj * 32 + sub * 8) >> 3));
+            }
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
+            if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 2000) P.trace[2048 + tr_e++] = clock64();
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kCout;
-#pragma unroll 1
-            for (int j = 0; j < kCout / 32; ++j) {
-                uint32_t v[32];
-                tmem_ld32(taddr + j * 32, v);
-                const int c0 = j * 32 + sub * 8;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kCout + half * 64;
+            uint32_t v[2][32];
+            tmem_ld32(taddr, v[0]);
+            tmem_ld32(taddr + 32, v[1]);
+            tmem_ld_wait();
+            // the accumulator is in registers: hand the TMEM stage back to the MMA warp right away
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * acc);
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+            if (no_io) continue;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int c0 = half * 64 + jj * 32 + sub * 8;
                 const float4 b0 = *reinterpret_cast<const float4*>(vec + c0), b1 = *reinterpret_cast<const float4*>(vec + c0 + 4);
                 const float4 s0 = *reinterpret_cast<const float4*>(vec + kCout + c0), s1 = *reinterpret_cast<const float4*>(vec + kCout + c0 + 4);
                 const float4 t0 = *reinterpret_cast<const float4*>(vec + 2 * kCout + c0), t1 = *reinterpret_cast<const float4*>(vec + 2 * kCout + c0 + 4);
                 const float bias8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 const float scale8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                 const float shift8[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-                tmem_ld_wait();
-                if (no_io) continue;
                 __syncwarp();                                   // previous chunk's readers are done with the staging tile
 #pragma unroll
                 for (int f = 0; f < 8; ++f)
-                    stg[lane * 8 + (f ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * f]), __uint_as_float(v[4 * f + 1]),
-                                                                   __uint_as_float(v[4 * f + 2]), __uint_as_float(v[4 * f + 3]));
+                    stg[lane * 8 + (f ^ (lane & 7))] = make_float4(__uint_as_float(v[jj][4 * f]), __uint_as_float(v[jj][4 * f + 1]),
+                                                                   __uint_as_float(v[jj][4 * f + 2]), __uint_as_float(v[jj][4 * f + 3]));
                 __syncwarp();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -330,8 +349,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                     const int64_t off = ((row0 + r) * kCout + c0) >> 3;            // in 16-byte units
                     if (P.residual) {
-                        const uint4 rr = __ldg(reinterpret_cast<const uint4*>(P.residual) + off);
-                        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rr);
+                        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&resv[jj][k]);
 #pragma unroll
                         for (int h = 0; h < 4; ++h) { const float2 f2 = __bfloat1622float2(r2[h]); x[2 * h] += f2.x; x[2 * h + 1] += f2.y; }
                     }
@@ -350,10 +368,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (P.out2) reinterpret_cast<uint4*>(P.out2)[off] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * acc);
-            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+            if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 2000) P.trace[2048 + tr_e++] = clock64();
         }
     }
 
@@ -415,8 +430,8 @@ int launch_conv(const void* x, const void* w, const ConvParams& P, cudaStream_t 
                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rc != CUDA_SUCCESS) { set_error("lzb_conv: cuTensorMapEncodeTiled failed (%d)", (int)rc); return LZB_ERR_CUDA; }
     }
-    constexpr size_t smem = 1024 + (size_t)TAPS * KCH * kWSlotBytes + (size_t)kStages * kStageBytes +
-                            8 * (2 * kStages + TAPS + 2 * kAccStages) + 32 + 3 * kCout * sizeof(float) + 4 * 32 * 128;
+    constexpr size_t smem = 1024 + (size_t)kStages * KCH * (kChunkBytes + kWSlotBytes) +
+                            8 * (2 * kStages + 2 * kAccStages) + 32 + 3 * kCout * sizeof(float) + 8 * 32 * 128;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(conv_tc_kernel<TAPS, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {

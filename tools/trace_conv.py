@@ -21,21 +21,24 @@ for _ in range(3):
 torch.cuda.synchronize()
 buf = np.zeros(8192, dtype=np.uint64)
 lib().lzb_conv_debug_trace(buf.ctypes.data_as(ctypes.POINTER(ctypes.c_ulonglong)))
-m = buf[:4096][buf[:4096] > 0].astype(np.int64)
+e = buf[2048:4096][buf[2048:4096] > 0].astype(np.int64)
+m = buf[:2048][buf[:2048] > 0].astype(np.int64)
 p = buf[4096:][buf[4096:] > 0].astype(np.int64)
 t0 = m[0]
+e = e - t0
+print("epilogue (warp 2) [tfull ok, done] per tile:", [(int(a), int(b), int(b - a)) for a, b in zip(e[0::2], e[1::2])])
 print("MMA thread stamps:", len(m), "producer stamps:", len(p))
 m = m - t0
 p = p - t0
 # layout of m: [start], then per tile: [tempty ok], then per stage: [full ok, committed]
-idx = 1
+idx = 0
 tiles = []
 for t in range(8):
     if idx >= len(m):
         break
-    te = m[idx]; idx += 1
+    te = 0
     st = []
-    for s in range(18):
+    for s in range(9):
         if idx + 1 >= len(m):
             break
         st.append((m[idx], m[idx + 1])); idx += 2
