@@ -239,7 +239,8 @@ LZB_API int lzb_tree_root_outputs(const lzb_tree *tree, int32_t *visit_counts, f
 LZB_API int lzb_tree_set_root_priors(const lzb_tree *tree, const float *priors, void *stream);
 
 /* Model-input planes from packed states (a6 on the native layout): layout 0 = f32 [n,11,6,6];
- * layout 1 = bf16 channels-last ([n,6,6,11] physical) ready for the bf16 network. */
+ * layout 1 = bf16 channels-last ([n,6,6,11] physical) ready for the bf16 network; layout 2 = the same padded to 64
+ * channels ([n,6,6,64] physical, channels 11..63 zero): the K = 64 operand of our tcgen05 stem convolution. */
 LZB_API int lzb_encode_inputs_packed(const uint64_t *states, int64_t n, int32_t layout, void *out, void *stream);
 /* Fused a7 + value decode on packed states: fp32 heads [n,36] x3 + value logits [n,bins] ->
  * priors f32[n,220] (softmax over the scalar-engine legal set) and values f32[n]. */
@@ -264,7 +265,7 @@ LZB_API int lzb_bn_relu_bf16(const void *u, const void *v, const float *scale, c
  * epilogue fused in (replaces F.conv2d + eval BatchNorm + ReLU + residual add of PreActResBlock,
  * src/neural_network.py:83-96,250-254; csrc/lz_conv.cu).
  *   x bf16 [n,6,6,cin] channels-last, w bf16 [taps][128][cin] (tap = ky*3+kx; BatchNorm that follows the conv
- *   folded into w / bias), cin = 128, taps = 9 (3x3, pad 1) or 1 (1x1), n a multiple of 64.
+ *   folded into w / bias), cin = 128 or 64, taps = 9 (3x3, pad 1) or 1 (1x1), n a multiple of 64.
  *   v    = conv(x, w) + bias (+ residual) ; optional ReLU (relu1)
  *   out1 = bf16(v)                                   (may be NULL)
  *   out2 = bf16(relu(scale * float(out1) + shift))   (may be NULL)

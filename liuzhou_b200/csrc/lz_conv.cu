@@ -74,8 +74,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Relaxed on purpose: this arrive only hands a TMEM accumulator back (ordered by tcgen05.fence::before_thread_sync);
+// a .release here is a MEMBAR.GPU that waits for the thread's outstanding global stores (~2,000 cycles per tile).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -222,6 +224,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     cluster_sync_all();            // the peer's barriers exist before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_p;
+    // Programmatic dependent launch: everything above touched only constants and on-chip state.  Let the next
+    // layer's grid be scheduled as our SMs free up, and wait here until the previous layer's outputs are complete.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp loops, one elected lane issues; both CTAs) ============
@@ -321,6 +327,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld32(taddr, v[0]);
             tmem_ld32(taddr + 32, v[1]);
             tmem_ld_wait();
+            if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 2000) P.trace[2048 + tr_e++] = clock64();
             // the accumulator is in registers: hand the TMEM stage back to the MMA warp right away
             tc_fence_before();
             __syncwarp();
@@ -333,9 +340,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float4 b0 = *reinterpret_cast<const float4*>(vec + c0), b1 = *reinterpret_cast<const float4*>(vec + c0 + 4);
                 const float4 s0 = *reinterpret_cast<const float4*>(vec + kCout + c0), s1 = *reinterpret_cast<const float4*>(vec + kCout + c0 + 4);
                 const float4 t0 = *reinterpret_cast<const float4*>(vec + 2 * kCout + c0), t1 = *reinterpret_cast<const float4*>(vec + 2 * kCout + c0 + 4);
-                const float bias8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                const float scale8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                const float shift8[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                const float2 bias2[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+                const float2 scale2[4] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w), make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
+                const float2 shift2[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w), make_float2(t1.x, t1.y), make_float2(t1.z, t1.w)};
                 __syncwarp();                                   // previous chunk's readers are done with the staging tile
 #pragma unroll
                 for (int f = 0; f < 8; ++f)
@@ -346,27 +353,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int k = 0; k < 4; ++k) {
                     const int r = rsub + 8 * k;
                     const float4 x0 = stg[r * 8 + ((2 * sub) ^ (r & 7))], x1 = stg[r * 8 + ((2 * sub + 1) ^ (r & 7))];
-                    float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                    float2 x[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y), make_float2(x1.z, x1.w)};
                     const int64_t off = ((row0 + r) * kCout + c0) >> 3;            // in 16-byte units
                     if (P.residual) {
-                        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&resv[jj][k]);
+                        const uint32_t* rw = reinterpret_cast<const uint32_t*>(&resv[jj][k]);
 #pragma unroll
-                        for (int h = 0; h < 4; ++h) { const float2 f2 = __bfloat1622float2(r2[h]); x[2 * h] += f2.x; x[2 * h + 1] += f2.y; }
+                        for (int h = 0; h < 4; ++h)      // bf16 pair -> two floats: low half << 16, high half masked
+                            x[h] = __fadd2_rn(x[h], make_float2(__uint_as_float(rw[h] << 16), __uint_as_float(rw[h] & 0xffff0000u)));
                     }
                     uint32_t p1[4], p2[4];
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
-                        float f0 = x[2 * h] + bias8[2 * h], f1 = x[2 * h + 1] + bias8[2 * h + 1];
-                        if (relu1) { f0 = fmaxf(f0, 0.0f); f1 = fmaxf(f1, 0.0f); }
-                        const __nv_bfloat162 hb = __floats2bfloat162_rn(f0, f1);
-                        p1[h] = *reinterpret_cast<const uint32_t*>(&hb);
-                        const float2 sv = __bfloat1622float2(hb);      // BN reads the stored (bf16) value
-                        p2[h] = pack_bf16(fmaxf(fmaf(scale8[2 * h], sv.x, shift8[2 * h]), 0.0f),
-                                          fmaxf(fmaf(scale8[2 * h + 1], sv.y, shift8[2 * h + 1]), 0.0f));
+                        float2 f = __fadd2_rn(x[h], bias2[h]);
+                        if (relu1) { f.x = fmaxf(f.x, 0.0f); f.y = fmaxf(f.y, 0.0f); }
+                        p1[h] = pack_bf16(f.x, f.y);
+                        // BN reads the stored (bf16) value: unpack the pair we just rounded
+                        const float2 sv = make_float2(__uint_as_float(p1[h] << 16), __uint_as_float(p1[h] & 0xffff0000u));
+                        const float2 g = __ffma2_rn(scale2[h], sv, shift2[h]);
+                        p2[h] = pack_bf16(fmaxf(g.x, 0.0f), fmaxf(g.y, 0.0f));
                     }
                     if (P.out1) reinterpret_cast<uint4*>(P.out1)[off] = make_uint4(p1[0], p1[1], p1[2], p1[3]);
                     if (P.out2) reinterpret_cast<uint4*>(P.out2)[off] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
                 }
+                if (jj == 0 && P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 2000) P.trace[2048 + tr_e++] = clock64();
             }
             if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 2000) P.trace[2048 + tr_e++] = clock64();
         }
@@ -442,7 +451,18 @@ int launch_conv(const void* x, const void* w, const ConvParams& P, cudaStream_t 
     }
     const int64_t pair_tiles = P.rows / (2 * kTileM);
     const int clusters = (int)(pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2);
-    conv_tc_kernel<TAPS, KCH><<<2 * clusters, kConvThreads, smem, stream>>>(tmA, tmW, P);
+    static const bool pdl = !(getenv("LZB_CONV_PDL") && atoi(getenv("LZB_CONV_PDL")) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, conv_tc_kernel<TAPS, KCH>, tmA, tmW, P) != cudaSuccess) return check_launch("conv_tc_kernel");
     return check_launch("conv_tc_kernel");
 }
 
@@ -461,7 +481,8 @@ extern "C" int lzb_conv_bf16(const void* x, const void* w, int64_t n, int32_t ci
                              const void* residual, const float* scale, const float* shift, int32_t relu1, void* out1,
                              void* out2, void* stream) {
     LZB_REQUIRE(n > 0 && n % 64 == 0, "batch must be a positive multiple of 64 (256-row tile pairs)");
-    LZB_REQUIRE(cin == 128 && (taps == 9 || taps == 1), "supported: cin = 128, taps = 9 (3x3, pad 1) or 1 (1x1)");
+    LZB_REQUIRE((cin == 128 && (taps == 9 || taps == 1)) || (cin == 64 && taps == 9),
+                "supported: cin = 128 with taps = 9 (3x3, pad 1) or 1 (1x1); cin = 64 with taps = 9");
     LZB_REQUIRE(x && w && (out1 || out2), "null pointer");
     LZB_REQUIRE(!out2 || (scale && shift), "out2 needs scale / shift");
     LZB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(residual) |
@@ -474,6 +495,7 @@ extern "C" int lzb_conv_bf16(const void* x, const void* w, int64_t n, int32_t ci
     P.debug = debug;
     if ((debug & 8) && !g_trace_buf) { cudaMalloc(&g_trace_buf, 8192 * 8); cudaMemset(g_trace_buf, 0, 8192 * 8); }
     P.trace = g_trace_buf;
+    if (cin == 64) return lzb::launch_conv<9, 1>(x, w, P, (cudaStream_t)stream);
     if (taps == 9) return lzb::launch_conv<9, 2>(x, w, P, (cudaStream_t)stream);
     return lzb::launch_conv<1, 2>(x, w, P, (cudaStream_t)stream);
 }

@@ -369,6 +369,37 @@ encode_inputs_kernel(const uint64_t* __restrict__ states, int64_t n, void* __res
     }
 }
 
+// layout 2: bf16 channels-last padded to 64 channels (physical [n,6,6,64], channels 11..63 zero): the K = 64 input of
+// our tcgen05 stem convolution (csrc/lz_conv.cu); 16-byte stores, 8 channels each.
+__global__ void __launch_bounds__(kThreads)
+encode_inputs_c64_kernel(const uint64_t* __restrict__ states, int64_t n, uint4* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t i = warp; i < n; i += nwarps) {
+        State<int> s;
+        unpack(load_packed(states, i), s);
+        const bool black = s.player == 1;
+        const uint64_t p0 = black ? s.black : s.white, p1 = black ? s.white : s.black;
+        const uint64_t p2 = black ? s.mb : s.mw, p3 = black ? s.mw : s.mb;
+        const int phase_plane = 3 + s.phase;
+        for (int e = lane; e < 288; e += 32) {
+            const int cell = e >> 3, oct = e & 7;
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            if (oct < 2) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int plane = oct * 8 + c;
+                    const uint64_t bits = plane == 0 ? p0 : plane == 1 ? p1 : plane == 2 ? p2 : p3;
+                    const bool on = plane < 4 ? ((bits >> cell) & 1) : (plane < 11 && plane == phase_plane);
+                    if (on) w[c >> 1] |= (c & 1) ? 0x3F800000u : 0x00003F80u;        // bf16 1.0
+                }
+            }
+            out[i * 288 + e] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
 // Policy heads -> dense priors over the legal actions of each leaf (masked softmax, fp32) and bucketed value
 // head -> scalar (expectation over linspace(-1, 1, bins)): fuses project_policy_logits_fast.cpp:16-164 with
 // neural_network.py:201-210 and takes the legal set from the packed state (scalar-engine semantics).
@@ -502,9 +533,14 @@ extern "C" int lzb_tree_set_root_priors(const lzb_tree* tree, const float* prior
 }
 
 extern "C" int lzb_encode_inputs_packed(const uint64_t* states, int64_t n, int32_t layout, void* out, void* stream) {
-    LZB_REQUIRE(n >= 0 && (layout == 0 || layout == 1), "bad arguments");
+    LZB_REQUIRE(n >= 0 && (layout == 0 || layout == 1 || layout == 2), "bad arguments");
     if (n == 0) return LZB_OK;
     LZB_REQUIRE(states && out, "null pointer");
+    if (layout == 2) {
+        LZB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "out must be 16-byte aligned");
+        encode_inputs_c64_kernel<<<warp_grid(n), kThreads, 0, (cudaStream_t)stream>>>(states, n, reinterpret_cast<uint4*>(out));
+        return check_launch("encode_inputs_c64_kernel");
+    }
     if (layout == 0) encode_inputs_kernel<0><<<warp_grid(n), kThreads, 0, (cudaStream_t)stream>>>(states, n, out);
     else encode_inputs_kernel<1><<<warp_grid(n), kThreads, 0, (cudaStream_t)stream>>>(states, n, out);
     return check_launch("encode_inputs_kernel");

@@ -231,6 +231,11 @@ class FusedTrunk:
         w, b = self._fold_into_conv(m.stem_conv, m.stem_bn)
         self._set("stem_w", w)
         self._set("stem_b", b)
+        if self.use_tc and m.stem_conv.in_channels <= 64:     # stem as a K = 64 tcgen05 conv on zero-padded channels
+            w64 = torch.zeros((w.size(0), 64, 3, 3), dtype=w.dtype, device=w.device)
+            w64[:, :m.stem_conv.in_channels] = w
+            self._set("stem_wp", pack_conv_weight(w64))
+            self._set("stem_bf", b.float())
         for i, blk in enumerate(m.blocks):
             w, b = self._fold_into_conv(blk.conv1, blk.bn2)
             self._set(f"w1_{i}", w)
@@ -289,10 +294,18 @@ class FusedTrunk:
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         m, t = self.model, self._t
         nb = len(m.blocks)
-        xr = self._conv_bn_relu(x, m.stem_conv, "stem_w", "stem_b", "stem_s", "stem_t")     # x0 = relu(stem_bn(conv))
-        if nb == 0:
-            return self._bn_relu(xr, None, t["trunk_s"], t["trunk_t"], False)[1]
-        _, a = self._bn_relu(xr, None, t["s1_0"], t["t1_0"], False)                           # a0 = relu(bn1_0(x0))
+        if x.size(1) == 64 and m.stem_conv.in_channels != 64:
+            # channel-padded input (InferenceNet.new_input on the tcgen05 path): stem conv + stem_bn + ReLU and the
+            # first block's bn1 + ReLU in ONE launch (x0 and a0 are the two outputs of the epilogue)
+            if not (self.use_tc and "stem_wp" in t and nb > 0 and x.size(0) % 64 == 0):
+                raise RuntimeError("64-channel padded inputs need the tcgen05 conv path (128-channel trunk, batch % 64 == 0)")
+            xr, a = conv_bf16(x, t["stem_wp"], bias=t["stem_bf"], relu1=True, scale=t["s1_0"], shift=t["t1_0"],
+                              want_out2=True)
+        else:
+            xr = self._conv_bn_relu(x, m.stem_conv, "stem_w", "stem_b", "stem_s", "stem_t")  # x0 = relu(stem_bn(conv))
+            if nb == 0:
+                return self._bn_relu(xr, None, t["trunk_s"], t["trunk_t"], False)[1]
+            _, a = self._bn_relu(xr, None, t["s1_0"], t["t1_0"], False)                       # a0 = relu(bn1_0(x0))
         if self.use_tc and x.size(0) % 64 == 0:
             # 2 launches per residual block, no elementwise pass: the residual add, the next BatchNorm and the
             # ReLU are the epilogue of conv2; BatchNorm + ReLU after conv1 are folded weights + the epilogue of conv1
@@ -475,7 +488,13 @@ class InferenceNet:
             return heads_to_priors(states, lp1, lp2, lpm, vl, priors_out=priors_out, values_out=values_out)
 
     def new_input(self, n: int) -> torch.Tensor:
-        return torch.empty((n, 11, 6, 6), dtype=self.dtype, device=self.device,
+        """Input buffer for ``encode_inputs(..., "bf16_nhwc", out=...)``: [n,11,6,6] channels-last, or -- when the
+        whole network runs on our tcgen05 convs -- the same planes zero-padded to 64 channels ([n,64,6,6])."""
+        c = self.model.num_input_channels
+        if (self.trunk is not None and self.trunk.use_tc and "stem_wp" in self.trunk._t and len(self.model.blocks) > 0
+                and n % 64 == 0):
+            c = 64
+        return torch.empty((n, c, 6, 6), dtype=self.dtype, device=self.device,
                            memory_format=torch.channels_last).zero_()
 
     def capture(self, n: int, static_input: Optional[torch.Tensor] = None):

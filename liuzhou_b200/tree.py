@@ -170,7 +170,7 @@ class DeviceTreeBatch:
 
 def encode_inputs(packed: torch.Tensor, layout: str = "f32_nchw", out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """packed int64[n,4] -> network input. 'f32_nchw': float32[n,11,6,6]; 'bf16_nhwc': bfloat16[n,11,6,6] in
-    channels_last memory format."""
+    channels_last memory format (or, if `out` has 64 channels, the same planes zero-padded to [n,64,6,6])."""
     require_cuda(packed, "packed")
     dev = packed.device
     packed = packed.contiguous()
@@ -183,7 +183,9 @@ def encode_inputs(packed: torch.Tensor, layout: str = "f32_nchw", out: Optional[
         elif layout == "bf16_nhwc":
             if out is None:
                 out = torch.empty((n, 11, 6, 6), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
-            code = 1
+            if out.size(1) not in (11, 64) or out.dtype != torch.bfloat16:
+                raise RuntimeError("bf16_nhwc output must be bfloat16 [n,11,6,6] or channel-padded [n,64,6,6]")
+            code = 1 if out.size(1) == 11 else 2          # 2: planes zero-padded to 64 channels (tcgen05 stem conv)
         else:
             raise RuntimeError(f"unknown layout {layout}")
         check(lib().lzb_encode_inputs_packed(ptr(packed), i64(n), ctypes.c_int32(code), ptr(out), stream_ptr(dev)))

@@ -85,9 +85,14 @@ def test_trunk_and_heads_tc_path_matches_cudnn_path():
             m.bias.data.normal_(0.0, 0.1)
     net = InferenceNet(model, DEV)
     assert net.trunk.use_tc and net.heads.use_tc
-    x = net.new_input(128)
-    x.copy_((torch.rand((128, 11, 6, 6), device=DEV) > 0.6).to(x.dtype))
-    out_tc = [o.clone() for o in net._forward_eager(x)]
+    x64 = net.new_input(128)
+    assert x64.size(1) == 64                      # channel-padded input: the stem runs on our conv too
+    x = (torch.rand((128, 11, 6, 6), device=DEV) > 0.6).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x64[:, :11] = x
+    out_tc = [o.clone() for o in net._forward_eager(x64)]
+    out_tc11 = [o.clone() for o in net._forward_eager(x)]      # 11-channel input: cuDNN stem + our trunk convs
+    for a, b in zip(out_tc, out_tc11):
+        torch.testing.assert_close(a, b, rtol=5e-2, atol=5e-2)
     net.trunk.use_tc = net.heads.use_tc = False
     out_cudnn = [o.clone() for o in net._forward_eager(x)]
     ref = model.to(DEV).float().eval()
@@ -96,3 +101,15 @@ def test_trunk_and_heads_tc_path_matches_cudnn_path():
     for a, b, r in zip(out_tc, out_cudnn, out_ref):
         torch.testing.assert_close(a, b, rtol=5e-2, atol=5e-2)
         torch.testing.assert_close(a, r.float().reshape(a.shape), rtol=8e-2, atol=8e-2)
+
+
+def test_encode_inputs_channel_padded_layout():
+    from liuzhou_b200 import native
+    from liuzhou_b200.tree import encode_inputs
+
+    pb = native.PlayoutBatch(256, seed=3, device=DEV)
+    pb.run(max_steps=40)
+    x11 = encode_inputs(pb.packed, "bf16_nhwc")
+    x64 = torch.full((256, 64, 6, 6), 7.0, dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last)
+    encode_inputs(pb.packed, "bf16_nhwc", out=x64)
+    assert torch.equal(x64[:, :11], x11) and not x64[:, 11:].any()

@@ -26,7 +26,8 @@ m = buf[:2048][buf[:2048] > 0].astype(np.int64)
 p = buf[4096:][buf[4096:] > 0].astype(np.int64)
 t0 = m[0]
 e = e - t0
-print("epilogue (warp 2) [tfull ok, done] per tile:", [(int(a), int(b), int(b - a)) for a, b in zip(e[0::2], e[1::2])])
+print("epilogue (warp 2) per tile [tfull ok | +tmem ld | +chunk0 | +chunk1]:",
+      [(int(a), int(b - a), int(c - b), int(d - c)) for a, b, c, d in zip(e[0::4], e[1::4], e[2::4], e[3::4])])
 print("MMA thread stamps:", len(m), "producer stamps:", len(p))
 m = m - t0
 p = p - t0
