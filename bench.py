@@ -416,6 +416,50 @@ def cpu_selfplay_baseline(budget_s: float = 20.0, trees: int = 32, sims: int = S
                       f"+ fp32 PyTorch ChessNet on {cores} host threads (subtree reuse as in the reference)"}
 
 
+def time_trunk_conv(net, n, stream, reps: int = 30) -> dict:
+    """One trunk layer of the network = one launch of conv_tc_kernel<9,2>; both epilogue variants (conv1: bias +
+    ReLU; conv2: residual + BatchNorm + ReLU, two outputs), each timed with CUDA events over graph replays."""
+    import torch
+
+    from liuzhou_b200.net import conv_bf16
+
+    t = net.trunk._t
+    if not (net.trunk is not None and net.trunk.use_tc and n % 64 == 0):
+        return {"ms": float("nan"), "ms_conv1": float("nan"), "ms_conv2": float("nan"), "tflops": float("nan"),
+                "flops_per_state": 0.0, "traffic_bytes": None}
+    dev = net.device
+    cl = torch.channels_last
+    a = torch.randn((n, 128, 6, 6), device=dev, dtype=torch.bfloat16).contiguous(memory_format=cl)
+    res = torch.randn_like(a)
+    o1, o2 = torch.empty_like(a), torch.empty_like(a)
+
+    def replay_ms(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g.replay()
+        e0.record(stream)
+        for _ in range(reps):
+            g.replay()
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms1 = replay_ms(lambda: conv_bf16(a, t["wp1_0"], bias=t["bf1_0"], relu1=True, out1=o1))
+    ms2 = replay_ms(lambda: conv_bf16(a, t["wp2_0"], residual=res, scale=t["s1_1"], shift=t["t1_1"], want_out2=True,
+                                      out1=o1, out2=o2))
+    flops_per_state = 2.0 * 36 * 128 * 128 * 9
+    ms = 0.5 * (ms1 + ms2)
+    # per-launch DRAM traffic of the 4,096-state launch measured by ncu (38.07 MB read + 2.78 MB written), scaled by n
+    traffic = (38.074e6 + 2.776e6) * n / 4096.0
+    return {"ms": ms, "ms_conv1": ms1, "ms_conv2": ms2, "tflops": n * flops_per_state / (ms / 1e3) / 1e12,
+            "flops_per_state": flops_per_state, "traffic_bytes": traffic}
+
+
 def run_selfplay(args, world, rank, local_rank):
     import torch
 
@@ -469,9 +513,10 @@ def run_selfplay(args, world, rank, local_rank):
     e1.synchronize()
     barrier_sync(world)
     clocks = sampler.stop() if rank == 0 else {}
-    # graph replays re-launch the captured kernels: count them (4 of ours per wave + root step + per-ply kernels)
+    # graph replays re-launch the captured kernels: our kernels inside the root / wave graphs were counted at capture
     waves = stepper.mcts.waves
-    launches = (_lib.launch_count() - launches0) + args.steps * (waves * 4 + 4)
+    launches = (_lib.launch_count() - launches0) + args.steps * (waves * stepper.mcts.wave_graph_launches
+                                                                 + stepper.mcts.root_graph_launches)
     elapsed_ms = max_over_ranks(e0.elapsed_time(e1), world)
     positions = sum_over_ranks(float(games * args.steps), world)
     value = positions / (elapsed_ms / 1e3)
@@ -506,6 +551,7 @@ def run_selfplay(args, world, rank, local_rank):
     wave_ms = w0.elapsed_time(w1) / reps
     tflops = slots * net.flops_per_state / (fwd_ms / 1e3) / 1e12
     tree_stats = stepper.mcts.tree.stats()
+    conv = time_trunk_conv(net, slots, stream)
 
     # e2e: the same ply through host buffers -- states (reference byte layout) H2D from pinned memory, search +
     # step on the device, new states + this ply's trajectory rows (2,692 B/position) D2H into pinned memory.
@@ -546,19 +592,28 @@ def run_selfplay(args, world, rank, local_rank):
         "mcts_sims_per_sec": value * sims, "network_evals_per_sec": evals * world / (elapsed_ms / 1e3),
         "config": {"workload": "v1 wave-batched MCTS self-play (BASELINE configs[2])", "games_per_gpu": games,
                    "sims_per_move": sims, "search": "full tree on device (select/expand/backup kernels)",
-                   "leaves_per_wave": k, "net": "ChessNet 128ch x 10 blocks, random init, seed 20260314",
+                   "leaves_per_wave": k, "net": "ChessNet 128ch x 10 blocks, random init, seed 20260314; all 22 "
+                   "convolutions per forward are our tcgen05 kernel, no cuDNN on the path",
                    "step": "one ply of every game; finished games refilled; batch pre-diversified by 0..120 random plies",
                    "dirichlet_noise": True, "temperature": "1.0 -> 0.1 at ply 10", "exploration_weight": 1.0,
                    "l2": "working set per step (node arena > 1 GB) exceeds the 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "positions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
-                     "traffic": None, "peak_kind": peak_kind + " (sustained bf16)",
-                     "kernel": "ChessNet forward (PyTorch/cuDNN bf16, CUDA graph) at the wave batch",
-                     "kernel_ms": fwd_ms, "units_per_launch": slots, "flops_per_unit": net.flops_per_state,
+        # dominant kernel: our tcgen05 implicit-GEMM convolution (20 of the 22 launches per forward are this 3x3
+        # 128->128 instance); achieved = algorithmic FLOPs of one launch / its CUDA-event duration in a graph replay
+        "roofline": {"bound": "tensor", "achieved": conv["tflops"], "peak": peak, "unit": "TFLOP/s",
+                     "frac": conv["tflops"] / peak, "traffic": conv["traffic_bytes"],
+                     "peak_kind": peak_kind + " (sustained bf16, cuBLAS)",
+                     "kernel": "conv_tc_kernel<9,2> (csrc/lz_conv.cu: 3x3 128->128 conv, bf16 tcgen05.mma cta_group::2, "
+                               "TMA im2col, fused bias/residual/BN/ReLU epilogue)",
+                     "kernel_ms": conv["ms"], "kernel_ms_conv1_epilogue": conv["ms_conv1"],
+                     "kernel_ms_conv2_epilogue": conv["ms_conv2"], "units_per_launch": slots,
+                     "flops_per_unit": conv["flops_per_state"], "launches_per_forward": 20,
+                     "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r01_conv_tc_ncu_full.csv",
+                     "forward_ms": fwd_ms, "forward_tflops": tflops, "forward_frac_of_peak": tflops / peak,
                      "wave_ms": wave_ms, "tree_kernels_ms_per_wave": max(0.0, wave_ms - fwd_ms),
-                     "share_of_step": fwd_ms * waves / (elapsed_ms / args.steps)},
+                     "share_of_step": 10 * (conv["ms_conv1"] + conv["ms_conv2"]) * (waves + 1) / (elapsed_ms / args.steps)},
         "tree": tree_stats,
         "cpu_baseline": cpu,
     }

@@ -64,6 +64,7 @@ class TreeMCTS:
         self._wave_val = self._root_val if k == 1 else torch.zeros((slots,), dtype=torch.float32, device=dev)
         self._wave_graph: Optional[torch.cuda.CUDAGraph] = None
         self._root_graph: Optional[torch.cuda.CUDAGraph] = None
+        self.root_graph_launches = self.wave_graph_launches = 0
         self.evals = 0
 
     # one network evaluation of the pending leaves + expansion (+ backup)
@@ -93,12 +94,18 @@ class TreeMCTS:
             self._wave_step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        from ._lib import launch_count
+
+        # kernels of OURS inside each graph (every replay launches them again; bench.py's gpu_launches)
+        c0 = launch_count()
         self._root_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._root_graph):
             self._root_step()
+        c1 = launch_count()
         self._wave_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._wave_graph, pool=self._root_graph.pool()):
             self._wave_step()
+        self.root_graph_launches, self.wave_graph_launches = c1 - c0, launch_count() - c1
 
     def _apply_root_noise(self) -> None:
         """Dirichlet(alpha) over each root's legal actions mixed with weight epsilon (portable_cpp_mcts.py:180-199,
