@@ -641,6 +641,62 @@ def run_reference_selfplay(args):
     }
 
 
+# ----------------------------------------------------------------------------------------------------
+# workload: config 5 -- checkpoint eval vs the random agent (2,000 games, 64 sims) + 4-checkpoint round robin
+# ----------------------------------------------------------------------------------------------------
+def run_eval(args, world, rank, local_rank):
+    import torch
+
+    from liuzhou_b200 import _lib
+    from liuzhou_b200.evaluate import play_match, round_robin_tournament
+    from liuzhou_b200.net import ChessNet, InferenceNet
+
+    dev = torch.device("cuda", local_rank)
+    games, sims = args.eval_games, args.eval_sims
+    nets = []
+    for sd in (1, 2, 3, 4):           # four random-init checkpoints, seeds 1-4
+        torch.manual_seed(sd)
+        nets.append(InferenceNet(ChessNet(), dev))
+    play_match(nets[0], None, num_games=128, mcts_simulations=sims, device=dev, seed=0)     # warm-up: graph capture
+    barrier_sync(world)
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    stream = torch.cuda.current_stream(dev)
+    e0.record(stream)
+    stats = play_match(nets[0], None, num_games=games, mcts_simulations=sims, temperature=0.0, device=dev,
+                       seed=SEED + rank)
+    e1.record(stream)
+    rr = round_robin_tournament(nets, games_per_match=args.eval_rr_games, mcts_simulations=sims, temperature=1.0,
+                                sample_moves=True, device=dev, seed=SEED + rank)
+    e2.record(stream)
+    e2.synchronize()
+    barrier_sync(world)
+    clocks = sampler.stop() if rank == 0 else {}
+    ms_eval = max_over_ranks(e0.elapsed_time(e1), world)
+    ms_rr = max_over_ranks(e1.elapsed_time(e2), world)
+    total_games = sum_over_ranks(float(stats.total_games), world)
+    plies = sum_over_ranks(float(stats.plies), world)
+    if rank != 0:
+        return None
+    return {
+        "metric": "eval_games_per_sec", "value": total_games / (ms_eval / 1e3), "unit": "games/s", "n_gpus": world,
+        "steps": 1, "warmup": 1, "ms_per_step": ms_eval, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "checkpoint eval vs random agent + 4-checkpoint round robin (BASELINE configs[4])",
+                   "games_per_gpu": stats.total_games, "sims_per_move": sims, "temperature": 0.0,
+                   "round_robin": f"4 random-init checkpoints (seeds 1-4), {args.eval_rr_games} games per pairing, T=1 sampled"},
+        "clocks": clocks, "positions_per_sec": plies / (ms_eval / 1e3),
+        "eval": {"wins": stats.wins, "losses": stats.losses, "draws": stats.draws, "plies": stats.plies,
+                 "searched_positions": stats.searches, "color_breakdown": stats.color_breakdown},
+        "round_robin": {"ms": ms_rr, "standings": [{k: r[k] for k in ("name", "match_points", "game_wins", "game_losses",
+                                                                        "game_draws")} for r in rr["standings"]]},
+        "gpu_launches": int(_lib.launch_count() - launches0),
+    }
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--games", type=int, default=SELFPLAY_GAMES)
@@ -651,7 +707,10 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["playout", "selfplay"], default="selfplay")
+    ap.add_argument("--workload", choices=["playout", "selfplay", "eval"], default="selfplay")
+    ap.add_argument("--eval-games", type=int, default=2000)
+    ap.add_argument("--eval-sims", type=int, default=64)
+    ap.add_argument("--eval-rr-games", type=int, default=256)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
 
@@ -663,7 +722,7 @@ def main() -> int:
         return 0
 
     world, rank, local_rank = dist_setup(args.gpus)
-    fn = run_selfplay if args.workload == "selfplay" else run_playout
+    fn = {"selfplay": run_selfplay, "playout": run_playout, "eval": run_eval}[args.workload]
     line = fn(args, world, rank, local_rank)
     if rank == 0:
         print(json.dumps(line), flush=True)
