@@ -223,14 +223,19 @@ typedef struct {
 /* Reset the arena to `num_trees` unexpanded roots (PortableTreeBatch ctor, :443-459). active u8[T] or NULL. */
 LZB_API int lzb_tree_init_roots(const lzb_tree *tree, const uint64_t *root_states, const uint8_t *active, void *stream);
 /* prepare_roots / select_leaves (:483-552): per slot (tree*K + k): leaf_node i32 (-1 if none), leaf_status i32
- * (0 = evaluate, 1 = terminal/inactive, already backed up, 2 = duplicate of a pending leaf), leaf_states u64[.,4]. */
+ * (0 = evaluate, 1 = terminal/inactive, already backed up, 2 = duplicate of a pending leaf), leaf_states u64[.,4].
+ * leaf_path i32[slots][LZB_TREE_PATH_STRIDE] (optional, may be NULL): the descent's node path ([0,32) node per depth,
+ * [32] depth or -1 if deeper than 32, [33] colour bits) so that lzb_tree_expand_backup can back up the whole path in
+ * one memory round trip instead of walking the parent chain. */
+#define LZB_TREE_PATH_STRIDE 34
 LZB_API int lzb_tree_select(const lzb_tree *tree, int32_t K, double exploration_weight, double virtual_loss,
-                            int32_t *leaf_node, int32_t *leaf_status, uint64_t *leaf_states, void *stream);
+                            int32_t *leaf_node, int32_t *leaf_status, uint64_t *leaf_states, int32_t *leaf_path,
+                            void *stream);
 /* complete_pending (:554-590): expand every status-0 leaf with dense priors f32[T*K,220] / values f32[T*K],
  * then back up (do_backup = 0 for roots, :575). */
 LZB_API int lzb_tree_expand_backup(const lzb_tree *tree, int32_t K, const int32_t *leaf_node, const int32_t *leaf_status,
                                    const float *priors, const float *values, int32_t do_backup, double virtual_loss,
-                                   void *stream);
+                                   const int32_t *leaf_path, void *stream);
 /* root_outputs + root_priors (:592-624,:664-737); any output pointer may be NULL. */
 LZB_API int lzb_tree_root_outputs(const lzb_tree *tree, int32_t *visit_counts, float *root_action_values,
                                   float *root_values, uint8_t *legal_masks, uint8_t *terminal, float *root_priors,

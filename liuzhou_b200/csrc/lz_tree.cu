@@ -84,6 +84,21 @@ __device__ __forceinline__ void backup_path(const lzb_tree& A, int node, double 
         node = p;
     }
 }
+// The same backup with the path known up front (recorded during the descent): lane j owns the node at depth j, so
+// the whole chain is ONE round trip to HBM instead of one per level.  The value flips sign once per colour change
+// between a node and its parent, i.e. node j receives +v iff it has the leaf's colour -- the parity of the colour
+// changes between j and the leaf.  Each node gets exactly the fp64 add the sequential walk would do (bit-identical).
+constexpr int kPathLanes = 32;                 // deeper paths fall back to the parent walk
+constexpr int kPathStride = kPathLanes + 2;    // [0,32) nodes | [32] depth (-1: use the parent walk) | [33] colour bits
+__device__ __forceinline__ void backup_recorded(const lzb_tree& A, int lane, int path_node, uint32_t white_mask, int depth,
+                                                double v) {
+    if (lane <= depth) {
+        const bool same = ((white_mask >> lane) & 1u) == ((white_mask >> depth) & 1u);
+        A.visit[path_node] += 1;
+        A.value_sum[path_node] = __dadd_rn(A.value_sum[path_node], same ? v : -v);
+    }
+}
+
 // Virtual loss for K > 1 leaves per tree per wave: every node on the path gets +1 visit; its value sum moves
 // by `vl` AGAINST the player who chose it, so q seen from the parent always drops.  sign = +1 apply, -1 revert.
 __device__ __forceinline__ void virtual_loss_path(const lzb_tree& A, int node, double vl, int sign) {
@@ -104,9 +119,9 @@ constexpr int kLeafEval = 0;       // needs a network evaluation, then expand (+
 constexpr int kLeafDone = 1;       // terminal / inactive: nothing to evaluate (backup already done)
 constexpr int kLeafDuplicate = 2;  // K > 1 only: same leaf already pending in this wave (simulation dropped)
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)      // 4 x 8 warps per SM: all 4,096 trees of a wave resident at once
 tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restrict__ leaf_node,
-                   int32_t* __restrict__ leaf_status, uint64_t* __restrict__ leaf_states) {
+                   int32_t* __restrict__ leaf_status, uint64_t* __restrict__ leaf_states, int32_t* __restrict__ leaf_path) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
@@ -119,25 +134,32 @@ tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restr
                 if (lane == 0) { leaf_node[slot] = -1; leaf_status[slot] = kLeafDone; }
                 continue;
             }
-            // SelectPath :862-874
+            // SelectPath :862-874.  One dependent HBM round trip per level: the sibling scan also fetches each
+            // child's first_child / info / visit, so the next level needs nothing else from the chosen child.
+            int fc = A.first_child[node], nv = A.visit[node];
+            int depth = 0, path_node = lane == 0 ? node : -1;
+            bool path_white = lane == 0 && (inf & kInfoWhite);
             while ((inf & kInfoExpanded) && info_nchild(inf) > 0 && !(inf & kInfoTerminal)) {
-                const int fc = A.first_child[node], n = info_nchild(inf);
-                const int nv = A.visit[node];
+                const int n = info_nchild(inf);
                 const double sqrt_total = sqrt((double)(nv > 1 ? nv : 1));
                 const uint32_t node_white = inf & kInfoWhite;
                 double best = -INFINITY;
-                int best_i = 0x7fffffff;
+                int best_i = 0x7fffffff, b_vc = 0, b_fc = -1;
+                uint32_t b_inf = 0;
                 for (int i = lane; i < n; i += 32) {                 // SelectChild :832-860
                     const int c = fc + i;
                     const int vc = A.visit[c];
+                    const uint32_t ci = A.info[c];
+                    const int cfc = A.first_child[c];
+                    const double pr = A.prior[c];
                     double q = 0.0;
                     if (vc > 0) {
                         q = __ddiv_rn(A.value_sum[c], (double)vc);
-                        if ((A.info[c] & kInfoWhite) != node_white) q = -q;
+                        if ((ci & kInfoWhite) != node_white) q = -q;
                     }
-                    const double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, A.prior[c]), sqrt_total), (double)(1 + vc));
+                    const double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, pr), sqrt_total), (double)(1 + vc));
                     const double score = __dadd_rn(q, u);
-                    if (score > best || (score == best && i < best_i)) { best = score; best_i = i; }
+                    if (score > best || (score == best && i < best_i)) { best = score; best_i = i; b_vc = vc; b_fc = cfc; b_inf = ci; }
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
@@ -146,23 +168,33 @@ tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restr
                     if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
                 }
                 if (best_i == 0x7fffffff) break;                     // child == nullptr
+                const int owner = best_i & 31;                       // that lane's local best IS the global best
                 node = fc + best_i;
-                inf = A.info[node];
+                inf = __shfl_sync(0xffffffffu, b_inf, owner);
+                nv = __shfl_sync(0xffffffffu, b_vc, owner);
+                fc = __shfl_sync(0xffffffffu, b_fc, owner);
+                ++depth;
+                if (depth < kPathLanes && lane == depth) { path_node = node; path_white = (inf & kInfoWhite) != 0; }
             }
+            const bool recorded = depth < kPathLanes;
+            const uint32_t white_mask = __ballot_sync(0xffffffffu, path_white);
             int status;
             if (inf & kInfoTerminal) {                               // :527-532
+                double tv = 0.0;
                 if (lane == 0) {
                     State<int> s;
                     unpack(load_packed(A.state, node), s);
-                    backup_path(A, node, (inf & kInfoNoLegal) ? -1.0 : terminal_value(s));
+                    tv = (inf & kInfoNoLegal) ? -1.0 : terminal_value(s);
                     atomicAdd(&A.counters[3], 1);
                 }
+                tv = __shfl_sync(0xffffffffu, tv, 0);
+                if (recorded) backup_recorded(A, lane, path_node, white_mask, depth, tv);
+                else if (lane == 0) backup_path(A, node, tv);
                 status = kLeafDone;
             } else if ((inf & kInfoExpanded) && info_nchild(inf) == 0) {   // :533-538
-                if (lane == 0) {
-                    A.info[node] = inf | kInfoTerminal | kInfoNoLegal;
-                    backup_path(A, node, -1.0);
-                }
+                if (lane == 0) A.info[node] = inf | kInfoTerminal | kInfoNoLegal;
+                if (recorded) backup_recorded(A, lane, path_node, white_mask, depth, -1.0);
+                else if (lane == 0) backup_path(A, node, -1.0);
                 status = kLeafDone;
             } else if (inf & kInfoPending) {
                 status = kLeafDuplicate;
@@ -172,6 +204,13 @@ tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restr
                     A.info[node] = inf | kInfoPending;
                     store_packed(leaf_states, slot, load_packed(A.state, node));
                     if (K > 1 && vl > 0.0) virtual_loss_path(A, node, vl, +1);
+                }
+                if (leaf_path) {                                     // the path travels to the expand / backup kernel
+                    leaf_path[slot * kPathStride + lane] = path_node;
+                    if (lane == 0) {
+                        leaf_path[slot * kPathStride + kPathLanes] = recorded ? depth : -1;
+                        leaf_path[slot * kPathStride + kPathLanes + 1] = (int32_t)white_mask;
+                    }
                 }
             }
             if (lane == 0) { leaf_node[slot] = status == kLeafEval ? node : -1; leaf_status[slot] = status; }
@@ -184,7 +223,8 @@ tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restr
 // order (deterministic).  priors f32[slots,220] dense over the 220-d action space, values f32[slots].
 __global__ void __launch_bounds__(kThreads)
 tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, const int32_t* __restrict__ leaf_status,
-                   const float* __restrict__ priors, const float* __restrict__ values, int do_backup, double vl) {
+                   const float* __restrict__ priors, const float* __restrict__ values, int do_backup, double vl,
+                   const int32_t* __restrict__ leaf_path) {
     __shared__ float s_pri[kWarpsPerBlock][kActionDim];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + w;
@@ -194,6 +234,14 @@ tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, con
             const int64_t slot = t * K + k;
             if (leaf_status[slot] != kLeafEval) continue;
             const int node = leaf_node[slot];
+            // the descent's path (for the one-round-trip backup): fetched up front, used at the end
+            int path_node = -1, path_depth = -1;
+            uint32_t path_white = 0;
+            if (do_backup && leaf_path) {
+                path_node = leaf_path[slot * kPathStride + lane];
+                path_depth = leaf_path[slot * kPathStride + kPathLanes];
+                path_white = (uint32_t)leaf_path[slot * kPathStride + kPathLanes + 1];
+            }
             State<int> s;
             unpack(load_packed(A.state, node), s);
             Legal L;
@@ -262,7 +310,10 @@ tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, con
                 }
             }
             __syncwarp();
-            if (do_backup && lane == 0) backup_path(A, node, value);
+            if (do_backup) {
+                if (path_depth >= 0) backup_recorded(A, lane, path_node, path_white, path_depth, value);
+                else if (lane == 0) backup_path(A, node, value);
+            }
             __syncwarp();
         }
     }
@@ -492,26 +543,26 @@ extern "C" int lzb_tree_init_roots(const lzb_tree* tree, const uint64_t* root_st
 }
 
 extern "C" int lzb_tree_select(const lzb_tree* tree, int32_t K, double c_puct, double virtual_loss, int32_t* leaf_node,
-                               int32_t* leaf_status, uint64_t* leaf_states, void* stream) {
+                               int32_t* leaf_status, uint64_t* leaf_states, int32_t* leaf_path, void* stream) {
     int rc = check_tree(tree);
     if (rc) return rc;
     LZB_REQUIRE(K >= 1 && K <= 64, "leaves per tree per wave must be in [1, 64]");
     LZB_REQUIRE(c_puct >= 0.0 && c_puct == c_puct, "exploration_weight must be finite and non-negative");
     LZB_REQUIRE(leaf_node && leaf_status && leaf_states, "null output");
     tree_select_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(
-        *tree, K, c_puct, virtual_loss, leaf_node, leaf_status, leaf_states);
+        *tree, K, c_puct, virtual_loss, leaf_node, leaf_status, leaf_states, leaf_path);
     return check_launch("tree_select_kernel");
 }
 
 extern "C" int lzb_tree_expand_backup(const lzb_tree* tree, int32_t K, const int32_t* leaf_node,
                                       const int32_t* leaf_status, const float* priors, const float* values,
-                                      int32_t do_backup, double virtual_loss, void* stream) {
+                                      int32_t do_backup, double virtual_loss, const int32_t* leaf_path, void* stream) {
     int rc = check_tree(tree);
     if (rc) return rc;
     LZB_REQUIRE(K >= 1 && K <= 64, "leaves per tree per wave must be in [1, 64]");
     LZB_REQUIRE(leaf_node && leaf_status && priors && values, "null input");
     tree_expand_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(
-        *tree, K, leaf_node, leaf_status, priors, values, do_backup, virtual_loss);
+        *tree, K, leaf_node, leaf_status, priors, values, do_backup, virtual_loss, leaf_path);
     return check_launch("tree_expand_kernel");
 }
 

@@ -60,6 +60,8 @@ class DeviceTreeBatch:
             self.leaf_node = torch.full((slots,), -1, dtype=torch.int32, device=dev)
             self.leaf_status = torch.full((slots,), LEAF_DONE, dtype=torch.int32, device=dev)
             self.leaf_states = torch.zeros((slots, 4), dtype=torch.int64, device=dev)
+            # descent paths (LZB_TREE_PATH_STRIDE ints per slot): written by select, consumed by expand + backup
+            self.leaf_path = torch.full((slots, 34), -1, dtype=torch.int32, device=dev)
             if self.k == 1:
                 self.root_leaf_node, self.root_leaf_status, self.root_leaf_states = (
                     self.leaf_node, self.leaf_status, self.leaf_states)
@@ -90,7 +92,7 @@ class DeviceTreeBatch:
             check(lib().lzb_tree_select(ctypes.byref(self._struct), ctypes.c_int32(k),
                                         ctypes.c_double(self.exploration_weight), ctypes.c_double(self.virtual_loss),
                                         ptr(self.leaf_node), ptr(self.leaf_status), ptr(self.leaf_states),
-                                        stream_ptr(self.device)))
+                                        ptr(self.leaf_path), stream_ptr(self.device)))
 
     def prepare_roots(self) -> None:
         """Unexpanded, non-terminal roots become the pending leaves (one slot per tree, whatever K is).
@@ -99,7 +101,7 @@ class DeviceTreeBatch:
             check(lib().lzb_tree_select(ctypes.byref(self._struct), ctypes.c_int32(1),
                                         ctypes.c_double(self.exploration_weight), ctypes.c_double(0.0),
                                         ptr(self.root_leaf_node), ptr(self.root_leaf_status),
-                                        ptr(self.root_leaf_states), stream_ptr(self.device)))
+                                        ptr(self.root_leaf_states), ptr(None), stream_ptr(self.device)))
         self._pending_is_root = True
 
     def select_leaves(self) -> None:
@@ -130,7 +132,8 @@ class DeviceTreeBatch:
         with torch.cuda.device(self.device):
             check(lib().lzb_tree_expand_backup(ctypes.byref(self._struct), ctypes.c_int32(k), ptr(node), ptr(status),
                                                ptr(p), ptr(v), ctypes.c_int32(0 if root else 1),
-                                               ctypes.c_double(self.virtual_loss), stream_ptr(self.device)))
+                                               ctypes.c_double(self.virtual_loss), ptr(None if root else self.leaf_path),
+                                               stream_ptr(self.device)))
 
     def root_outputs(self, with_priors: bool = True) -> dict:
         t, dev = self.num_trees, self.device
