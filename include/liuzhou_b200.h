@@ -284,7 +284,10 @@ LZB_API int lzb_conv_bf16(const void *x, const void *w, int64_t n, int32_t cin, 
  * log-softmax, value MLP) + bucket expectation (:201-210) + masked softmax over the legal actions of the
  * packed state (project_policy_logits_fast.cpp:16-164) in one kernel.
  * pv bf16[n,36,pc+vc] = relu(bn1(conv1x1)) of both heads (policy channels first); weights fp32, transposed:
- * wgl_t[3pc][pc], wout[3][pc], wfc1_t[3vc][mlp], wfc2_t[mlp][bins]. Any output may be NULL:
+ * wout[3][pc] plain; the three dense layers (gpool_linear [3pc -> pc], fc1 [3vc -> mlp], fc2 [mlp -> bins]) come
+ * pre-packed in mma.sync m16n8k8 B-fragment order, TF32-rounded: w*_t = float2[ceil(N/8)][ceil(K/8)][32] with
+ * element (nt, ks, lane) = (W[n][k], W[n][k + 4]), n = nt*8 + lane/4, k = ks*8 + lane%4, zero outside [N) x [K)
+ * (liuzhou_b200.net.pack_mma_b builds it from the nn.Linear weight [N][K]). Any output may be NULL:
  * priors f32[n,220] (needs states), values f32[n], log_heads f32[n,3,36], value_logits f32[n,bins]. */
 LZB_API int lzb_heads_tail(const void *pv, int64_t n, int32_t pc, int32_t vc, int32_t mlp, int32_t bins,
                            const float *wgl_t, const float *bn2_scale, const float *bn2_shift, const float *wout,

@@ -107,6 +107,32 @@ struct HeadsParams {
     const uint64_t* states; float *priors, *values, *log_heads, *value_logits;
 };
 
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+// C[8 states x 8 outputs] += A[8 x K] * B[K x 8] for one n-tile.  featT = features transposed in shared memory,
+// [K][kTile] fp32 (A fragment: a0 = (row lane/4, k lane%4), a2 = (row lane/4, k lane%4 + 4); rows 8-15 are zero
+// padding).  wfrag = this n-tile's packed B fragments: [k_step][lane] float2 = (B[k lane%4][n lane/4], B[k lane%4 + 4][..]).
+// Result: c0 / c1 = C[row lane/4][col 2*(lane%4) (+1)].
+__device__ __forceinline__ void mma_rows8(const float* __restrict__ wfrag, int ks_n, int K, const float* featT, int lane,
+                                          float& c0, float& c1) {
+    float c2 = 0.0f, c3 = 0.0f;
+    const int kq = lane & 3, row = lane >> 2;
+#pragma unroll 4
+    for (int ks = 0; ks < ks_n; ++ks) {
+        const float2 b = __ldg(reinterpret_cast<const float2*>(wfrag) + ks * 32 + lane);
+        const int k0 = ks * 8 + kq;
+        const uint32_t a0 = k0 < K ? to_tf32(featT[k0 * kTile + row]) : 0u;
+        const uint32_t a2 = k0 + 4 < K ? to_tf32(featT[(k0 + 4) * kTile + row]) : 0u;
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                     "{%0, %1, %2, %3};"
+                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                     : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)));
+    }
+}
+
 __global__ void __launch_bounds__(kHeadsThreads, 4)
 heads_tail_kernel(HeadsParams P) {
     __shared__ __align__(16) float poolT_p[3 * kMaxHeadCh][kTile];   // [feature][state]
@@ -128,69 +154,91 @@ heads_tail_kernel(HeadsParams P) {
         const int ns = (int)min((int64_t)kTile, P.n - base);
         __syncthreads();
         // 1. global pooling per (state, channel): mean / max / std (biased variance + 1e-6)  neural_network.py:68-81
-        //    thread -> (state, channel): 36 independent loads in flight, consecutive channels across the warp
-        for (int idx = t; idx < kTile * c2; idx += kHeadsThreads) {
-            const int s = idx / c2, ch = idx - s * c2;
-            float r0 = 0.0f, r1 = 0.0f, r2 = 1e-3f;
-            if (s < ns) {
-                const __nv_bfloat16* src = P.pv + (base + s) * 36 * c2 + ch;
-                float x[36], sum = 0.0f, mx = -INFINITY;
-#pragma unroll
-                for (int cell = 0; cell < 36; ++cell) { x[cell] = __bfloat162float(src[cell * c2]); sum += x[cell]; mx = fmaxf(mx, x[cell]); }
-                const float mean = sum * (1.0f / 36.0f);
-                float var = 0.0f;
-#pragma unroll
-                for (int cell = 0; cell < 36; ++cell) { const float d = x[cell] - mean; var = fmaf(d, d, var); }
-                r0 = mean; r1 = mx; r2 = sqrtf(var * (1.0f / 36.0f) + 1e-6f);
-            }
-            if (ch < pc) { poolT_p[ch][s] = r0; poolT_p[pc + ch][s] = r1; poolT_p[2 * pc + ch][s] = r2; }
-            else { const int cv = ch - pc; poolT_v[cv][s] = r0; poolT_v[vc + cv][s] = r1; poolT_v[2 * vc + cv][s] = r2; }
-        }
-        __syncthreads();
-        // 2a. g = gpool_linear(pooled_p) (no bias): thread -> (output j, group of 2 states)
+        //    thread -> (state, channel octet, half of the board): 18 independent 16-byte loads, one pass (sum, sum of
+        //    squares, max in fp32); the two halves sit in adjacent lanes and meet by shuffle.
         {
-            const int j = t & (kMaxHeadCh - 1), sg = t >> 6;          // 4 groups x 2 states
-            if (j < pc) {
-                float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll 4
-                for (int k = 0; k < 3 * pc; ++k) {
-                    const float w = __ldg(P.wgl_t + k * pc + j);
-                    const float2 p = *reinterpret_cast<const float2*>(&poolT_p[k][2 * sg]);
-                    a0 = fmaf(w, p.x, a0); a1 = fmaf(w, p.y, a1);
+            const int octets = c2 >> 3, items = kTile * octets * 2;
+            for (int idx0 = 0; idx0 < items; idx0 += kHeadsThreads) {
+                const int idx = idx0 + t;
+                const bool valid = idx < items;
+                const int hf = idx & 1, so = idx >> 1, s = valid ? so / octets : 0, o = valid ? so - s * octets : 0;
+                float sm[8], sq[8], mx[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { sm[c] = 0.0f; sq[c] = 0.0f; mx[c] = -INFINITY; }
+                if (valid && s < ns) {
+                    const uint4* src = reinterpret_cast<const uint4*>(P.pv + ((base + s) * 36 + hf * 18) * c2 + o * 8);
+                    const int stride = c2 >> 3;                    // uint4 per cell
+#pragma unroll
+                    for (int cell = 0; cell < 18; ++cell) {
+                        const uint4 raw = __ldg(src + cell * stride);
+                        const uint32_t wv[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const float lo = __uint_as_float(wv[h] << 16), hi = __uint_as_float(wv[h] & 0xffff0000u);
+                            sm[2 * h] += lo; sq[2 * h] = fmaf(lo, lo, sq[2 * h]); mx[2 * h] = fmaxf(mx[2 * h], lo);
+                            sm[2 * h + 1] += hi; sq[2 * h + 1] = fmaf(hi, hi, sq[2 * h + 1]); mx[2 * h + 1] = fmaxf(mx[2 * h + 1], hi);
+                        }
+                    }
                 }
-                g[2 * sg][j] = a0; g[2 * sg + 1][j] = a1;
-            }
-        }
-        // 2b. hid = relu(fc1(pooled_v)): thread -> (output m, group of 4 states)
-        {
-            const int m = t & (kMaxMlp - 1), sg = t >> 7;             // 2 groups x 4 states
-            if (m < mlp) {
-                const float b = __ldg(P.bfc1 + m);
-                float a0 = b, a1 = b, a2 = b, a3 = b;
-#pragma unroll 4
-                for (int k = 0; k < 3 * vc; ++k) {
-                    const float w = __ldg(P.wfc1_t + k * mlp + m);
-                    const float4 p = *reinterpret_cast<const float4*>(&poolT_v[k][4 * sg]);
-                    a0 = fmaf(w, p.x, a0); a1 = fmaf(w, p.y, a1); a2 = fmaf(w, p.z, a2); a3 = fmaf(w, p.w, a3);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    sm[c] += __shfl_xor_sync(0xffffffffu, sm[c], 1);
+                    sq[c] += __shfl_xor_sync(0xffffffffu, sq[c], 1);
+                    mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], 1));
                 }
-                *reinterpret_cast<float4*>(&hidT[m][4 * sg]) =
-                    make_float4(fmaxf(a0, 0.0f), fmaxf(a1, 0.0f), fmaxf(a2, 0.0f), fmaxf(a3, 0.0f));
+                if (valid && hf == 0) {
+                    const bool live = s < ns;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int ch = o * 8 + c;
+                        const float mean = sm[c] * (1.0f / 36.0f);
+                        const float var = fmaxf(fmaf(-mean, mean, sq[c] * (1.0f / 36.0f)), 0.0f);
+                        const float r0 = live ? mean : 0.0f, r1 = live ? mx[c] : 0.0f, r2 = live ? sqrtf(var + 1e-6f) : 1e-3f;
+                        if (ch < pc) { poolT_p[ch][s] = r0; poolT_p[pc + ch][s] = r1; poolT_p[2 * pc + ch][s] = r2; }
+                        else { const int cv = ch - pc; poolT_v[cv][s] = r0; poolT_v[vc + cv][s] = r1; poolT_v[2 * vc + cv][s] = r2; }
+                    }
+                }
             }
         }
         __syncthreads();
-        // 3a. value logits = fc2(hid): thread -> (bucket k, group of 4 states)
+        // 2a / 2b / 3a: the three small dense layers on the tensor cores (mma.sync m16n8k8, TF32 inputs, fp32
+        // accumulate): M = the tile's 8 states (rows 8-15 of the fragment are padding), N = outputs in tiles of 8
+        // spread over the 8 warps, K in steps of 8.  Weights are pre-packed on the host in B-fragment order
+        // ([n_tile][k_step][lane] float2, TF32-rounded), so each mma costs one coalesced 8-byte load per lane; the
+        // A fragments come from the transposed feature tiles in shared memory (conflict-free).  This replaced a CUDA-core
+        // version that was issue-bound at 21 k instructions per warp (ncu), 60 % of them in these three layers.
+        // 2a. g = gpool_linear(pooled_p) (no bias)
         {
-            const int k = t & (kMaxBins - 1), sg = t >> 7;
-            if (k < bins) {
-                const float b = __ldg(P.bfc2 + k);
-                float a0 = b, a1 = b, a2 = b, a3 = b;
-#pragma unroll 4
-                for (int m = 0; m < mlp; ++m) {
-                    const float w = __ldg(P.wfc2_t + m * bins + k);
-                    const float4 h = *reinterpret_cast<const float4*>(&hidT[m][4 * sg]);
-                    a0 = fmaf(w, h.x, a0); a1 = fmaf(w, h.y, a1); a2 = fmaf(w, h.z, a2); a3 = fmaf(w, h.w, a3);
-                }
-                vlog[4 * sg][k] = a0; vlog[4 * sg + 1][k] = a1; vlog[4 * sg + 2][k] = a2; vlog[4 * sg + 3][k] = a3;
+            const int K = 3 * pc, ks_n = (K + 7) >> 3, nt_n = (pc + 7) >> 3;
+            for (int nt = warp; nt < nt_n; nt += kHeadsThreads / 32) {
+                float c0 = 0.0f, c1 = 0.0f;
+                mma_rows8(P.wgl_t + (size_t)nt * ks_n * 64, ks_n, K, &poolT_p[0][0], lane, c0, c1);
+                const int j = nt * 8 + 2 * (lane & 3), srow = lane >> 2;
+                if (j < pc) g[srow][j] = c0;
+                if (j + 1 < pc) g[srow][j + 1] = c1;
+            }
+        }
+        // 2b. hid = relu(fc1(pooled_v))
+        {
+            const int K = 3 * vc, ks_n = (K + 7) >> 3, nt_n = (mlp + 7) >> 3;
+            for (int nt = warp; nt < nt_n; nt += kHeadsThreads / 32) {
+                float c0 = 0.0f, c1 = 0.0f;
+                mma_rows8(P.wfc1_t + (size_t)nt * ks_n * 64, ks_n, K, &poolT_v[0][0], lane, c0, c1);
+                const int m = nt * 8 + 2 * (lane & 3), srow = lane >> 2;
+                if (m < mlp) hidT[m][srow] = fmaxf(c0 + __ldg(P.bfc1 + m), 0.0f);
+                if (m + 1 < mlp) hidT[m + 1][srow] = fmaxf(c1 + __ldg(P.bfc1 + m + 1), 0.0f);
+            }
+        }
+        __syncthreads();
+        // 3a. value logits = fc2(hid)
+        {
+            const int K = mlp, ks_n = (K + 7) >> 3, nt_n = (bins + 7) >> 3;
+            for (int nt = warp; nt < nt_n; nt += kHeadsThreads / 32) {
+                float c0 = 0.0f, c1 = 0.0f;
+                mma_rows8(P.wfc2_t + (size_t)nt * ks_n * 64, ks_n, K, &hidT[0][0], lane, c0, c1);
+                const int k = nt * 8 + 2 * (lane & 3), srow = lane >> 2;
+                if (k < bins) vlog[srow][k] = c0 + __ldg(P.bfc2 + k);
+                if (k + 1 < bins) vlog[srow][k + 1] = c1 + __ldg(P.bfc2 + k + 1);
             }
         }
         // 3b. policy: p2 = relu(bn2(p + g)); three 1-channel output convs -> raw logits (stored in lp).
@@ -345,7 +393,7 @@ extern "C" int lzb_heads_tail(const void* pv, int64_t n, int32_t pc, int32_t vc,
     if (n == 0) return LZB_OK;
     LZB_REQUIRE(pv && wgl_t && bn2_scale && bn2_shift && wout && wfc1_t && bfc1 && wfc2_t && bfc2, "null weights");
     LZB_REQUIRE(!priors || states, "priors need the packed states");
-    LZB_REQUIRE((pc + vc) % 2 == 0 && (reinterpret_cast<uintptr_t>(pv) & 15) == 0, "pv: even channel count, 16-byte aligned");
+    LZB_REQUIRE((pc + vc) % 8 == 0 && (reinterpret_cast<uintptr_t>(pv) & 15) == 0, "pv: channel count a multiple of 8, 16-byte aligned");
     lzb::HeadsParams P;
     P.pv = reinterpret_cast<const __nv_bfloat16*>(pv); P.n = n; P.pc = pc; P.vc = vc; P.mlp = mlp; P.bins = bins;
     P.wgl_t = wgl_t; P.bn2_scale = bn2_scale; P.bn2_shift = bn2_shift; P.wout = wout; P.wfc1_t = wfc1_t; P.bfc1 = bfc1;

@@ -167,6 +167,20 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
     return w.detach().permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).to(torch.bfloat16).contiguous()
 
 
+def pack_mma_b(weight: torch.Tensor) -> torch.Tensor:
+    """nn.Linear weight [N][K] (fp32) -> the B-fragment order of mma.sync m16n8k8 that heads_tail_kernel reads with one
+    coalesced 8-byte load per lane: float32[ceil(N/8)][ceil(K/8)][32][2], element (nt, ks, lane) = (W[n][k], W[n][k+4])
+    with n = nt*8 + lane//4, k = ks*8 + lane%4; zero padded; rounded to TF32 (10-bit mantissa, nearest)."""
+    n, k = weight.shape
+    nt, ks = -(-n // 8), -(-k // 8)
+    w = torch.zeros((nt * 8, ks * 8), dtype=torch.float32, device=weight.device)
+    w[:n, :k] = weight.detach().float()
+    bits = w.view(torch.int32)
+    w = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)                  # round-to-nearest at 13 dropped bits
+    w = w.view(nt, 8, ks, 2, 4)                                           # [nt][n_in][ks][half][kq]
+    return w.permute(0, 2, 1, 4, 3).reshape(nt, ks, 32, 2).contiguous()   # lane = n_in * 4 + kq
+
+
 def conv_bf16(x: torch.Tensor, w_packed: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
               residual: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
               shift: Optional[torch.Tensor] = None, relu1: bool = False, want_out1: bool = True,
@@ -362,15 +376,15 @@ class FusedHeads:
             wf = torch.cat([ph.conv1.weight.detach(), vh.conv1.weight.detach()], 0).float()
             self._set("conv_wp", pack_conv_weight(wf * torch.cat([s1, s2]).view(-1, 1, 1, 1)))
             self._set("conv_bias", torch.cat([t1, t2]).float())
-        self._set("wgl_t", f(ph.gpool_linear.weight).t())
+        self._set("wgl_t", pack_mma_b(f(ph.gpool_linear.weight)))
         sb, tb = _fold_bn(ph.bn2)
         self._set("bn2_scale", sb)
         self._set("bn2_shift", tb)
         self._set("wout", torch.stack([f(ph.out_pos1.weight).view(-1), f(ph.out_pos2.weight).view(-1),
                                        f(ph.out_mark.weight).view(-1)]))
-        self._set("wfc1_t", f(vh.fc1.weight).t())
+        self._set("wfc1_t", pack_mma_b(f(vh.fc1.weight)))
         self._set("bfc1", f(vh.fc1.bias))
-        self._set("wfc2_t", f(vh.fc2.weight).t())
+        self._set("wfc2_t", pack_mma_b(f(vh.fc2.weight)))
         self._set("bfc2", f(vh.fc2.bias))
 
     def __call__(self, a: torch.Tensor, states: Optional[torch.Tensor] = None, *, priors_out=None, values_out=None,

@@ -91,3 +91,20 @@ def test_trajectory_buffer_growth_and_views_cpu():
     assert buf._player_signs[:3].tolist() == [1, -1, 1]
     empty = TensorTrajectoryBuffer("cpu", 220).build()
     assert empty.num_samples == 0 and tuple(empty.state_tensors.shape) == (0, 11, 6, 6)
+
+
+def test_eval_game_count_normalisation_and_stats():
+    """Host logic of liuzhou_b200/evaluate.py (no GPU): even game counts (eval_checkpoint.py:48-55), outcome
+    aggregation with the colour breakdown (:73-124)."""
+    import torch
+
+    from liuzhou_b200.evaluate import DRAW, LOSS, WIN, _stats_from_outcomes, normalize_eval_games
+
+    assert [normalize_eval_games(n) for n in (-3, 0, 1, 2, 3, 2000, 2001)] == [2, 2, 2, 2, 4, 2000, 2002]
+    outcomes = torch.tensor([WIN, WIN, LOSS, DRAW, WIN, DRAW, LOSS, LOSS])
+    black = torch.tensor([True] * 4 + [False] * 4)
+    st = _stats_from_outcomes(outcomes, black, seed=9)
+    assert (st.wins, st.losses, st.draws, st.total_games, st.seed) == (3, 3, 2, 8, 9)
+    assert st.color_breakdown["challenger_black"] == {"wins": 2, "losses": 1, "draws": 1, "games": 4}
+    assert st.color_breakdown["challenger_white"] == {"wins": 1, "losses": 2, "draws": 1, "games": 4}
+    assert abs(st.win_rate - 0.375) < 1e-12 and abs(st.draw_rate - 0.25) < 1e-12
