@@ -91,6 +91,51 @@ def gather_trajectories(batch: TensorSelfPlayBatch, dst: int = 0, group=None) ->
     return TensorSelfPlayBatch(*merged)
 
 
+def _gather_rows(t: torch.Tensor, counts: List[int], dst: int, group) -> Optional[torch.Tensor]:
+    """Variable-length gather along dim 0 (rows of rank r: counts[r]); returns the rank-major concatenation on dst."""
+    world, rank = _world(group), _rank(group)
+    n_max = max(counts) if counts else 0
+    carrier = t.to(torch.uint8) if t.dtype == torch.bool else t
+    padded = torch.zeros((n_max,) + tuple(carrier.shape[1:]), dtype=carrier.dtype, device=carrier.device)
+    padded[: carrier.shape[0]].copy_(carrier)
+    if rank == dst:
+        bufs = [torch.empty_like(padded) for _ in range(world)]
+        dist.gather(padded, bufs, dst=dst, group=group)
+        out = torch.cat([b[:c] for b, c in zip(bufs, counts)], 0)
+        return out.to(torch.bool) if t.dtype == torch.bool else out
+    dist.gather(padded, None, dst=dst, group=group)
+    return None
+
+
+def gather_trajectories_compact(batch: TensorSelfPlayBatch, dst: int = 0, group=None) -> Optional[TensorSelfPlayBatch]:
+    """Same result as ``gather_trajectories`` with ~15x fewer bytes on the wire: every rank compacts its batch
+    (liuzhou_b200.compact: bitboards + legal bits + sparse policy, lossless), the compact pieces are gathered, and
+    rank `dst` expands the merged batch back to the reference's five dense tensors."""
+    from . import compact as cp
+
+    world, rank = _world(group), _rank(group)
+    if world == 1:
+        return batch
+    dev = batch.state_tensors.device
+    c = cp.compact(batch)
+    sizes = torch.tensor([c.num_samples, int(c.policy_index.numel())], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    n_rows = [int(s[0].item()) for s in all_sizes]
+    n_nnz = [int(s[1].item()) for s in all_sizes]
+    per_row_counts = c.policy_offsets[1:] - c.policy_offsets[:-1]           # offsets are rebuilt at the destination
+    parts = [_gather_rows(t, n_rows, dst, group) for t in (c.boards, c.legal_bits, per_row_counts, c.value_targets,
+                                                            c.soft_value_targets)]
+    idx = _gather_rows(c.policy_index, n_nnz, dst, group)
+    val = _gather_rows(c.policy_value, n_nnz, dst, group)
+    if rank != dst:
+        return None
+    boards, legal_bits, counts, vt, svt = parts
+    offsets = torch.zeros((counts.numel() + 1,), dtype=torch.int64, device=dev)
+    offsets[1:] = torch.cumsum(counts, 0)
+    return cp.expand(cp.CompactSelfPlayBatch(boards, legal_bits, offsets, idx, val, vt, svt))
+
+
 def all_reduce_stats(values: List[float], device=None, group=None) -> List[float]:
     """Sum a small vector of counters (W/L/D, positions, lengths, seconds) over ranks."""
     if _world(group) == 1:
@@ -100,7 +145,8 @@ def all_reduce_stats(values: List[float], device=None, group=None) -> List[float
     return [float(v) for v in t.tolist()]
 
 
-def self_play_sharded(model, total_games: int, *, iteration_seed: int, device, group=None, **self_play_kwargs):
+def self_play_sharded(model, total_games: int, *, iteration_seed: int, device, group=None, compact_gather: bool = True,
+                      **self_play_kwargs):
     """Config-4 style entry: every rank plays its share of `total_games` (split_games) with the per-rank seed
     rule, weights come from rank 0, trajectories and statistics return to rank 0.
     Returns (merged TensorSelfPlayBatch or None, summed stats dict)."""
@@ -121,7 +167,7 @@ def self_play_sharded(model, total_games: int, *, iteration_seed: int, device, g
                                     torch.empty((0, 220), device=dev), torch.empty((0,), device=dev),
                                     torch.empty((0,), device=dev))
         vec = [0.0] * 7
-    merged = gather_trajectories(batch, dst=0, group=group)
+    merged = (gather_trajectories_compact if compact_gather else gather_trajectories)(batch, dst=0, group=group)
     tot = all_reduce_stats(vec, device=device, group=group)
     summary = {"num_games": tot[0], "num_positions": tot[1], "black_wins": tot[2], "white_wins": tot[3],
                "draws": tot[4], "avg_game_length": tot[5] / max(1.0, tot[0]), "sum_elapsed_sec": tot[6]}

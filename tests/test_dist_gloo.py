@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from liuzhou_b200.dist import (all_reduce_stats, broadcast_model, gather_trajectories, rank_seed, split_games)
+from liuzhou_b200.dist import (all_reduce_stats, broadcast_model, gather_trajectories, gather_trajectories_compact,
+                               rank_seed, split_games)
 from liuzhou_b200.trajectory_buffer import TensorSelfPlayBatch
 
 
@@ -31,10 +32,15 @@ def _free_port() -> int:
 
 def _make_batch(n: int, rank: int) -> TensorSelfPlayBatch:
     g = torch.Generator().manual_seed(100 + rank)
+    planes = torch.zeros((n, 11, 6, 6))
+    planes[:, :4] = (torch.rand((n, 4, 6, 6), generator=g) > 0.5).float()
+    phase = torch.randint(1, 8, (n,), generator=g)
+    planes[torch.arange(n), 3 + phase] = 1.0                  # one-hot phase plane (v0/src/net/encoding.cpp:26-79)
+    legal = torch.rand((n, 220), generator=g) > 0.7
     return TensorSelfPlayBatch(
-        state_tensors=(torch.rand((n, 11, 6, 6), generator=g) > 0.5).float(),
-        legal_masks=torch.rand((n, 220), generator=g) > 0.7,
-        policy_targets=torch.rand((n, 220), generator=g),
+        state_tensors=planes,
+        legal_masks=legal,
+        policy_targets=torch.rand((n, 220), generator=g) * legal,
         value_targets=torch.randint(-1, 2, (n,), generator=g).float(),
         soft_value_targets=torch.rand((n,), generator=g) * 2 - 1)
 
@@ -59,6 +65,7 @@ def _worker(rank: int, world: int, port: int, sizes, ret):
         same = all(torch.equal(ref[0], r) for r in ref)
         batch = _make_batch(sizes[rank], rank)
         merged = gather_trajectories(batch, dst=0)
+        merged_c = gather_trajectories_compact(batch, dst=0)
         stats = all_reduce_stats([1.0, float(sizes[rank]), float(rank)])
         if rank == 0:
             expect = [_make_batch(sizes[r], r) for r in range(world)]
@@ -66,9 +73,12 @@ def _worker(rank: int, world: int, port: int, sizes, ret):
             for name in ("state_tensors", "legal_masks", "policy_targets", "value_targets", "soft_value_targets"):
                 cat = torch.cat([getattr(e, name) for e in expect], 0)
                 ok = ok and torch.equal(getattr(merged, name), cat) and getattr(merged, name).dtype == cat.dtype
+                got = getattr(merged_c, name)                       # compact wire format: same tensors, bit for bit
+                ok = ok and got.dtype == cat.dtype and torch.equal(torch.nan_to_num(got.float(), nan=7.0),
+                                                                   torch.nan_to_num(cat.float(), nan=7.0))
             ret["rank0"] = (same, ok, stats, moved)
         else:
-            ret[f"rank{rank}"] = (same, merged is None, stats, moved)
+            ret[f"rank{rank}"] = (same, merged is None and merged_c is None, stats, moved)
     finally:
         dist.destroy_process_group()
 
