@@ -483,19 +483,19 @@ def run_selfplay(args, world, rank, local_rank):
     stepper.diversify(seed=SEED + rank)
     stream = torch.cuda.current_stream(dev)
 
-    gather_buf = None
-    if world > 1:
-        import torch.distributed as dist
-
-        if rank == 0:
-            gather_buf = [torch.empty((games, 220), dtype=torch.float32, device=dev) for _ in range(world)]
-
     def step():
         stepper.step()
-        if world > 1:   # trajectories return to the trainer rank over NCCL (policy block shown; 880 of 2,692 B/pos)
-            import torch.distributed as dist
+        if world > 1:
+            # this ply's trajectory rows (all five tensors of the reference format) return to the trainer rank over
+            # NCCL in the compact lossless wire format (liuzhou_b200/compact.py, ~15x fewer bytes than 2,692 B/position)
+            import torch as _t
 
-            dist.gather(stepper.trajectory_block()[2], gather_buf, dst=0)
+            from liuzhou_b200.dist import gather_trajectories_compact
+            from liuzhou_b200.trajectory_buffer import TensorSelfPlayBatch
+
+            planes, legal, policy, _sign = stepper.trajectory_block()
+            nan = _t.full((games,), float("nan"), device=dev)
+            gather_trajectories_compact(TensorSelfPlayBatch(planes, legal, policy, nan, nan), dst=0)
 
     for _ in range(args.warmup):
         step()
