@@ -619,6 +619,101 @@ def run_selfplay(args, world, rank, local_rank):
     }
 
 
+def run_selfplay_root(args, world, rank, local_rank):
+    """The reference's PRODUCTION search (`--search_backend cuda_root`: root-only PUCT, v1/python/mcts_gpu.py:1249-1457)
+    through our drop-in entry: one step = one full `self_play_v1_gpu` iteration (all games played to the end), which
+    is what v1/train.py runs per worker and what the reference's published H20 numbers measure."""
+    import torch
+
+    from liuzhou_b200 import _lib
+    from liuzhou_b200.net import InferenceNet
+    from liuzhou_b200.self_play import self_play_v1_gpu
+
+    dev = torch.device("cuda", local_rank)
+    peaks, peak_kind = measured_peaks()
+    games, sims = args.games, args.sims
+    model = _default_model()
+    if world > 1:
+        import torch.distributed as dist
+
+        model = model.to(dev)
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=0)
+    net = InferenceNet(model, dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def iteration(seed):
+        torch.manual_seed(seed * 10007 + (rank + 1) * 9973)
+        return self_play_v1_gpu(net, num_games=games, mcts_simulations=sims, temperature_init=1.0, temperature_final=0.1,
+                                temperature_threshold=10, exploration_weight=1.0, device=str(dev),
+                                add_dirichlet_noise=True, soft_value_k=2.0, max_game_plies=512, sample_moves=True,
+                                concurrent_games=games, search_backend="root")
+
+    for w in range(max(1, min(args.warmup, 1))):
+        iteration(SEED + w)
+    barrier_sync(world)
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, min(args.steps, 3))
+    positions = 0
+    last = None
+    e0.record(stream)
+    for it in range(steps):
+        batch, stats = iteration(SEED + 100 + it)
+        positions += batch.num_samples
+        last = (batch, stats)
+    e1.record(stream)
+    e1.synchronize()
+    barrier_sync(world)
+    clocks = sampler.stop() if rank == 0 else {}
+    elapsed_ms = max_over_ranks(e0.elapsed_time(e1), world)
+    launches = _lib.launch_count() - launches0
+    all_positions = sum_over_ranks(float(positions), world)
+    value = all_positions / (elapsed_ms / 1e3)
+    # e2e: the same iteration with the resulting trajectory batch (reference format, 2,692 B/position) read to the host
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    batch, stats = iteration(SEED + 200)
+    host = batch.to("cpu")
+    e2e_s = time.perf_counter() - t0
+    e2e_value = sum_over_ranks(float(host.num_samples), world) / max_over_ranks(e2e_s, world)
+    conv = time_trunk_conv(net, 4096, stream)
+    if rank != 0:
+        return None
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    st = last[1]
+    cpu = cpu_selfplay_baseline(budget_s=args.cpu_budget, sims=sims)
+    return {
+        "metric": "selfplay_positions_per_sec", "value": value, "unit": "positions/s", "n_gpus": world, "steps": steps,
+        "warmup": 1, "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "mcts_sims_per_sec": value * sims,
+        "config": {"workload": "v1 wave-batched self-play, root-PUCT search (the reference's production backend; BASELINE "
+                               "configs[2] with search_backend=cuda_root)", "games_per_gpu": games, "sims_per_move": sims,
+                   "search": "root-only PUCT: 1 + #legal-children network evaluations per position, root_puct kernel",
+                   "step": "one full self_play_v1_gpu iteration (every game played to its end, trajectory batch built)",
+                   "net": "ChessNet 128ch x 10 blocks, random init, seed 20260314", "dirichlet_noise": True,
+                   "temperature": "1.0 -> 0.1 at ply 10",
+                   "l2": "activations of a child batch (>= 100 MB per tensor) exceed the 126 MB L2",
+                   "published_reference": "4,995.8 positions/s on 1 x H20 at sims=1024, 64 concurrent games "
+                                          "(v1/Design.md:1528; other hardware / config, so vs_baseline stays null)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "positions/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": int(host.nbytes())},
+        "gpu_launches": int(launches),
+        "selfplay_stats": {"games": st.num_games, "positions": st.num_positions, "avg_game_length": st.avg_game_length,
+                           "black_wins": st.black_wins, "white_wins": st.white_wins, "draws": st.draws},
+        "roofline": {"bound": "tensor", "achieved": conv["tflops"], "peak": peak, "unit": "TFLOP/s",
+                     "frac": conv["tflops"] / peak, "traffic": conv["traffic_bytes"],
+                     "peak_kind": peak_kind + " (sustained bf16, cuBLAS)",
+                     "kernel": "conv_tc_kernel<9,2> (csrc/lz_conv.cu)", "kernel_ms": conv["ms"], "units_per_launch": 4096,
+                     "flops_per_unit": conv["flops_per_state"]},
+        "cpu_baseline": cpu,
+    }
+
+
 def run_reference_selfplay(args):
     per_step = max(5.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
     vals, last = [], None
@@ -702,6 +797,8 @@ def main() -> int:
     ap.add_argument("--games", type=int, default=SELFPLAY_GAMES)
     ap.add_argument("--sims", type=int, default=SELFPLAY_SIMS)
     ap.add_argument("--leaves-per-wave", type=int, default=1)
+    ap.add_argument("--search", choices=["tree", "root"], default="tree",
+                    help="tree: device-resident full tree (north_star, default); root: the reference's root-PUCT backend")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -722,7 +819,8 @@ def main() -> int:
         return 0
 
     world, rank, local_rank = dist_setup(args.gpus)
-    fn = {"selfplay": run_selfplay, "playout": run_playout, "eval": run_eval}[args.workload]
+    fn = {"selfplay": run_selfplay_root if args.search == "root" else run_selfplay, "playout": run_playout,
+          "eval": run_eval}[args.workload]
     line = fn(args, world, rank, local_rank)
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -529,11 +529,42 @@ class InferenceNet:
         self._graphs[n] = (g, x, outs)
         return x, outs
 
+    def _tc_ready(self) -> bool:
+        return (self.trunk is not None and self.trunk.use_tc and "stem_wp" in self.trunk._t
+                and len(self.model.blocks) > 0 and self.heads is not None)
+
+    @torch.no_grad()
+    def _forward_chunked(self, inputs: torch.Tensor, chunk: int = 16384):
+        """Arbitrary batch sizes on the tcgen05 path: rows are processed in chunks of <= `chunk`, each padded up to a
+        multiple of 64 rows and to 64 input channels in a cached staging buffer (padding rows compute garbage that is
+        dropped).  inputs: [n,11,6,6], any float dtype / memory format."""
+        n = int(inputs.size(0))
+        dev = self.device
+        bins = self.heads.bins
+        outs = (torch.empty((n, 36), dtype=torch.float32, device=dev), torch.empty((n, 36), dtype=torch.float32, device=dev),
+                torch.empty((n, 36), dtype=torch.float32, device=dev), torch.empty((n, bins), dtype=torch.float32, device=dev))
+        if getattr(self, "_pad_buf", None) is None or self._pad_buf.size(0) < min(chunk, -(-n // 64) * 64):
+            rows = min(chunk, max(64, -(-n // 64) * 64))
+            self._pad_buf = torch.empty((rows, 64, 6, 6), dtype=self.dtype, device=dev,
+                                        memory_format=torch.channels_last).zero_()
+        c_in = self.model.num_input_channels
+        for s0 in range(0, n, chunk):
+            m = min(chunk, n - s0)
+            mp = -(-m // 64) * 64
+            x = self._pad_buf[:mp]
+            x[:m, :c_in].copy_(inputs[s0:s0 + m])
+            o = self._forward_eager(x)
+            for dst, src in zip(outs, o):
+                dst[s0:s0 + m].copy_(src[:m])
+        return outs
+
     @torch.no_grad()
     def forward(self, inputs: torch.Tensor):
         n = inputs.size(0)
         entry = self._graphs.get(n)
         if entry is None:
+            if n > 0 and self._tc_ready() and inputs.size(1) == self.model.num_input_channels:
+                return self._forward_chunked(inputs.to(self.device))
             x = inputs.to(device=self.device, dtype=self.dtype).contiguous(memory_format=torch.channels_last)
             return self._forward_eager(x)
         g, x, outs = entry
