@@ -581,6 +581,32 @@ def run_selfplay(args, world, rank, local_rank):
     e2e_elapsed = max_over_ranks(sum(e2e_times), world)
     e2e_value = sum_over_ranks(float(games * len(e2e_times)), world) / e2e_elapsed
 
+    # the same workload on the reference's production backend (root-only PUCT through the drop-in v0_core ops): one
+    # warm-up + one timed full self_play_v1_gpu iteration; reported next to the tree-search headline (N = 1 only)
+    root_line = None
+    if world == 1 and not args.no_root_line:
+        from liuzhou_b200.self_play import self_play_v1_gpu
+
+        def root_iteration(seed):
+            torch.manual_seed(seed)
+            return self_play_v1_gpu(net, num_games=games, mcts_simulations=sims, temperature_init=1.0,
+                                    temperature_final=0.1, temperature_threshold=10, exploration_weight=1.0,
+                                    device=str(dev), add_dirichlet_noise=True, concurrent_games=games,
+                                    search_backend="root")
+
+        del stepper
+        torch.cuda.empty_cache()
+        root_iteration(SEED)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        rb, _rs = root_iteration(SEED + 1)
+        r1.record(stream)
+        r1.synchronize()
+        root_line = {"value": rb.num_samples / (r0.elapsed_time(r1) / 1e3), "unit": "positions/s",
+                     "positions": rb.num_samples, "seconds": r0.elapsed_time(r1) / 1e3,
+                     "what": "one full self_play_v1_gpu iteration, search_backend=root (reference production path), "
+                             "same games / sims / net; see bench.py --search root"}
+
     if rank != 0:
         return None
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
@@ -588,6 +614,7 @@ def run_selfplay(args, world, rank, local_rank):
     return {
         "metric": "selfplay_positions_per_sec", "value": value, "unit": "positions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+        "root_puct_backend": root_line,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "mcts_sims_per_sec": value * sims, "network_evals_per_sec": evals * world / (elapsed_ms / 1e3),
         "config": {"workload": "v1 wave-batched MCTS self-play (BASELINE configs[2])", "games_per_gpu": games,
@@ -797,6 +824,7 @@ def main() -> int:
     ap.add_argument("--games", type=int, default=SELFPLAY_GAMES)
     ap.add_argument("--sims", type=int, default=SELFPLAY_SIMS)
     ap.add_argument("--leaves-per-wave", type=int, default=1)
+    ap.add_argument("--no-root-line", action="store_true", help="skip the extra root-PUCT iteration in the default line")
     ap.add_argument("--search", choices=["tree", "root"], default="tree",
                     help="tree: device-resident full tree (north_star, default); root: the reference's root-PUCT backend")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
