@@ -300,3 +300,44 @@ def test_fused_heads_kernel_vs_fp32_pytorch_heads(dims):
         legal[i, oracle.legal_actions(st, i)[0]] = True
     p = _np(pri)
     assert (p[~legal] == 0).all() and np.allclose(p[legal.any(1)].sum(1), 1.0, atol=1e-5)
+
+
+def test_tree_search_full_size_properties():
+    """BASELINE configs[2] size (4,096 trees x 200 simulations, default 128-channel net on the tcgen05 convs) through
+    size-independent properties: every live root receives exactly `sims` visits, visits only on legal actions, the
+    policy is a distribution over them, the chosen move is the most visited one, and a second search of the same
+    roots reproduces the visit counts bit for bit (no atomics on tree statistics, no noise)."""
+    from liuzhou_b200 import native
+    from liuzhou_b200.net import ChessNet, InferenceNet
+    from liuzhou_b200.tree_search import TreeMCTS, TreeMCTSConfig
+
+    n, sims = 4096, 200
+    torch.manual_seed(20260314)
+    net = InferenceNet(ChessNet(), DEV)
+    chunks = []
+    for i, steps in enumerate((0, 9, 30, 45, 70, 100, 140, 200)):
+        pb = native.PlayoutBatch(n // 8, seed=99, device=DEV, game_offset=i * (n // 8))
+        if steps:
+            pb.run(max_steps=steps)
+        chunks.append(pb.packed)
+    roots = torch.cat(chunks).contiguous()
+    mcts = TreeMCTS(net, n, TreeMCTSConfig(num_simulations=sims, add_dirichlet_noise=False, sample_moves=False), DEV)
+    temps = torch.ones((n,), device=DEV)
+    out1 = mcts.search(roots, temperatures=temps)
+    v1 = out1.visit_counts.clone()
+    pol1 = out1.policy_dense.clone()
+    out2 = mcts.search(roots, temperatures=temps)
+    assert torch.equal(v1, out2.visit_counts)
+    mcts.tree.check_capacity()
+    words, counts = native.legal_masks(roots, scalar_semantics=True)
+    legal = native.mask_words_to_bool(words)
+    live = ~out1.terminal_mask
+    assert int(live.sum()) > n // 2
+    assert torch.equal(out1.legal_mask[live], legal[live])
+    assert bool((v1[~legal] == 0).all())
+    assert bool((v1.sum(1)[live] == sims).all())
+    assert torch.allclose(pol1.sum(1)[live], torch.ones_like(pol1.sum(1)[live]), atol=1e-5)
+    chosen = out1.chosen_action_indices
+    assert bool((chosen[live] >= 0).all()) and bool(legal[live].gather(1, chosen[live].view(-1, 1)).all())
+    assert bool((v1[live].gather(1, chosen[live].view(-1, 1)).view(-1) == v1[live].max(1).values).all())
+    assert bool((chosen[~live] == -1).all())

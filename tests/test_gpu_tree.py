@@ -50,7 +50,8 @@ def _complete(tree, rows, pri, val):
     tree.complete_pending(torch.from_numpy(p).to(DEV), torch.from_numpy(v).to(DEV))
 
 
-def _run_both(st, sims, c_puct, check_every_wave=True):
+def _run_both(st, sims, c_puct, check_every_wave=True, net=None):
+    fake = net or fake_net
     from liuzhou_b200 import native
     from liuzhou_b200.tree import DeviceTreeBatch
 
@@ -63,7 +64,7 @@ def _run_both(st, sims, c_puct, check_every_wave=True):
     rows, inputs, masks = _pending_from_device(tree, native)
     assert np.array_equal(rows, pend["tree_indices"])
     assert np.array_equal(inputs, pend["model_inputs"]) and np.array_equal(masks, pend["legal_masks"])
-    pri, val = fake_net(pend["model_inputs"], pend["legal_masks"], 0)
+    pri, val = fake(pend["model_inputs"], pend["legal_masks"], 0)
     ref.complete_pending(pri, val)
     _complete(tree, rows, pri, val)
     for s in range(sims):
@@ -74,8 +75,8 @@ def _run_both(st, sims, c_puct, check_every_wave=True):
             assert np.array_equal(rows, pend["tree_indices"]), s
             assert np.array_equal(inputs, pend["model_inputs"]), s
             assert np.array_equal(masks, pend["legal_masks"]), s
-        pri, val = fake_net(inputs, masks, 1)
-        ref.complete_pending(*fake_net(pend["model_inputs"], pend["legal_masks"], 1))
+        pri, val = fake(inputs, masks, 1)
+        ref.complete_pending(*fake(pend["model_inputs"], pend["legal_masks"], 1))
         _complete(tree, rows, pri, val)
     tree.check_capacity()
     return ref.root_outputs(), ref.root_priors(), tree.root_outputs()
@@ -94,6 +95,29 @@ def test_tree_visit_counts_identical_to_oracle(sims, c_puct):
     total = _np(mo["visit_counts"]).sum(1)
     live = ro["terminal"] == 0
     assert (total[live] == sims).all()
+
+
+def test_tree_deep_paths_beyond_recorded_depth():
+    """A network that puts (almost) all prior mass on the lowest legal action and returns value 0 makes every
+    simulation descend the same line one level deeper: depth reaches the number of simulations, far beyond the 32
+    levels the select kernel records for the one-round-trip backup -- the parent-walk fallback and the hand-over
+    between the two must leave visit counts / values identical to the oracle."""
+    def line_net(inputs, masks, salt):
+        n = masks.shape[0]
+        pri = np.where(masks != 0, 1e-7, 0.0).astype(np.float32)
+        first = (masks != 0).argmax(1)
+        pri[np.arange(n), first] = 1.0
+        return pri, np.zeros((n,), np.float32)
+
+    st = _playout_states(3, 5, every=40)
+    sims = 90
+    ro, rp, mo = _run_both(st, sims, 1.0, net=line_net)
+    v = _np(mo["visit_counts"])
+    assert np.array_equal(v, ro["visit_counts"])
+    assert np.array_equal(_np(mo["root_action_values"]), ro["root_action_values"])
+    assert np.array_equal(_np(mo["root_values"]), ro["root_values"])
+    live = ro["terminal"] == 0
+    assert (v.max(1)[live] >= sims - 2).all()          # one child took (almost) every visit: the line is really deep
 
 
 def test_tree_golden_reference_vectors():
