@@ -48,6 +48,19 @@ def main():
                           "manifest_keys": sorted(man.keys()), "avg_bytes_per_sample": man["avg_bytes_per_sample"],
                           "shard_keys": sorted(torch.load(str(Path(d) / man["shard_files"][0])).keys()),
                           "shard_meta_keys": sorted(torch.load(str(Path(d) / man["shard_files"][0]))["metadata"].keys())}
+    # stable bootstrap init (v1/train.py:162-217) of the reference's ChessNet under the production seed
+    import hashlib
+
+    from src.neural_network import ChessNet as RefNet
+
+    torch.manual_seed(123)
+    net = RefNet()
+    T._init_model_stable_resnet(net, seed=20260314)
+    h = hashlib.sha256()
+    for k, v in net.state_dict().items():
+        h.update(k.encode())
+        h.update(v.detach().cpu().contiguous().numpy().tobytes())
+    out["stable_init_sha256"] = h.hexdigest()
     (Path(__file__).resolve().parent / "storage_formats.json").write_text(json.dumps(out, indent=1, sort_keys=True))
     print("wrote storage_formats.json")
 

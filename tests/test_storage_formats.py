@@ -232,6 +232,80 @@ def test_worker_manifest_merge_and_reference_loader(tmp_path):
     _eq_batches(back, b0)
 
 
+def test_stable_init_matches_reference(golden):
+    """Same seed -> bit-identical bootstrap weights as the reference's `_init_model_stable_resnet` on its ChessNet."""
+    import hashlib
+
+    from liuzhou_b200.net import ChessNet
+    from liuzhou_b200.selfplay_stage import init_model_stable_resnet
+
+    torch.manual_seed(999)
+    before = torch.random.get_rng_state()
+    net = ChessNet()
+    torch.random.set_rng_state(before)
+    init_model_stable_resnet(net, seed=20260314)
+    assert torch.equal(torch.random.get_rng_state(), before)             # ambient RNG state restored
+    h = hashlib.sha256()
+    for k, v in net.state_dict().items():
+        h.update(k.encode())
+        h.update(v.detach().cpu().contiguous().numpy().tobytes())
+    assert h.hexdigest() == golden["stable_init_sha256"]
+    with pytest.raises(ValueError):
+        init_model_stable_resnet(net, seed=0)
+
+
+def test_stage_cli_accepts_big_train_flags(tmp_path):
+    """The flag list scripts/big_train_v1.sh:667-700 passes for --stage selfplay parses; other stages' flags are ignored."""
+    from liuzhou_b200 import selfplay_stage as S
+
+    argv = ["--pipeline", "v1", "--stage", "selfplay", "--device", "cuda:0", "--devices", "cuda:0,cuda:1,cuda:1",
+            "--train_devices", "cuda:0", "--infer_devices", "cuda:0", "--self_play_games", "32768", "--mcts_simulations", "800",
+            "--temperature_init", "1.0", "--temperature_final", "0.1", "--temperature_threshold", "10",
+            "--exploration_weight", "1.0", "--dirichlet_alpha", "0.3", "--dirichlet_epsilon", "0.25", "--soft_value_k", "2.0",
+            "--soft_label_alpha", "0.25", "--max_game_plies", "512", "--self_play_concurrent_games", "4096",
+            "--self_play_opening_random_moves", "4", "--sparse_ply", "1", "--sparse_top_k", "8", "--self_play_backend", "process",
+            "--self_play_target_samples_per_shard", "0", "--self_play_chunk_target_bytes", "268435456",
+            "--model_init_seed", "20260314", "--checkpoint_dir", str(tmp_path), "--self_play_output", str(tmp_path / "sp.pt"),
+            "--self_play_iteration_seed", "7", "--self_play_stats_json", str(tmp_path / "sp.json")]
+    args, ignored = S.build_parser().parse_known_args(argv)
+    assert ignored == ["--train_devices", "cuda:0", "--infer_devices", "cuda:0"]
+    assert args.self_play_games == 32768 and args.self_play_chunk_target_bytes == 268435456 and args.self_play_sample_moves
+    assert S.parse_device_list(args.device, args.devices) == ["cuda:0", "cuda:1"]
+    assert S._resolve_seeds(args) == (7, 20260314)
+    with pytest.raises(RuntimeError):
+        S.parse_device_list("cpu", None)                                  # no CPU path
+    args.self_play_iteration_seed = -3
+    with pytest.raises(ValueError):
+        S._resolve_seeds(args)
+    # checkpoint loader: `model_state_dict` wrapper and bare state dicts
+    from liuzhou_b200.net import ChessNet
+    a, b = ChessNet(), ChessNet()
+    torch.save({"model_state_dict": a.state_dict(), "iteration": 3}, str(tmp_path / "ck.pt"))
+    S.load_checkpoint_into_model(b, str(tmp_path / "ck.pt"))
+    assert all(torch.equal(x, y) for x, y in zip(a.state_dict().values(), b.state_dict().values()))
+    with pytest.raises(FileNotFoundError):
+        S.load_checkpoint_into_model(b, str(tmp_path / "none.pt"))
+
+
+@pytest.mark.gpu
+def test_stage_cli_end_to_end(tmp_path):
+    """`python -m liuzhou_b200.selfplay_stage` on one GPU: manifest + stats JSON as the next stage expects them."""
+    import subprocess
+
+    out, js = tmp_path / "run" / "selfplay_iter_001.pt", tmp_path / "run" / "selfplay_iter_001.json"
+    cmd = [sys.executable, "-m", "liuzhou_b200.selfplay_stage", "--stage", "selfplay", "--device", "cuda:0",
+           "--self_play_games", "96", "--mcts_simulations", "16", "--self_play_concurrent_games", "64", "--max_game_plies", "48",
+           "--self_play_output", str(out), "--self_play_iteration_seed", "1", "--self_play_stats_json", str(js),
+           "--self_play_target_samples_per_shard", "1500", "--batch_size", "256"]
+    r = subprocess.run(cmd, cwd=str(Path(__file__).resolve().parents[1]), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rep = json.loads(js.read_text())
+    assert rep["num_games"] == 96.0 and rep["self_play_iteration_seed"] == 1 and rep["piece_delta_bucket_total"] == 96
+    assert rep["value_target_summary"]["total"] == int(rep["num_positions"])
+    batch, stats, meta = st.load_self_play_payload(str(out))
+    assert batch.num_samples == int(rep["num_positions"]) and meta["stage"] == "selfplay" and meta["self_play_games"] == 96
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("backend", ["cuda_root", "portable"])
 def test_run_self_play_worker_end_to_end(tmp_path, backend):
