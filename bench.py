@@ -479,7 +479,8 @@ def run_selfplay(args, world, rank, local_rank):
             dist.broadcast(t.data, src=0)
     net = InferenceNet(model, dev)
     torch.manual_seed(SEED * 10007 + (rank + 1) * 9973)          # per-rank seed rule of v1/train.py:795,998
-    stepper = SelfPlayStepper(net, games, simulations=sims, leaves_per_wave=k, seed=SEED, device=dev)
+    stepper = SelfPlayStepper(net, games, simulations=sims, leaves_per_wave=k, seed=SEED, device=dev,
+                              reuse_subtree=bool(args.tree_reuse))
     stepper.diversify(seed=SEED + rank)
     stream = torch.cuda.current_stream(dev)
 
@@ -619,7 +620,10 @@ def run_selfplay(args, world, rank, local_rank):
         "mcts_sims_per_sec": value * sims, "network_evals_per_sec": evals * world / (elapsed_ms / 1e3),
         "config": {"workload": "v1 wave-batched MCTS self-play (BASELINE configs[2])", "games_per_gpu": games,
                    "sims_per_move": sims, "search": "full tree on device (select/expand/backup kernels)",
-                   "leaves_per_wave": k, "net": "ChessNet 128ch x 10 blocks, random init, seed 20260314; all 22 "
+                   "leaves_per_wave": k,
+                   "subtree_reuse": bool(args.tree_reuse) and "advance_roots after every move (portable_cpp_self_play.py:170): "
+                                    "200 NEW simulations per move on top of the inherited subtree, arena compacted per ply",
+                   "net": "ChessNet 128ch x 10 blocks, random init, seed 20260314; all 22 "
                    "convolutions per forward are our tcgen05 kernel, no cuDNN on the path",
                    "step": "one ply of every game; finished games refilled; batch pre-diversified by 0..120 random plies",
                    "dirichlet_noise": True, "temperature": "1.0 -> 0.1 at ply 10", "exploration_weight": 1.0,
@@ -824,6 +828,9 @@ def main() -> int:
     ap.add_argument("--games", type=int, default=SELFPLAY_GAMES)
     ap.add_argument("--sims", type=int, default=SELFPLAY_SIMS)
     ap.add_argument("--leaves-per-wave", type=int, default=1)
+    ap.add_argument("--tree-reuse", type=int, default=1,
+                    help="1: the played child's subtree is kept between moves (advance_roots, as the reference's "
+                         "portable self-play does); 0: every search starts from a bare root")
     ap.add_argument("--no-root-line", action="store_true", help="skip the extra root-PUCT iteration in the default line")
     ap.add_argument("--search", choices=["tree", "root"], default="tree",
                     help="tree: device-resident full tree (north_star, default); root: the reference's root-PUCT backend")

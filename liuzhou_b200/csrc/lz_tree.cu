@@ -121,7 +121,8 @@ constexpr int kLeafDuplicate = 2;  // K > 1 only: same leaf already pending in t
 
 __global__ void __launch_bounds__(kThreads, 4)      // 4 x 8 warps per SM: all 4,096 trees of a wave resident at once
 tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restrict__ leaf_node,
-                   int32_t* __restrict__ leaf_status, uint64_t* __restrict__ leaf_states, int32_t* __restrict__ leaf_path) {
+                   int32_t* __restrict__ leaf_status, uint64_t* __restrict__ leaf_states, int32_t* __restrict__ leaf_path,
+                   int roots_only) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
@@ -130,7 +131,9 @@ tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restr
             const int64_t slot = t * K + k;
             int node = (int)t;
             uint32_t inf = A.info[node];
-            if (inf & (kInfoTerminal | kInfoInactive)) {            // SelectLeaves :519-521
+            // SelectLeaves :519-521; PrepareRoots (:483-513) only ever evaluates an unexpanded root -- a root that
+            // kept its subtree through advance_roots is left alone
+            if ((inf & (kInfoTerminal | kInfoInactive)) || (roots_only && (inf & kInfoExpanded))) {
                 if (lane == 0) { leaf_node[slot] = -1; leaf_status[slot] = kLeafDone; }
                 continue;
             }
@@ -277,7 +280,7 @@ tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, con
                     for (uint64_t m = L.sel; m; m &= m - 1) prior_sum = __dadd_rn(prior_sum, (double)s_pri[w][180 + ctz64(m)]);
                     if (L.process) prior_sum = __dadd_rn(prior_sum, (double)s_pri[w][216]);
                     fc = atomicAdd(&A.counters[0], n);
-                    if ((int64_t)fc + n > A.capacity) { A.counters[1] = 1; fc = -1; }
+                    if ((int64_t)fc + n > A.capacity) { atomicOr(&A.counters[1], 1); fc = -1; }
                     else atomicAdd(&A.counters[2], 1);
                 }
                 prior_sum = __shfl_sync(0xffffffffu, prior_sum, 0);
@@ -317,6 +320,140 @@ tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, con
             __syncwarp();
         }
     }
+}
+
+// AdvanceRoots (portable_mcts.cpp:739-768): the child reached by the played action becomes the root and keeps its whole
+// subtree (visit counts, value sums, priors, states); everything else of the old tree is dropped.  The reference
+// moves a unique_ptr; here the kept subtree is copied breadth-first into a scratch arena (children blocks stay
+// contiguous, one atomicAdd on the scratch bump pointer per block), which is then copied back over the arena prefix --
+// a copying collector, so the arena never accumulates dead nodes over a game.  One warp per tree; the BFS queue
+// (src node, dst node) of a tree lives in its own slice of `queue`.
+//   action < 0 or inactive tree : the tree is kept as it is (reference: early return), i.e. copied with its own root
+//   reset_mask[t]               : the tree is replaced by a fresh unexpanded root for reset_states[t] (a new game)
+//   action not among the root's children : counters[1] |= 2 (the reference throws), tree kept
+//   queue / scratch exhausted   : counters[1] |= 4 / |= 1, the affected node is kept as an unexpanded leaf
+constexpr int32_t kFlagArena = 1, kFlagIllegalAdvance = 2, kFlagQueue = 4;
+
+__global__ void tree_advance_begin_kernel(lzb_tree A, lzb_tree B) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        B.counters[0] = (int32_t)A.num_trees; B.counters[1] = A.counters[1];
+        B.counters[2] = A.counters[2]; B.counters[3] = A.counters[3];
+    }
+}
+
+__device__ __forceinline__ void copy_node(const lzb_tree& A, int s, const lzb_tree& B, int d, uint32_t info, int parent) {
+    B.visit[d] = A.visit[s]; B.value_sum[d] = A.value_sum[s]; B.prior[d] = A.prior[s];
+    B.info[d] = info; B.first_child[d] = -1; B.parent[d] = parent;
+    store_packed(B.state, d, load_packed(A.state, s));
+}
+
+__global__ void __launch_bounds__(kThreads)
+tree_advance_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ actions, const uint64_t* __restrict__ reset_states,
+                    const uint8_t* __restrict__ reset_mask, int64_t* __restrict__ queue, int queue_cap) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t t = warp; t < A.num_trees; t += nwarps) {
+        const uint32_t root_inf = A.info[t];
+        if (reset_mask && reset_mask[t]) {                              // a new game starts in this slot
+            if (lane == 0) {
+                const Packed p = load_packed(reset_states, t);
+                State<int> s;
+                unpack(p, s);
+                store_packed(B.state, t, p);
+                B.visit[t] = 0; B.value_sum[t] = 0.0; B.prior[t] = 1.0; B.first_child[t] = -1; B.parent[t] = -1;
+                uint32_t inf = 0xFFu;
+                if (game_over(s)) inf |= kInfoTerminal;
+                if (s.player == -1) inf |= kInfoWhite;
+                B.info[t] = inf;
+                B.root_value[t] = 0.0;
+            }
+            continue;
+        }
+        int src_root = (int)t;
+        const int a = actions[t];
+        if (!(root_inf & kInfoInactive) && a >= 0) {
+            const int n = (root_inf & kInfoExpanded) ? info_nchild(root_inf) : 0;
+            const int fc = A.first_child[t];
+            int found = -1;
+            for (int base = 0; base < n && found < 0; base += 32) {
+                const int i = base + lane;
+                const bool hit = i < n && (int)(A.info[fc + i] & kInfoActionMask) == a;
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (m) found = base + __ffs(m) - 1;
+            }
+            if (found >= 0) src_root = fc + found;
+            else if (lane == 0) atomicOr(&B.counters[1], kFlagIllegalAdvance);
+        }
+        const uint32_t src_inf = A.info[src_root];
+        if (lane == 0) {
+            const uint32_t inf = ((src_inf & ~(kInfoActionMask | kInfoPending | kInfoInactive)) | 0xFFu) | (root_inf & kInfoInactive);
+            copy_node(A, src_root, B, (int)t, inf, -1);
+            B.root_value[t] = src_root == (int)t ? A.root_value[t] : 0.0;
+        }
+        int64_t* q = queue + t * (int64_t)queue_cap;
+        int head = 0, tail = 0;
+        if ((src_inf & kInfoExpanded) && info_nchild(src_inf) > 0) {
+            if (lane == 0) q[0] = ((int64_t)src_root << 32) | (uint32_t)t;
+            tail = 1;
+        }
+        __syncwarp();
+        while (head < tail) {
+            const int64_t e = q[head++];
+            const int s = (int)(e >> 32), d = (int)(e & 0xffffffff);
+            const uint32_t inf = A.info[s];
+            const int n = info_nchild(inf), sfc = A.first_child[s];
+            int dfc = 0;
+            if (lane == 0) {
+                dfc = atomicAdd(&B.counters[0], n);
+                if ((int64_t)dfc + n > B.capacity) { atomicOr(&B.counters[1], kFlagArena); dfc = -1; }
+            }
+            dfc = __shfl_sync(0xffffffffu, dfc, 0);
+            if (dfc < 0) {                                               // scratch exhausted: d stays an unexpanded leaf
+                if (lane == 0) B.info[d] = B.info[d] & ~(kInfoExpanded | (0xFFu << 8));
+                __syncwarp();
+                continue;
+            }
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                uint32_t ci = 0;
+                bool grow = false;
+                if (i < n) {
+                    ci = A.info[sfc + i] & ~kInfoPending;
+                    grow = (ci & kInfoExpanded) && info_nchild(ci) > 0;
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, grow);
+                const int pos = tail + __popc(m & ((1u << lane) - 1u));
+                if (grow && pos >= queue_cap) {                          // queue exhausted: keep as an unexpanded leaf
+                    ci &= ~(kInfoExpanded | (0xFFu << 8));
+                    atomicOr(&B.counters[1], kFlagQueue);
+                    grow = false;
+                }
+                if (i < n) copy_node(A, sfc + i, B, dfc + i, ci, d);
+                if (grow) q[pos] = ((int64_t)(sfc + i) << 32) | (uint32_t)(dfc + i);
+                tail = min(tail + __popc(m), queue_cap);
+            }
+            if (lane == 0) B.first_child[d] = dfc;
+            __syncwarp();
+        }
+    }
+}
+
+// scratch prefix [0, counters[0]) -> arena (the scratch never holds more nodes than the arena did)
+__global__ void __launch_bounds__(256)
+tree_copy_back_kernel(lzb_tree B, lzb_tree A) {
+    const int64_t n = min((int64_t)B.counters[0], min(A.capacity, B.capacity));
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = tid; i < n; i += stride) {
+        A.visit[i] = B.visit[i]; A.value_sum[i] = B.value_sum[i]; A.prior[i] = B.prior[i];
+        A.info[i] = B.info[i]; A.first_child[i] = B.first_child[i]; A.parent[i] = B.parent[i];
+    }
+    const ulonglong2* bs = reinterpret_cast<const ulonglong2*>(B.state);
+    ulonglong2* as = reinterpret_cast<ulonglong2*>(A.state);
+    for (int64_t i = tid; i < 2 * n; i += stride) as[i] = bs[i];
+    for (int64_t i = tid; i < A.num_trees; i += stride) A.root_value[i] = B.root_value[i];
+    if (tid < 4) A.counters[tid] = tid == 0 ? (int32_t)n : B.counters[tid];
 }
 
 // RootOutputs (portable_mcts.cpp:664-737) + RootPriors (:592-624)
@@ -550,8 +687,37 @@ extern "C" int lzb_tree_select(const lzb_tree* tree, int32_t K, double c_puct, d
     LZB_REQUIRE(c_puct >= 0.0 && c_puct == c_puct, "exploration_weight must be finite and non-negative");
     LZB_REQUIRE(leaf_node && leaf_status && leaf_states, "null output");
     tree_select_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(
-        *tree, K, c_puct, virtual_loss, leaf_node, leaf_status, leaf_states, leaf_path);
+        *tree, K, c_puct, virtual_loss, leaf_node, leaf_status, leaf_states, leaf_path, 0);
     return check_launch("tree_select_kernel");
+}
+
+extern "C" int lzb_tree_prepare_roots(const lzb_tree* tree, int32_t* leaf_node, int32_t* leaf_status,
+                                      uint64_t* leaf_states, void* stream) {
+    int rc = check_tree(tree);
+    if (rc) return rc;
+    LZB_REQUIRE(leaf_node && leaf_status && leaf_states, "null output");
+    tree_select_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(
+        *tree, 1, 0.0, 0.0, leaf_node, leaf_status, leaf_states, nullptr, 1);
+    return check_launch("tree_select_kernel(roots)");
+}
+
+extern "C" int lzb_tree_advance_roots(const lzb_tree* tree, const lzb_tree* scratch, const int32_t* actions,
+                                      const uint64_t* reset_states, const uint8_t* reset_mask, int64_t* queue,
+                                      int32_t queue_cap, void* stream) {
+    int rc = check_tree(tree);
+    if (rc) return rc;
+    rc = check_tree(scratch);
+    if (rc) return rc;
+    LZB_REQUIRE(scratch->num_trees == tree->num_trees && scratch->capacity >= tree->num_trees, "scratch arena mismatch");
+    LZB_REQUIRE(scratch->visit != tree->visit && scratch->state != tree->state, "scratch arena must not alias the tree");
+    LZB_REQUIRE(actions && queue && queue_cap >= 1, "null actions / queue");
+    LZB_REQUIRE((reset_states == nullptr) == (reset_mask == nullptr), "reset_states and reset_mask go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    tree_advance_begin_kernel<<<1, 32, 0, st>>>(*tree, *scratch);
+    tree_advance_kernel<<<warp_grid(tree->num_trees), kThreads, 0, st>>>(*tree, *scratch, actions, reset_states, reset_mask,
+                                                                        queue, queue_cap);
+    tree_copy_back_kernel<<<148 * 8, 256, 0, st>>>(*scratch, *tree);
+    return check_launch("tree_advance_kernel");
 }
 
 extern "C" int lzb_tree_expand_backup(const lzb_tree* tree, int32_t K, const int32_t* leaf_node,

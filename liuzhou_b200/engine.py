@@ -32,7 +32,7 @@ class SelfPlayStepper:
                  leaves_per_wave: int = 1, add_dirichlet_noise: bool = True, dirichlet_alpha: float = 0.3,
                  dirichlet_epsilon: float = 0.25, temperature_init: float = 1.0, temperature_final: float = 0.1,
                  temperature_threshold: int = 10, max_game_plies: int = 512, sample_moves: bool = True,
-                 seed: int = 0, ring_steps: int = 4, device=None):
+                 seed: int = 0, ring_steps: int = 4, device=None, reuse_subtree: bool = False):
         self.net = net
         self.device = torch.device(device) if device is not None else net.device
         self.g = int(num_games)
@@ -42,7 +42,7 @@ class SelfPlayStepper:
             num_simulations=int(simulations), exploration_weight=float(exploration_weight),
             add_dirichlet_noise=bool(add_dirichlet_noise), dirichlet_alpha=float(dirichlet_alpha),
             dirichlet_epsilon=float(dirichlet_epsilon), sample_moves=bool(sample_moves),
-            leaves_per_wave=int(leaves_per_wave)), self.device)
+            leaves_per_wave=int(leaves_per_wave), reuse_subtree=bool(reuse_subtree)), self.device)
         dev = self.device
         self.states = native.init_states(self.g, dev)
         self.plies = torch.zeros((self.g,), dtype=torch.int32, device=dev)
@@ -109,6 +109,8 @@ class SelfPlayStepper:
         self.states = torch.where(done.view(-1, 1), self._init_state.expand(g, 4), nxt).contiguous()
         self.plies = torch.where(done, torch.zeros_like(self.plies), self.plies)
         self._last_done = done
+        # subtree reuse: the played child becomes the root; finished games restart from a fresh root
+        self.mcts.advance(torch.where(done, torch.full_like(chosen, -1), chosen), self.states, done)
 
     def trajectory_block(self, ring_index: Optional[int] = None):
         """(planes, legal, policy, sign) rows of one ply in the reference format."""

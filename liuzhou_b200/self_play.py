@@ -95,6 +95,7 @@ def self_play_v1_gpu(
     verbose: bool = False,
     search_backend: str = "root",
     leaves_per_wave: int = 1,
+    tree_reuse: bool = True,
 ) -> Tuple[TensorSelfPlayBatch, SelfPlayV1Stats]:
     if num_games <= 0:
         raise ValueError("num_games must be positive.")
@@ -140,7 +141,9 @@ def self_play_v1_gpu(
                 num_simulations=sims, exploration_weight=float(exploration_weight),
                 add_dirichlet_noise=bool(add_dirichlet_noise), dirichlet_alpha=float(dirichlet_alpha),
                 dirichlet_epsilon=float(dirichlet_epsilon), sample_moves=bool(sample_moves),
-                leaves_per_wave=int(leaves_per_wave)), dev)
+                leaves_per_wave=int(leaves_per_wave), reuse_subtree=bool(tree_reuse)), dev)
+        if tree_mcts is not None:
+            tree_mcts._advanced = False          # a new wave of games starts from reset roots
 
         while True:
             active_idx = torch.where(~done)[0]
@@ -185,6 +188,8 @@ def self_play_v1_gpu(
                 meta_a = meta_all.index_select(0, active_idx)
                 chosen_codes = meta_a.gather(1, chosen_a.clamp_min(0).view(-1, 1, 1).expand(-1, 1, 4)).view(-1, 4)
                 chosen_codes = torch.where(chosen_valid.view(-1, 1), chosen_codes, torch.full_like(chosen_codes, -1))
+                # subtree reuse (portable_cpp_self_play.py:170): played child -> root; finished / inactive games keep -1
+                tree_mcts.advance(torch.where(done | out.terminal_mask, torch.full_like(chosen_all, -1), chosen_all))
 
             step_indices = buffer.append_steps(model_input=model_input, legal_mask=legal_mask,
                                                policy_dense=policy_dense, player_sign=player_sign)

@@ -25,12 +25,16 @@ class _TreeStruct(ctypes.Structure):
                                                                              ("num_trees", ctypes.c_int64)]
 
 
+_ARENA_FIELDS = ("visit", "value_sum", "prior", "info", "first_child", "parent", "state", "root_value", "counters")
+FLAG_ARENA, FLAG_ILLEGAL_ADVANCE, FLAG_QUEUE = 1, 2, 4       # sticky bits of counters[1]
+
+
 class DeviceTreeBatch:
     """``num_trees`` independent search trees in one node arena on one GPU."""
 
     def __init__(self, num_trees: int, device="cuda", *, exploration_weight: float = 1.0, leaves_per_wave: int = 1,
                  virtual_loss: float = 1.0, node_capacity: Optional[int] = None,
-                 nodes_per_tree_hint: int = 200 * 40) -> None:
+                 nodes_per_tree_hint: int = 200 * 40, reuse_queue_per_tree: int = 4096) -> None:
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("DeviceTreeBatch needs a CUDA device (no CPU path)")
@@ -70,11 +74,16 @@ class DeviceTreeBatch:
                 self.root_leaf_status = torch.full((t,), LEAF_DONE, dtype=torch.int32, device=dev)
                 self.root_leaf_states = torch.zeros((t, 4), dtype=torch.int64, device=dev)
         self._struct = _TreeStruct()
-        for name in ("visit", "value_sum", "prior", "info", "first_child", "parent", "state", "root_value", "counters"):
+        for name in _ARENA_FIELDS:
             setattr(self._struct, name, getattr(self, name).data_ptr())
         self._struct.capacity = cap
         self._struct.num_trees = t
         self._pending_is_root = False
+        # second arena + BFS work lists for advance_roots (subtree reuse); allocated on first use
+        self.reuse_queue_per_tree = int(reuse_queue_per_tree)
+        self._scratch: Optional[dict] = None
+        self._scratch_struct: Optional[_TreeStruct] = None
+        self._queue: Optional[torch.Tensor] = None
 
     # -- protocol ------------------------------------------------------------------------------------
     def reset(self, root_states: torch.Tensor, active: Optional[torch.Tensor] = None) -> None:
@@ -95,14 +104,94 @@ class DeviceTreeBatch:
                                         ptr(self.leaf_path), stream_ptr(self.device)))
 
     def prepare_roots(self) -> None:
-        """Unexpanded, non-terminal roots become the pending leaves (one slot per tree, whatever K is).
-        Valid right after reset(): an unexpanded root ends the descent immediately, so leaf == root."""
+        """Unexpanded, non-terminal, active roots become the pending leaves (one slot per tree, whatever K is);
+        roots that kept their subtree through advance_roots() need no evaluation (portable_mcts.cpp:483-513)."""
         with torch.cuda.device(self.device):
-            check(lib().lzb_tree_select(ctypes.byref(self._struct), ctypes.c_int32(1),
-                                        ctypes.c_double(self.exploration_weight), ctypes.c_double(0.0),
-                                        ptr(self.root_leaf_node), ptr(self.root_leaf_status),
-                                        ptr(self.root_leaf_states), ptr(None), stream_ptr(self.device)))
+            check(lib().lzb_tree_prepare_roots(ctypes.byref(self._struct), ptr(self.root_leaf_node),
+                                               ptr(self.root_leaf_status), ptr(self.root_leaf_states),
+                                               stream_ptr(self.device)))
         self._pending_is_root = True
+
+    def _ensure_scratch(self) -> None:
+        if self._scratch is not None:
+            return
+        dev, cap, t = self.device, self.capacity, self.num_trees
+        with torch.cuda.device(dev):
+            sc = {"visit": torch.empty((cap,), dtype=torch.int32, device=dev),
+                  "value_sum": torch.empty((cap,), dtype=torch.float64, device=dev),
+                  "prior": torch.empty((cap,), dtype=torch.float64, device=dev),
+                  "info": torch.empty((cap,), dtype=torch.int32, device=dev),
+                  "first_child": torch.empty((cap,), dtype=torch.int32, device=dev),
+                  "parent": torch.empty((cap,), dtype=torch.int32, device=dev),
+                  "state": torch.empty((cap, 4), dtype=torch.int64, device=dev),
+                  "root_value": torch.zeros((t,), dtype=torch.float64, device=dev),
+                  "counters": torch.zeros((4,), dtype=torch.int32, device=dev)}
+            self._queue = torch.empty((t * self.reuse_queue_per_tree,), dtype=torch.int64, device=dev)
+        st = _TreeStruct()
+        for name in _ARENA_FIELDS:
+            setattr(st, name, sc[name].data_ptr())
+        st.capacity, st.num_trees = cap, t
+        self._scratch, self._scratch_struct = sc, st
+
+    def advance_roots(self, actions: torch.Tensor, reset_states: Optional[torch.Tensor] = None,
+                      reset_mask: Optional[torch.Tensor] = None) -> None:
+        """Subtree reuse after a real move (``PortableTreeBatch.advance_roots``, portable_mcts.cpp:739-768): the child
+        reached by ``actions[t]`` (action index; < 0 = keep the tree as it is) becomes the root of tree t with all its
+        statistics.  ``reset_mask`` / ``reset_states`` start a new game in the marked slots (fresh unexpanded root).
+        The arena is compacted in the same pass, so node indices change and memory use stays bounded over a game.
+        No pending evaluation may be outstanding.  Asynchronous; errors surface in ``check_capacity()``."""
+        t = self.num_trees
+        require_cuda(actions, "actions")
+        if actions.numel() != t:
+            raise RuntimeError(f"actions must contain one entry per tree ({t})")
+        if (reset_states is None) != (reset_mask is None):
+            raise RuntimeError("reset_states and reset_mask go together")
+        a = actions.to(torch.int32).contiguous()
+        rs = rm = None
+        if reset_states is not None:
+            require_cuda(reset_states, "reset_states")
+            if tuple(reset_states.shape) != (t, 4):
+                raise RuntimeError(f"reset_states must be int64[{t}, 4]")
+            rs = reset_states.contiguous()
+            rm = reset_mask.to(device=self.device, dtype=torch.bool).contiguous()
+        self._ensure_scratch()
+        with torch.cuda.device(self.device):
+            check(lib().lzb_tree_advance_roots(ctypes.byref(self._struct), ctypes.byref(self._scratch_struct), ptr(a),
+                                               ptr(rs), ptr(rm), ptr(self._queue),
+                                               ctypes.c_int32(self.reuse_queue_per_tree), stream_ptr(self.device)))
+
+    def deactivate(self, tree_indices) -> None:
+        """``PortableTreeBatch.deactivate`` (:770-778): the listed trees are skipped by every later call."""
+        idx = torch.as_tensor(tree_indices, dtype=torch.int64, device=self.device).view(-1)
+        if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= self.num_trees):
+            raise RuntimeError("deactivate tree index is out of range")
+        self.set_active(torch.ones((self.num_trees,), dtype=torch.bool, device=self.device).index_fill_(0, idx, False),
+                        only_clear=True)
+
+    def set_active(self, active: torch.Tensor, only_clear: bool = False) -> None:
+        """Set (or with ``only_clear`` just clear) the per-tree active flag from bool[T]; no host synchronisation."""
+        act = active.to(device=self.device, dtype=torch.bool).view(-1)
+        roots = self.info[: self.num_trees]
+        bit = 1 << 21                                                     # kInfoInactive (csrc/lz_tree.cu)
+        roots.copy_(torch.where(act, roots if only_clear else roots & ~bit, roots | bit))
+
+    def root_states(self) -> torch.Tensor:
+        """Packed states int64[T,4] of the current roots (a view into the arena)."""
+        return self.state[: self.num_trees]
+
+    def root_status(self) -> dict:
+        """``PortableTreeBatch.root_status`` (:780-822) as device tensors."""
+        from .engine import _popcount36, packed_status
+
+        p = self.root_states()
+        over, winner = packed_status(p)
+        meta = (p[:, 0] >> 36) & 0xFFFFFFF
+        mask36 = (1 << 36) - 1
+        return {"winner": winner.to(torch.int32), "black_pieces": _popcount36(p[:, 0] & mask36).to(torch.int32),
+                "white_pieces": _popcount36(p[:, 1] & mask36).to(torch.int32),
+                "current_players": (1 - 2 * ((meta >> 3) & 1)).to(torch.int32), "phases": (meta & 7).to(torch.int32),
+                "move_counts": ((meta >> 14) & 255).to(torch.int32),
+                "moves_since_capture": ((meta >> 22) & 63).to(torch.int32), "game_over": over}
 
     def select_leaves(self) -> None:
         self._select(self.k)
@@ -163,12 +252,18 @@ class DeviceTreeBatch:
 
     def stats(self) -> dict:
         c = self.counters.tolist()
-        return {"nodes_used": int(c[0]), "overflow": bool(c[1]), "expansions": int(c[2]), "terminal_hits": int(c[3]),
-                "capacity": self.capacity}
+        return {"nodes_used": int(c[0]), "overflow": bool(c[1] & (FLAG_ARENA | FLAG_QUEUE)), "flags": int(c[1]),
+                "expansions": int(c[2]), "terminal_hits": int(c[3]), "capacity": self.capacity}
 
     def check_capacity(self) -> None:
-        if int(self.counters[1].item()):
+        flags = int(self.counters[1].item())
+        if flags & FLAG_ILLEGAL_ADVANCE:
+            raise RuntimeError("selected action is not a child of the current root")       # the reference's message
+        if flags & FLAG_ARENA:
             raise RuntimeError(f"tree node arena exhausted (capacity {self.capacity}); raise node_capacity")
+        if flags & FLAG_QUEUE:
+            raise RuntimeError(f"advance_roots work list exhausted ({self.reuse_queue_per_tree} per tree); "
+                               "raise reuse_queue_per_tree")
 
 
 def encode_inputs(packed: torch.Tensor, layout: str = "f32_nchw", out: Optional[torch.Tensor] = None) -> torch.Tensor:

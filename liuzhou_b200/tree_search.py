@@ -29,6 +29,9 @@ class TreeMCTSConfig:
     virtual_loss: float = 1.0
     nodes_per_tree_hint: Optional[int] = None
     use_cuda_graph: bool = True
+    # keep the played child's subtree between consecutive searches of a game (``advance()`` after every move), as the
+    # reference's portable self-play does (portable_cpp_self_play.py:170, portable_mcts.cpp:739-768)
+    reuse_subtree: bool = False
 
 
 @dataclass
@@ -51,9 +54,12 @@ class TreeMCTS:
         k = max(1, int(config.leaves_per_wave))
         waves = -(-int(config.num_simulations) // k)
         self.waves = waves
-        hint = config.nodes_per_tree_hint or min((waves * k + 2) * 40, 60_000)
+        # with reuse a root starts from the statistics it inherited (up to a few x num_simulations visits)
+        hint = config.nodes_per_tree_hint or min((waves * k + 2) * 40, 60_000) * (3 if config.reuse_subtree else 1)
         self.tree = DeviceTreeBatch(self.num_trees, self.device, exploration_weight=config.exploration_weight,
-                                    leaves_per_wave=k, virtual_loss=config.virtual_loss, nodes_per_tree_hint=hint)
+                                    leaves_per_wave=k, virtual_loss=config.virtual_loss, nodes_per_tree_hint=hint,
+                                    reuse_queue_per_tree=max(1024, 16 * waves * k))
+        self._advanced = False
         t, slots = self.num_trees, self.num_trees * k
         dev = self.device
         self._root_in = net.new_input(t)
@@ -122,15 +128,33 @@ class TreeMCTS:
         many = legal.sum(dim=1, keepdim=True) > 1
         self.tree.set_root_priors(torch.where(many, mixed, pri))
 
+    def advance(self, actions: torch.Tensor, restart_states: Optional[torch.Tensor] = None,
+                restart_mask: Optional[torch.Tensor] = None) -> None:
+        """After the moves of a ply are chosen: tree t continues from the child reached by ``actions[t]`` (< 0: tree
+        kept as it is); slots in ``restart_mask`` start a new game from ``restart_states``.  The next ``search()``
+        then skips the reset and every root starts from its inherited subtree.  No-op unless ``reuse_subtree``."""
+        if not self.cfg.reuse_subtree:
+            return
+        self.tree.advance_roots(actions, restart_states, restart_mask)
+        self._advanced = True
+
     @torch.no_grad()
     def search(self, root_states: torch.Tensor, *, active: Optional[torch.Tensor] = None,
                temperatures: Optional[torch.Tensor] = None, add_dirichlet_noise: Optional[bool] = None,
                sample_moves: Optional[bool] = None) -> TreeSearchOutput:
         cfg = self.cfg
         tree = self.tree
-        tree.reset(root_states, active)
+        keep = bool(cfg.reuse_subtree) and self._advanced      # roots already in place (advance() after the last move)
+        self._advanced = False
+        if keep:
+            if active is not None:
+                tree.set_active(active)
+        else:
+            tree.reset(root_states, active)
         use_graph = bool(cfg.use_cuda_graph)
         if use_graph and self._wave_graph is None:
+            if keep:
+                raise RuntimeError("TreeMCTS: the first search must start from reset roots")
             self._capture()
             tree.reset(root_states, active)
         if use_graph:

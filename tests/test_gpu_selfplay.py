@@ -341,3 +341,78 @@ def test_tree_search_full_size_properties():
     assert bool((chosen[live] >= 0).all()) and bool(legal[live].gather(1, chosen[live].view(-1, 1)).all())
     assert bool((v1[live].gather(1, chosen[live].view(-1, 1)).view(-1) == v1[live].max(1).values).all())
     assert bool((chosen[~live] == -1).all())
+
+
+def test_tree_mcts_subtree_reuse_across_moves_vs_oracle_replay():
+    """TreeMCTS(reuse_subtree=True): search -> advance(chosen) -> search ... over 4 moves (CUDA-graph waves) gives, at
+    every move, the visit counts of an oracle tree driven through prepare_roots / select_leaves / advance_roots with
+    the same GPU network as evaluator; and the roots the device tree holds are the states the game moved to."""
+    from liuzhou_b200 import native
+    from liuzhou_b200.net import InferenceNet
+    from liuzhou_b200.tree import encode_inputs, heads_to_priors
+    from liuzhou_b200.tree_search import TreeMCTS, TreeMCTSConfig
+
+    st = _playout_states(5, 41, every=9)
+    n = st["board"].shape[0]
+    sims = 40
+    net = InferenceNet(_small_net(), DEV)
+
+    def gpu_eval(pend_states, tree_idx):
+        full = oracle.initial_states(n)
+        for k in STATE_FIELDS:
+            full[k][tree_idx] = pend_states[k]
+        pk = native.pack_states(to_torch(full, DEV))
+        lp1, lp2, lpm, vl = net._forward_eager(encode_inputs(pk, "bf16_nhwc"))
+        p, v = heads_to_priors(pk, lp1, lp2, lpm, vl)
+        return _np(p)[tree_idx], _np(v)[tree_idx]
+
+    mcts = TreeMCTS(net, n, TreeMCTSConfig(num_simulations=sims, exploration_weight=1.25, add_dirichlet_noise=False,
+                                           sample_moves=False, reuse_subtree=True), DEV)
+    ref = oracle.TreeBatch(st, 1.25)
+    states = native.pack_states(to_torch(st, DEV))
+    inherited = 0
+    for move in range(4):
+        out = mcts.search(states, temperatures=torch.ones(n, device=DEV))
+        pend = ref.prepare_roots()
+        if len(pend["tree_indices"]):
+            ref.complete_pending(*gpu_eval(ref.pending_states(), pend["tree_indices"]))
+        else:
+            ref.complete_pending(np.zeros((0, 220), np.float32), np.zeros((0,), np.float32))
+        for _ in range(sims):
+            pend = ref.select_leaves()
+            ref.complete_pending(*gpu_eval(ref.pending_states(), pend["tree_indices"]))
+        ro = ref.root_outputs()
+        visits = _np(out.visit_counts)
+        assert np.array_equal(ro["visit_counts"], visits), move
+        live = ~_np(out.terminal_mask)
+        if move > 0:
+            inherited += int((visits[live].sum(1) > sims).sum())
+        chosen = out.chosen_action_indices
+        nxt = native.apply_actions(states, chosen.clamp_min(0).to(torch.int32))
+        states = torch.where((chosen >= 0).view(-1, 1), nxt, states).contiguous()
+        mcts.advance(chosen)
+        ref.advance_roots(_np(chosen).astype(np.int32))
+        mcts.tree.check_capacity()
+        assert torch.equal(mcts.tree.root_states(), states), move
+    assert inherited > 0            # some roots really started from inherited visits
+
+
+def test_stepper_with_subtree_reuse_keeps_roots_in_sync():
+    from liuzhou_b200.engine import SelfPlayStepper
+    from liuzhou_b200.net import InferenceNet
+
+    net = InferenceNet(_small_net(), DEV)
+    torch.manual_seed(3)
+    sp = SelfPlayStepper(net, 256, simulations=24, seed=11, device=DEV, reuse_subtree=True, max_game_plies=40)
+    sp.diversify(seed=5, max_random_plies=30, groups=4)
+    finished = 0
+    for ply in range(14):
+        sp.step()
+        sp.mcts.tree.check_capacity()
+        assert torch.equal(sp.mcts.tree.root_states(), sp.states), ply        # tree roots == game states, restarts incl.
+        finished += int(sp._last_done.sum())
+        legal, policy = sp.trajectory_block()[1], sp.trajectory_block()[2]
+        assert torch.all((policy > 0) <= legal)
+    assert finished > 0                                                        # restarts were exercised
+    used = sp.mcts.tree.stats()["nodes_used"]
+    assert used < 256 * 24 * 40 * 3                                            # compaction bounds the arena

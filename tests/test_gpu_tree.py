@@ -240,3 +240,149 @@ def test_encode_inputs_and_heads_to_priors():
     probs = torch.softmax(logits, 1)
     ev = (probs * torch.linspace(-1.0, 1.0, 101)).sum(1).numpy()   # neural_network.py:201-210
     np.testing.assert_allclose(_np(val), ev, rtol=1e-5, atol=1e-6)
+
+
+def _search_both(ref, tree, native, sims, move):
+    """prepare_roots + `sims` waves on both; every pending batch (tree indices, inputs, masks) must agree."""
+    pend = ref.prepare_roots()
+    tree.prepare_roots()
+    rows, inputs, masks = _pending_from_device(tree, native)
+    assert np.array_equal(rows, pend["tree_indices"]), move
+    assert np.array_equal(inputs, pend["model_inputs"]) and np.array_equal(masks, pend["legal_masks"]), move
+    pri, val = fake_net(pend["model_inputs"], pend["legal_masks"], 0)
+    ref.complete_pending(pri, val)
+    _complete(tree, rows, pri, val)
+    for s in range(sims):
+        pend = ref.select_leaves()
+        tree.select_leaves()
+        rows, inputs, masks = _pending_from_device(tree, native)
+        assert np.array_equal(rows, pend["tree_indices"]), (move, s)
+        assert np.array_equal(inputs, pend["model_inputs"]), (move, s)
+        pri, val = fake_net(inputs, masks, 1)
+        ref.complete_pending(pri, val)
+        _complete(tree, rows, pri, val)
+
+
+def _assert_root_outputs_equal(ref, tree):
+    ro, mo = ref.root_outputs(), tree.root_outputs()
+    assert np.array_equal(_np(mo["visit_counts"]), ro["visit_counts"])
+    assert np.array_equal(_np(mo["legal_masks"]).astype(np.uint8), ro["legal_masks"])
+    assert np.array_equal(_np(mo["root_action_values"]), ro["root_action_values"])
+    assert np.array_equal(_np(mo["root_values"]), ro["root_values"])
+    assert np.array_equal(_np(mo["terminal"]).astype(np.uint8), ro["terminal"])
+    assert np.array_equal(_np(mo["root_priors"]), ref.root_priors()["priors"])
+    return ro
+
+
+@pytest.mark.parametrize("sims,c_puct,pick", [(64, 1.0, "max"), (120, 1.5, "second")])
+def test_tree_advance_roots_subtree_reuse_identical_to_oracle(sims, c_puct, pick):
+    """advance_roots (portable_mcts.cpp:739-768): after each searched move the played child becomes the root and
+    keeps its subtree; the next search starts from those statistics.  Visit counts / Q / priors / root values and
+    every pending batch stay identical to the oracle over 5 consecutive moves (the oracle itself is pinned against
+    the reference binary on exactly this protocol, tests/test_oracle_vs_reference.py)."""
+    from liuzhou_b200 import native
+    from liuzhou_b200.tree import DeviceTreeBatch
+
+    st = _playout_states(4, 77, every=11)
+    n = st["board"].shape[0]
+    ref = oracle.TreeBatch(st, c_puct)
+    tree = DeviceTreeBatch(n, DEV, exploration_weight=c_puct, nodes_per_tree_hint=(sims + 2) * 64 * 3)
+    tree.reset(native.pack_states(to_torch(st, DEV)))
+    for move in range(5):
+        _search_both(ref, tree, native, sims, move)
+        ro = _assert_root_outputs_equal(ref, tree)
+        v = ro["visit_counts"].astype(np.int64)
+        if pick == "second":                      # a less-visited (possibly unvisited -> unexpanded) child
+            order = np.argsort(-(v * 1000 + ro["legal_masks"]), axis=1, kind="stable")
+            cand = order[:, 1]
+            ok = ro["legal_masks"][np.arange(n), cand] != 0
+            actions = np.where(ok, cand, order[:, 0])
+        else:
+            actions = v.argmax(1)
+        actions = np.where((ro["terminal"] != 0) | (ro["legal_masks"].sum(1) == 0), -1, actions).astype(np.int32)
+        ref.advance_roots(actions)
+        tree.advance_roots(torch.from_numpy(actions).to(DEV))
+        tree.check_capacity()
+        # the new roots' states agree with the oracle's
+        for i in (0, n // 2, n - 1):
+            want = native.pack_states(to_torch(ref.root_state(i), DEV))
+            assert torch.equal(tree.root_states()[i], want[0])
+        status = tree.root_status()
+        assert status["game_over"].shape == (n,)
+    # inherited statistics really were reused: live roots carry more visits than one search adds
+    total = _np(tree.root_outputs()["visit_counts"]).sum(1)
+    assert total.max() > 0
+
+
+def test_tree_advance_roots_reset_deactivate_and_errors():
+    from liuzhou_b200 import native
+    from liuzhou_b200.tree import DeviceTreeBatch
+
+    st = _playout_states(2, 5, every=17)
+    n = st["board"].shape[0]
+    sims = 40
+    ref = oracle.TreeBatch(st, 1.0)
+    tree = DeviceTreeBatch(n, DEV, exploration_weight=1.0, nodes_per_tree_hint=(sims + 2) * 64 * 3)
+    packed0 = native.pack_states(to_torch(st, DEV))
+    tree.reset(packed0)
+    _search_both(ref, tree, native, sims, 0)
+    ro = _assert_root_outputs_equal(ref, tree)
+    actions = np.where(ro["terminal"] != 0, -1, ro["visit_counts"].argmax(1)).astype(np.int32)
+    # tree 0 restarts from the initial position, tree 1 is deactivated, the rest advance
+    reset_mask = np.zeros((n,), bool)
+    reset_mask[0] = True
+    reset_states = packed0.clone()
+    reset_states[0] = native.init_states(1, DEV)[0]
+    tree.advance_roots(torch.from_numpy(actions).to(DEV), reset_states, torch.from_numpy(reset_mask).to(DEV))
+    tree.deactivate([1])
+    ref.advance_roots(actions)
+    ref.deactivate([1])
+    fresh = oracle.TreeBatch(oracle.initial_states(1), 1.0)
+    # second search: compare all trees but 0 with `ref`, tree 0 with a fresh oracle tree
+    pend_ref = ref.prepare_roots()
+    pend_fresh = fresh.prepare_roots()
+    tree.prepare_roots()
+    rows, inputs, masks = _pending_from_device(tree, native)
+    want_rows = sorted([0] + [int(r) for r in pend_ref["tree_indices"] if r != 0])
+    assert list(rows) == want_rows and 1 not in rows
+    pri, val = fake_net(inputs, masks, 0)
+    _complete(tree, rows, pri, val)
+    ref.complete_pending(*fake_net(pend_ref["model_inputs"], pend_ref["legal_masks"], 0))
+    fresh.complete_pending(*fake_net(pend_fresh["model_inputs"], pend_fresh["legal_masks"], 0))
+    for _ in range(sims):
+        pr, pf = ref.select_leaves(), fresh.select_leaves()
+        tree.select_leaves()
+        rows, inputs, masks = _pending_from_device(tree, native)
+        _complete(tree, rows, *fake_net(inputs, masks, 1))
+        ref.complete_pending(*fake_net(pr["model_inputs"], pr["legal_masks"], 1))
+        fresh.complete_pending(*fake_net(pf["model_inputs"], pf["legal_masks"], 1))
+    mo = tree.root_outputs()
+    rv, fv = ref.root_outputs()["visit_counts"], fresh.root_outputs()["visit_counts"]
+    got = _np(mo["visit_counts"])
+    assert np.array_equal(got[0], fv[0])
+    assert np.array_equal(got[2:], rv[2:])
+    assert got[1].sum() == rv[1].sum()          # deactivated: nothing added after the advance
+    tree.check_capacity()
+    # an action that is not a child of the root is reported like the reference does (it throws)
+    bad = np.full((n,), -1, np.int32)
+    live = np.nonzero((_np(mo["terminal"]) == 0) & (np.arange(n) != 1))[0]
+    illegal = int(np.nonzero(_np(mo["legal_masks"])[live[0]] == 0)[0][0])
+    bad[live[0]] = illegal
+    tree.advance_roots(torch.from_numpy(bad).to(DEV))
+    with pytest.raises(RuntimeError, match="not a child"):
+        tree.check_capacity()
+    with pytest.raises(RuntimeError):
+        tree.advance_roots(torch.zeros((n + 1,), dtype=torch.int32, device=DEV))
+    # a work list that is too small is reported, not silently truncated
+    small = DeviceTreeBatch(n, DEV, exploration_weight=1.0, nodes_per_tree_hint=(sims + 2) * 64, reuse_queue_per_tree=2)
+    small.reset(packed0)
+    small.prepare_roots()
+    rows, inputs, masks = _pending_from_device(small, native)
+    _complete(small, rows, *fake_net(inputs, masks, 0))
+    for _ in range(sims):
+        small.select_leaves()
+        rows, inputs, masks = _pending_from_device(small, native)
+        _complete(small, rows, *fake_net(inputs, masks, 1))
+    small.advance_roots(torch.full((n,), -1, dtype=torch.int32, device=DEV))
+    with pytest.raises(RuntimeError, match="work list"):
+        small.check_capacity()
