@@ -484,19 +484,30 @@ def run_selfplay(args, world, rank, local_rank):
     stepper.diversify(seed=SEED + rank)
     stream = torch.cuda.current_stream(dev)
 
+    # N > 1: this ply's trajectory rows (all five tensors of the reference format) return to the trainer rank over NCCL
+    # in the compact lossless wire format (liuzhou_b200/compact.py, ~15x fewer bytes than 2,692 B/position).  The
+    # gather is issued on a side stream so that it overlaps the next ply's search; the ring keeps 4 plies, and before
+    # ply p the main stream waits for the gather of ply p-3, so a slot is never overwritten while in flight.
+    side = torch.cuda.Stream(dev) if world > 1 else None
+    gather_done = []
+
     def step():
+        if world > 1 and len(gather_done) >= 3:
+            stream.wait_event(gather_done[-3])
         stepper.step()
         if world > 1:
-            # this ply's trajectory rows (all five tensors of the reference format) return to the trainer rank over
-            # NCCL in the compact lossless wire format (liuzhou_b200/compact.py, ~15x fewer bytes than 2,692 B/position)
-            import torch as _t
-
             from liuzhou_b200.dist import gather_trajectories_compact
             from liuzhou_b200.trajectory_buffer import TensorSelfPlayBatch
 
-            planes, legal, policy, _sign = stepper.trajectory_block()
-            nan = _t.full((games,), float("nan"), device=dev)
-            gather_trajectories_compact(TensorSelfPlayBatch(planes, legal, policy, nan, nan), dst=0)
+            side.wait_stream(stream)
+            with torch.cuda.stream(side):
+                planes, legal, policy, _sign = stepper.trajectory_block()
+                nan = torch.full((games,), float("nan"), device=dev)
+                gather_trajectories_compact(TensorSelfPlayBatch(planes, legal, policy, nan, nan), dst=0)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                gather_done.append(ev)
+                del gather_done[:-4]
 
     for _ in range(args.warmup):
         step()
@@ -510,6 +521,8 @@ def run_selfplay(args, world, rank, local_rank):
     e0.record(stream)
     for _ in range(args.steps):
         step()
+    if world > 1:
+        stream.wait_stream(side)          # the last ply's gather is inside the timed region
     e1.record(stream)
     e1.synchronize()
     barrier_sync(world)
