@@ -426,6 +426,7 @@ def time_trunk_conv(net, n, stream, reps: int = 30) -> dict:
     t = net.trunk._t
     if not (net.trunk is not None and net.trunk.use_tc and n % 64 == 0):
         return {"ms": float("nan"), "ms_conv1": float("nan"), "ms_conv2": float("nan"), "tflops": float("nan"),
+                "ms_in_chain": float("nan"), "tflops_in_chain": float("nan"), "launches_in_chain": 0,
                 "flops_per_state": 0.0, "traffic_bytes": None}
     dev = net.device
     cl = torch.channels_last
@@ -452,12 +453,75 @@ def time_trunk_conv(net, n, stream, reps: int = 30) -> dict:
     ms1 = replay_ms(lambda: conv_bf16(a, t["wp1_0"], bias=t["bf1_0"], relu1=True, out1=o1))
     ms2 = replay_ms(lambda: conv_bf16(a, t["wp2_0"], residual=res, scale=t["s1_1"], shift=t["t1_1"], want_out2=True,
                                       out1=o1, out2=o2))
+    # the same 20 launches as they run in the forward: one chain (conv1, conv2) x 10 with programmatic dependent launch
+    # between the layers (a layer's prologue / weight prefetch overlaps the previous layer's epilogue)
+    nb = len(net.trunk.model.blocks)
+
+    def chain():
+        xr, act = res, a
+        for i in range(nb):
+            h, _ = conv_bf16(act, t[f"wp1_{i}"], bias=t[f"bf1_{i}"], relu1=True)
+            last = i == nb - 1
+            sn, tn = ("trunk_s", "trunk_t") if last else (f"s1_{i + 1}", f"t1_{i + 1}")
+            xr, act = conv_bf16(h, t[f"wp2_{i}"], residual=xr, scale=t[sn], shift=t[tn], want_out1=not last, want_out2=True)
+
+    ms_chain = replay_ms(chain) / max(1, 2 * nb)
     flops_per_state = 2.0 * 36 * 128 * 128 * 9
     ms = 0.5 * (ms1 + ms2)
     # per-launch DRAM traffic of the 4,096-state launch measured by ncu (38.07 MB read + 2.78 MB written), scaled by n
     traffic = (38.074e6 + 2.776e6) * n / 4096.0
     return {"ms": ms, "ms_conv1": ms1, "ms_conv2": ms2, "tflops": n * flops_per_state / (ms / 1e3) / 1e12,
-            "flops_per_state": flops_per_state, "traffic_bytes": traffic}
+            "ms_in_chain": ms_chain, "tflops_in_chain": n * flops_per_state / (ms_chain / 1e3) / 1e12,
+            "launches_in_chain": 2 * nb, "flops_per_state": flops_per_state, "traffic_bytes": traffic}
+
+
+def time_tree_kernels(stepper, peaks, reps: int = 20) -> dict:
+    """select and expand+backup of one simulation wave, launched eagerly and timed with CUDA events on their stream
+    (inside the wave graph they run back to back with the network); algorithmic bytes from the tree's own counters:
+    select  = 28 B per sibling record scanned (visit 4 + info 4 + first_child 4 + prior 8 + value_sum 8) + per
+              simulation 12 B root header + 32 B leaf state read + 32 B leaf state / 8 B slot / 136 B path written;
+    expand  = per expanded leaf 32 B state + 880 B priors + 4 B value read, 64 B per child node written,
+              12 B read + 12 B written per node on the backed-up path + 136 B path read."""
+    import torch
+
+    from liuzhou_b200.tree import encode_inputs
+
+    m, tree = stepper.mcts, stepper.mcts.tree
+    stream = torch.cuda.current_stream(stepper.device)
+    torch.cuda.synchronize()
+    c0 = tree.stats()
+    ev = []
+    for _ in range(reps):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record(stream)
+        tree.select_leaves()
+        e[1].record(stream)
+        encode_inputs(tree.pending_states, "bf16_nhwc", out=m._wave_in)
+        m.net.forward_priors(m._wave_in, tree.pending_states, priors_out=m._wave_pri, values_out=m._wave_val)
+        e[2].record(stream)
+        tree.complete_pending(m._wave_pri, m._wave_val)
+        e[3].record(stream)
+        ev.append(e)
+    torch.cuda.synchronize()
+    c1 = tree.stats()
+    sel_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / reps
+    exp_ms = sum(e[2].elapsed_time(e[3]) for e in ev) / reps
+    sims = reps * tree.num_trees * tree.k
+    sibs = c1["siblings_scanned"] - c0["siblings_scanned"]
+    levels = c1["levels_descended"] - c0["levels_descended"]
+    new_nodes = c1["nodes_used"] - c0["nodes_used"]
+    expansions = c1["expansions"] - c0["expansions"]
+    sel_bytes = sibs * 28 + sims * (12 + 32 + 32 + 8 + 136)
+    exp_bytes = expansions * (32 + 880 + 4) + new_nodes * 64 + (levels + sims) * 24 + sims * 136
+    sel_gbs = sel_bytes / reps / (sel_ms / 1e3) / 1e9
+    exp_gbs = exp_bytes / reps / (exp_ms / 1e3) / 1e9
+    return {"bound": "hbm (latency-limited: one dependent HBM round trip per tree level, one warp per tree)",
+            "select_ms": sel_ms, "expand_backup_ms": exp_ms, "select_gbs": sel_gbs, "expand_backup_gbs": exp_gbs,
+            "peak_gbs": peaks["hbm_gbs"], "select_frac": sel_gbs / peaks["hbm_gbs"],
+            "expand_backup_frac": exp_gbs / peaks["hbm_gbs"],
+            "bytes_per_simulation": (sel_bytes + exp_bytes) / max(1, sims), "avg_depth": levels / max(1, sims),
+            "avg_siblings_per_level": sibs / max(1, levels), "children_per_expansion": new_nodes / max(1, expansions),
+            "ncu": "profiles/r01_tree_heads_ncu_full.csv (DRAM bytes, occupancy, issue utilisation of both kernels)"}
 
 
 def run_selfplay(args, world, rank, local_rank):
@@ -564,6 +628,7 @@ def run_selfplay(args, world, rank, local_rank):
     w1.synchronize()
     wave_ms = w0.elapsed_time(w1) / reps
     tflops = slots * net.flops_per_state / (fwd_ms / 1e3) / 1e12
+    tree_roof = time_tree_kernels(stepper, peaks)
     tree_stats = stepper.mcts.tree.stats()
     conv = time_trunk_conv(net, slots, stream)
 
@@ -646,8 +711,12 @@ def run_selfplay(args, world, rank, local_rank):
         "gpu_launches": int(launches),
         # dominant kernel: our tcgen05 implicit-GEMM convolution (20 of the 22 launches per forward are this 3x3
         # 128->128 instance); achieved = algorithmic FLOPs of one launch / its CUDA-event duration in a graph replay
-        "roofline": {"bound": "tensor", "achieved": conv["tflops"], "peak": peak, "unit": "TFLOP/s",
-                     "frac": conv["tflops"] / peak, "traffic": conv["traffic_bytes"],
+        # (average launch duration = the 20-launch trunk chain / 20, the way the launches run inside the step; a launch
+        # replayed alone, without the PDL overlap with its neighbours, is reported next to it)
+        "roofline": {"bound": "tensor", "achieved": conv["tflops_in_chain"], "peak": peak, "unit": "TFLOP/s",
+                     "frac": conv["tflops_in_chain"] / peak, "traffic": conv["traffic_bytes"],
+                     "kernel_ms_in_chain": conv["ms_in_chain"], "achieved_launch_alone": conv["tflops"],
+                     "frac_launch_alone": conv["tflops"] / peak,
                      "peak_kind": peak_kind + " (sustained bf16, cuBLAS)",
                      "kernel": "conv_tc_kernel<9,2> (csrc/lz_conv.cu: 3x3 128->128 conv, bf16 tcgen05.mma cta_group::2, "
                                "TMA im2col, fused bias/residual/BN/ReLU epilogue)",
@@ -657,8 +726,9 @@ def run_selfplay(args, world, rank, local_rank):
                      "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r01_conv_tc_ncu_full.csv",
                      "forward_ms": fwd_ms, "forward_tflops": tflops, "forward_frac_of_peak": tflops / peak,
                      "wave_ms": wave_ms, "tree_kernels_ms_per_wave": max(0.0, wave_ms - fwd_ms),
-                     "share_of_step": 10 * (conv["ms_conv1"] + conv["ms_conv2"]) * (waves + 1) / (elapsed_ms / args.steps)},
+                     "share_of_step": 20 * conv["ms_in_chain"] * (waves + 1) / (elapsed_ms / args.steps)},
         "tree": tree_stats,
+        "tree_roofline": tree_roof,
         "cpu_baseline": cpu,
     }
 
@@ -749,8 +819,12 @@ def run_selfplay_root(args, world, rank, local_rank):
         "gpu_launches": int(launches),
         "selfplay_stats": {"games": st.num_games, "positions": st.num_positions, "avg_game_length": st.avg_game_length,
                            "black_wins": st.black_wins, "white_wins": st.white_wins, "draws": st.draws},
-        "roofline": {"bound": "tensor", "achieved": conv["tflops"], "peak": peak, "unit": "TFLOP/s",
-                     "frac": conv["tflops"] / peak, "traffic": conv["traffic_bytes"],
+        # (average launch duration = the 20-launch trunk chain / 20, the way the launches run inside the step; a launch
+        # replayed alone, without the PDL overlap with its neighbours, is reported next to it)
+        "roofline": {"bound": "tensor", "achieved": conv["tflops_in_chain"], "peak": peak, "unit": "TFLOP/s",
+                     "frac": conv["tflops_in_chain"] / peak, "traffic": conv["traffic_bytes"],
+                     "kernel_ms_in_chain": conv["ms_in_chain"], "achieved_launch_alone": conv["tflops"],
+                     "frac_launch_alone": conv["tflops"] / peak,
                      "peak_kind": peak_kind + " (sustained bf16, cuBLAS)",
                      "kernel": "conv_tc_kernel<9,2> (csrc/lz_conv.cu)", "kernel_ms": conv["ms"], "units_per_launch": 4096,
                      "flops_per_unit": conv["flops_per_state"]},

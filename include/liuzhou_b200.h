@@ -202,8 +202,9 @@ LZB_API int lzb_playout_run(uint64_t *packed, int32_t *plies, int8_t *result, ui
  *      (v0/src/mcts/mcts_core.cpp:252-268,640-701).
  * Node arena (structure of arrays, `capacity` nodes; nodes [0, num_trees) are the roots):
  *   visit i32 | value_sum f64 | prior f64 | info u32 (action:8 | nchild:8 | flags) | first_child i32 |
- *   parent i32 | state u64[4] | root_value f64[num_trees] | counters i32[4] = {top, overflow, expansions,
- *   terminal hits}.
+ *   parent i32 | state u64[4] | root_value f64[num_trees] | counters i32[8] = {top, sticky flags
+ *   (see lzb_tree_advance_roots), expansions, terminal hits, sibling records scanned by select, levels descended,
+ *   2 x reserved}.
  * One warp per tree; K leaves per tree per wave (K = 1 reproduces the reference exactly).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {

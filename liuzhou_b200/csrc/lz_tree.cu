@@ -70,6 +70,7 @@ tree_init_kernel(lzb_tree A, const uint64_t* __restrict__ roots, const uint8_t* 
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         A.counters[0] = (int32_t)T; A.counters[1] = 0; A.counters[2] = 0; A.counters[3] = 0;
+        A.counters[4] = 0; A.counters[5] = 0;      // [4] sibling records scanned by select, [5] levels descended
     }
 }
 
@@ -140,10 +141,11 @@ tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restr
             // SelectPath :862-874.  One dependent HBM round trip per level: the sibling scan also fetches each
             // child's first_child / info / visit, so the next level needs nothing else from the chosen child.
             int fc = A.first_child[node], nv = A.visit[node];
-            int depth = 0, path_node = lane == 0 ? node : -1;
+            int depth = 0, path_node = lane == 0 ? node : -1, scanned = 0;
             bool path_white = lane == 0 && (inf & kInfoWhite);
             while ((inf & kInfoExpanded) && info_nchild(inf) > 0 && !(inf & kInfoTerminal)) {
                 const int n = info_nchild(inf);
+                scanned += n;
                 const double sqrt_total = sqrt((double)(nv > 1 ? nv : 1));
                 const uint32_t node_white = inf & kInfoWhite;
                 double best = -INFINITY;
@@ -180,6 +182,7 @@ tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restr
                 if (depth < kPathLanes && lane == depth) { path_node = node; path_white = (inf & kInfoWhite) != 0; }
             }
             const bool recorded = depth < kPathLanes;
+            if (lane == 0 && depth > 0) { atomicAdd(&A.counters[4], scanned); atomicAdd(&A.counters[5], depth); }
             const uint32_t white_mask = __ballot_sync(0xffffffffu, path_white);
             int status;
             if (inf & kInfoTerminal) {                               // :527-532
@@ -338,6 +341,7 @@ __global__ void tree_advance_begin_kernel(lzb_tree A, lzb_tree B) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         B.counters[0] = (int32_t)A.num_trees; B.counters[1] = A.counters[1];
         B.counters[2] = A.counters[2]; B.counters[3] = A.counters[3];
+        B.counters[4] = A.counters[4]; B.counters[5] = A.counters[5];
     }
 }
 
@@ -453,7 +457,7 @@ tree_copy_back_kernel(lzb_tree B, lzb_tree A) {
     ulonglong2* as = reinterpret_cast<ulonglong2*>(A.state);
     for (int64_t i = tid; i < 2 * n; i += stride) as[i] = bs[i];
     for (int64_t i = tid; i < A.num_trees; i += stride) A.root_value[i] = B.root_value[i];
-    if (tid < 4) A.counters[tid] = tid == 0 ? (int32_t)n : B.counters[tid];
+    if (tid < 6) A.counters[tid] = tid == 0 ? (int32_t)n : B.counters[tid];
 }
 
 // RootOutputs (portable_mcts.cpp:664-737) + RootPriors (:592-624)

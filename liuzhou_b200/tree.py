@@ -60,7 +60,7 @@ class DeviceTreeBatch:
             self.parent = torch.empty((cap,), dtype=torch.int32, device=dev)
             self.state = torch.empty((cap, 4), dtype=torch.int64, device=dev)
             self.root_value = torch.zeros((t,), dtype=torch.float64, device=dev)
-            self.counters = torch.zeros((4,), dtype=torch.int32, device=dev)
+            self.counters = torch.zeros((8,), dtype=torch.int32, device=dev)
             self.leaf_node = torch.full((slots,), -1, dtype=torch.int32, device=dev)
             self.leaf_status = torch.full((slots,), LEAF_DONE, dtype=torch.int32, device=dev)
             self.leaf_states = torch.zeros((slots, 4), dtype=torch.int64, device=dev)
@@ -125,7 +125,7 @@ class DeviceTreeBatch:
                   "parent": torch.empty((cap,), dtype=torch.int32, device=dev),
                   "state": torch.empty((cap, 4), dtype=torch.int64, device=dev),
                   "root_value": torch.zeros((t,), dtype=torch.float64, device=dev),
-                  "counters": torch.zeros((4,), dtype=torch.int32, device=dev)}
+                  "counters": torch.zeros((8,), dtype=torch.int32, device=dev)}
             self._queue = torch.empty((t * self.reuse_queue_per_tree,), dtype=torch.int64, device=dev)
         st = _TreeStruct()
         for name in _ARENA_FIELDS:
@@ -253,7 +253,8 @@ class DeviceTreeBatch:
     def stats(self) -> dict:
         c = self.counters.tolist()
         return {"nodes_used": int(c[0]), "overflow": bool(c[1] & (FLAG_ARENA | FLAG_QUEUE)), "flags": int(c[1]),
-                "expansions": int(c[2]), "terminal_hits": int(c[3]), "capacity": self.capacity}
+                "expansions": int(c[2]), "terminal_hits": int(c[3]), "capacity": self.capacity,
+                "siblings_scanned": int(c[4]) & 0xFFFFFFFF, "levels_descended": int(c[5]) & 0xFFFFFFFF}
 
     def check_capacity(self) -> None:
         flags = int(self.counters[1].item())
