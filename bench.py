@@ -549,9 +549,10 @@ def run_selfplay(args, world, rank, local_rank):
     stream = torch.cuda.current_stream(dev)
 
     # N > 1: this ply's trajectory rows (all five tensors of the reference format) return to the trainer rank over NCCL
-    # in the compact lossless wire format (liuzhou_b200/compact.py, ~15x fewer bytes than 2,692 B/position).  The
-    # gather is issued on a side stream so that it overlaps the next ply's search; the ring keeps 4 plies, and before
-    # ply p the main stream waits for the gather of ply p-3, so a slot is never overwritten while in flight.
+    # as fixed-size compact rows (liuzhou_b200/compact.py: 336 B instead of 2,692 B per position, lossless; static
+    # shapes, so nothing on the path synchronises with the host).  Compaction + gather are queued on a side stream and
+    # overlap the next ply's search; the ring keeps 4 plies, and before ply p the main stream waits for the gather of
+    # ply p-3, so a slot is never overwritten while in flight.
     side = torch.cuda.Stream(dev) if world > 1 else None
     gather_done = []
 
@@ -560,14 +561,15 @@ def run_selfplay(args, world, rank, local_rank):
             stream.wait_event(gather_done[-3])
         stepper.step()
         if world > 1:
-            from liuzhou_b200.dist import gather_trajectories_compact
+            from liuzhou_b200.compact import compact_rows_fixed
+            from liuzhou_b200.dist import gather_rows_fixed
             from liuzhou_b200.trajectory_buffer import TensorSelfPlayBatch
 
             side.wait_stream(stream)
             with torch.cuda.stream(side):
                 planes, legal, policy, _sign = stepper.trajectory_block()
                 nan = torch.full((games,), float("nan"), device=dev)
-                gather_trajectories_compact(TensorSelfPlayBatch(planes, legal, policy, nan, nan), dst=0)
+                gather_rows_fixed(compact_rows_fixed(TensorSelfPlayBatch(planes, legal, policy, nan, nan)), dst=0)
                 ev = torch.cuda.Event()
                 ev.record(side)
                 gather_done.append(ev)

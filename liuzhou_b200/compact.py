@@ -130,3 +130,74 @@ def concat(parts) -> CompactSelfPlayBatch:
                                 torch.cat([p.policy_value for p in parts]),
                                 torch.cat([p.value_targets for p in parts]),
                                 torch.cat([p.soft_value_targets for p in parts]))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Fixed-size rows for streaming (one ply of every game, every ply): no data-dependent shapes, hence no host
+# synchronisation anywhere on the path -- compaction, the NCCL gather and the expansion can all be queued on a side
+# stream while the next ply is searched.
+#   words [0,4)   boards + phase (as above)
+#   words [4,8)   legal bits
+#   words [8,40)  64 x f32: the policy values of the legal actions in ascending action order (a position has at most
+#                 64 legal actions: <= 36 placements; moves <= 4 * min(own pieces, empty cells) with own + empty <= 32
+#                 because the opponent keeps >= 4 pieces; selections <= 18), zero beyond the legal count
+#   word  40      value target | soft value target (2 x f32, NaN preserved)
+#   word  41      flags: bit 0 = row not representable (policy mass on an illegal action or > 64 legal actions)
+# 336 B per position instead of 2,692 B.
+# ----------------------------------------------------------------------------------------------------------------------
+FIXED_ROW_WORDS = 42
+_FIXED_SLOTS = 64
+
+
+def _legal_order(legal: torch.Tensor) -> torch.Tensor:
+    """int64[n,64]: indices of the legal actions in ascending order first (then illegal ones, ascending)."""
+    key = (~legal).to(torch.int16) * ACTION_DIM + torch.arange(ACTION_DIM, device=legal.device, dtype=torch.int16)
+    return torch.argsort(key, dim=1)[:, :_FIXED_SLOTS]
+
+
+def compact_rows_fixed(batch: TensorSelfPlayBatch) -> torch.Tensor:
+    """-> int64[n, FIXED_ROW_WORDS]; never synchronises with the host (validity travels in the flags word)."""
+    x = batch.state_tensors
+    n = int(x.shape[0])
+    dev = x.device
+    flat = x.reshape(n, 11, 36)
+    legal = batch.legal_masks.to(torch.bool)
+    pol = batch.policy_targets.to(torch.float32)
+    out = torch.empty((n, FIXED_ROW_WORDS), dtype=torch.int64, device=dev)
+    for k in range(4):
+        out[:, k] = _pack_bits(flat[:, k, :] == 1, 1)[:, 0]
+    phase_on = flat[:, 4:, 0] == 1
+    out[:, 0] |= (phase_on.to(torch.int64).argmax(dim=1) + 1) << 36
+    out[:, 4:8] = _pack_bits(legal, 4)
+    order = _legal_order(legal)
+    out[:, 8:40] = pol.gather(1, order).contiguous().view(torch.int64)
+    out[:, 40] = torch.stack([batch.value_targets.to(torch.float32), batch.soft_value_targets.to(torch.float32)],
+                             dim=1).contiguous().view(torch.int64)[:, 0]
+    planes_ok = ((flat[:, :4] == 0) | (flat[:, :4] == 1)).all(dim=2).all(dim=1) & (phase_on.sum(1) == 1) & \
+        (flat[:, 4:, :] == flat[:, 4:, :1]).all(dim=2).all(dim=1)
+    bad = ((pol != 0) & ~legal).any(dim=1) | (legal.sum(dim=1) > _FIXED_SLOTS) | ~planes_ok
+    out[:, 41] = bad.to(torch.int64)
+    return out
+
+
+def expand_rows_fixed(rows: torch.Tensor, check: bool = True) -> TensorSelfPlayBatch:
+    """Inverse of ``compact_rows_fixed`` (bit-identical tensors). ``check`` reads the flags (one host sync)."""
+    n = int(rows.shape[0])
+    dev = rows.device
+    if tuple(rows.shape[1:]) != (FIXED_ROW_WORDS,) or rows.dtype != torch.int64:
+        raise ValueError(f"rows must be int64[n,{FIXED_ROW_WORDS}]")
+    if check and n and bool((rows[:, 41] != 0).any()):
+        raise ValueError("fixed-row block holds rows that were not representable (flags word set)")
+    planes = torch.zeros((n, 11, 36), dtype=torch.float32, device=dev)
+    mask36 = (1 << 36) - 1
+    for k in range(4):
+        planes[:, k, :] = _unpack_bits((rows[:, k] & mask36).view(n, 1), 36).to(torch.float32)
+    phase = (rows[:, 0] >> 36) & 7
+    if n:
+        planes[torch.arange(n, device=dev), 3 + phase, :] = 1.0
+    legal = _unpack_bits(rows[:, 4:8], ACTION_DIM)
+    vals = rows[:, 8:40].contiguous().view(torch.float32)                    # [n,64]
+    policy = torch.zeros((n, ACTION_DIM), dtype=torch.float32, device=dev)
+    policy.scatter_(1, _legal_order(legal), vals)
+    vt = rows[:, 40:41].contiguous().view(torch.float32)                     # [n,2]
+    return TensorSelfPlayBatch(planes.view(n, 11, 6, 6), legal, policy, vt[:, 0].clone(), vt[:, 1].clone())

@@ -225,9 +225,12 @@ tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restr
     }
 }
 
+#ifndef LZB_EXPAND_MIN_BLOCKS
+#define LZB_EXPAND_MIN_BLOCKS 1
+#endif
 // Expand (portable_mcts.cpp:894-939) + Backup for every evaluated leaf slot of a tree, sequentially in slot
 // order (deterministic).  priors f32[slots,220] dense over the 220-d action space, values f32[slots].
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, LZB_EXPAND_MIN_BLOCKS)
 tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, const int32_t* __restrict__ leaf_status,
                    const float* __restrict__ priors, const float* __restrict__ values, int do_backup, double vl,
                    const int32_t* __restrict__ leaf_path) {

@@ -136,6 +136,22 @@ def gather_trajectories_compact(batch: TensorSelfPlayBatch, dst: int = 0, group=
     return cp.expand(cp.CompactSelfPlayBatch(boards, legal_bits, offsets, idx, val, vt, svt))
 
 
+def gather_rows_fixed(rows: torch.Tensor, dst: int = 0, group=None) -> Optional[torch.Tensor]:
+    """Streaming gather of fixed-size compact rows (``compact.compact_rows_fixed``: int64[n,42], the same n on every
+    rank -- one ply of every game): ONE collective with static shapes and no host synchronisation, so it can be queued
+    on a side stream every ply.  Returns int64[world * n, 42] in rank-major order on ``dst``, None elsewhere."""
+    world, rank = _world(group), _rank(group)
+    if world == 1:
+        return rows
+    rows = rows.contiguous()
+    if rank == dst:
+        out = torch.empty((world,) + tuple(rows.shape), dtype=rows.dtype, device=rows.device)
+        dist.gather(rows, list(out.unbind(0)), dst=dst, group=group)
+        return out.view(world * rows.shape[0], rows.shape[1])
+    dist.gather(rows, None, dst=dst, group=group)
+    return None
+
+
 def all_reduce_stats(values: List[float], device=None, group=None) -> List[float]:
     """Sum a small vector of counters (W/L/D, positions, lengths, seconds) over ranks."""
     if _world(group) == 1:

@@ -66,3 +66,30 @@ def test_empty_batch_and_rejections():
     bad.state_tensors[1, 4:] = 1.0                              # two phase planes on
     with pytest.raises(ValueError):
         cp.compact(bad)
+
+
+def test_fixed_rows_round_trip_and_flags():
+    """Streaming form (compact_rows_fixed / expand_rows_fixed): 336 B per position, static shapes, bit-identical
+    expansion on positions of real games; rows that cannot be represented are flagged, not silently mangled."""
+    b = _oracle_batch()
+    rows = cp.compact_rows_fixed(b)
+    n = b.num_samples
+    assert rows.dtype == torch.int64 and tuple(rows.shape) == (n, cp.FIXED_ROW_WORDS) and cp.FIXED_ROW_WORDS * 8 == 336
+    assert int(rows[:, 41].sum()) == 0
+    assert int(b.legal_masks.sum(1).max()) <= 64                 # the bound the format relies on
+    _same(cp.expand_rows_fixed(rows), b)
+    _same(cp.expand_rows_fixed(rows), cp.expand(cp.compact(b)))   # and it agrees with the CSR form
+    # policy mass on an illegal action / more than 64 legal actions / non-canonical planes -> flags
+    bad = TensorSelfPlayBatch(b.state_tensors.clone(), b.legal_masks.clone(), b.policy_targets.clone(),
+                              b.value_targets.clone(), b.soft_value_targets.clone())
+    illegal = int((~bad.legal_masks[0]).nonzero()[0])
+    bad.policy_targets[0, illegal] = 0.5
+    bad.legal_masks[1, :80] = True
+    bad.state_tensors[2, 0, 0, 0] = 0.5
+    flags = cp.compact_rows_fixed(bad)[:, 41]
+    assert flags[:3].tolist() == [1, 1, 1] and int(flags[3:].sum()) == 0
+    with pytest.raises(ValueError):
+        cp.expand_rows_fixed(cp.compact_rows_fixed(bad))
+    empty = TensorSelfPlayBatch(b.state_tensors[:0], b.legal_masks[:0], b.policy_targets[:0], b.value_targets[:0],
+                                b.soft_value_targets[:0])
+    assert cp.expand_rows_fixed(cp.compact_rows_fixed(empty)).num_samples == 0

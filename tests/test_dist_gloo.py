@@ -30,13 +30,13 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _make_batch(n: int, rank: int) -> TensorSelfPlayBatch:
+def _make_batch(n: int, rank: int, density: float = 0.3) -> TensorSelfPlayBatch:
     g = torch.Generator().manual_seed(100 + rank)
     planes = torch.zeros((n, 11, 6, 6))
     planes[:, :4] = (torch.rand((n, 4, 6, 6), generator=g) > 0.5).float()
     phase = torch.randint(1, 8, (n,), generator=g)
     planes[torch.arange(n), 3 + phase] = 1.0                  # one-hot phase plane (v0/src/net/encoding.cpp:26-79)
-    legal = torch.rand((n, 220), generator=g) > 0.7
+    legal = torch.rand((n, 220), generator=g) > 1.0 - density
     return TensorSelfPlayBatch(
         state_tensors=planes,
         legal_masks=legal,
@@ -67,6 +67,21 @@ def _worker(rank: int, world: int, port: int, sizes, ret):
         merged = gather_trajectories(batch, dst=0)
         merged_c = gather_trajectories_compact(batch, dst=0)
         stats = all_reduce_stats([1.0, float(sizes[rank]), float(rank)])
+        # streaming form: fixed-size rows, the same row count on every rank, one collective, no host sync
+        from liuzhou_b200 import compact as cp
+        from liuzhou_b200.dist import gather_rows_fixed
+
+        fixed_in = _make_batch(6, 50 + rank, density=0.2)
+        fixed_rows = gather_rows_fixed(cp.compact_rows_fixed(fixed_in), dst=0)
+        if rank == 0:
+            fb = cp.expand_rows_fixed(fixed_rows)
+            fexp = [_make_batch(6, 50 + r, density=0.2) for r in range(world)]
+            fixed_ok = fb.num_samples == 6 * world
+            for name in ("state_tensors", "legal_masks", "policy_targets", "value_targets", "soft_value_targets"):
+                cat = torch.cat([getattr(e, name) for e in fexp], 0)
+                fixed_ok = fixed_ok and torch.equal(getattr(fb, name), cat) and getattr(fb, name).dtype == cat.dtype
+        else:
+            fixed_ok = fixed_rows is None
         if rank == 0:
             expect = [_make_batch(sizes[r], r) for r in range(world)]
             ok = merged is not None and merged.num_samples == sum(sizes)
@@ -76,9 +91,9 @@ def _worker(rank: int, world: int, port: int, sizes, ret):
                 got = getattr(merged_c, name)                       # compact wire format: same tensors, bit for bit
                 ok = ok and got.dtype == cat.dtype and torch.equal(torch.nan_to_num(got.float(), nan=7.0),
                                                                    torch.nan_to_num(cat.float(), nan=7.0))
-            ret["rank0"] = (same, ok, stats, moved)
+            ret["rank0"] = (same, ok and fixed_ok, stats, moved)
         else:
-            ret[f"rank{rank}"] = (same, merged is None and merged_c is None, stats, moved)
+            ret[f"rank{rank}"] = (same, merged is None and merged_c is None and fixed_ok, stats, moved)
     finally:
         dist.destroy_process_group()
 
