@@ -131,6 +131,19 @@ def max_over_ranks(value: float, world: int) -> float:
     return float(t.item())
 
 
+def all_ranks(value: float, world: int) -> list:
+    """The value of every rank, in rank order (diagnostic next to the max the metric is computed from)."""
+    if world <= 1:
+        return [value]
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([value], dtype=torch.float64, device="cuda")
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [float(x.item()) for x in out]
+
+
 def sum_over_ranks(value: float, world: int) -> float:
     if world <= 1:
         return value
@@ -507,8 +520,8 @@ def time_tree_kernels(stepper, peaks, reps: int = 20) -> dict:
     sel_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / reps
     exp_ms = sum(e[2].elapsed_time(e[3]) for e in ev) / reps
     sims = reps * tree.num_trees * tree.k
-    sibs = c1["siblings_scanned"] - c0["siblings_scanned"]
-    levels = c1["levels_descended"] - c0["levels_descended"]
+    sibs = (c1["siblings_scanned"] - c0["siblings_scanned"]) & 0xFFFFFFFF        # 32-bit wrapping device counters
+    levels = (c1["levels_descended"] - c0["levels_descended"]) & 0xFFFFFFFF
     new_nodes = c1["nodes_used"] - c0["nodes_used"]
     expansions = c1["expansions"] - c0["expansions"]
     sel_bytes = sibs * 28 + sims * (12 + 32 + 32 + 8 + 136)
@@ -597,7 +610,8 @@ def run_selfplay(args, world, rank, local_rank):
     waves = stepper.mcts.waves
     launches = (_lib.launch_count() - launches0) + args.steps * (waves * stepper.mcts.wave_graph_launches
                                                                  + stepper.mcts.root_graph_launches)
-    elapsed_ms = max_over_ranks(e0.elapsed_time(e1), world)
+    rank_ms = all_ranks(e0.elapsed_time(e1), world)
+    elapsed_ms = max(rank_ms)                                         # max over ranks, device-timed
     positions = sum_over_ranks(float(games * args.steps), world)
     value = positions / (elapsed_ms / 1e3)
     evals = stepper.mcts.evals - evals0
@@ -695,6 +709,7 @@ def run_selfplay(args, world, rank, local_rank):
     return {
         "metric": "selfplay_positions_per_sec", "value": value, "unit": "positions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+        "ms_per_step_by_rank": [m / args.steps for m in rank_ms],
         "root_puct_backend": root_line,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "mcts_sims_per_sec": value * sims, "network_evals_per_sec": evals * world / (elapsed_ms / 1e3),
