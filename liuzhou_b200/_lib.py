@@ -6,12 +6,13 @@ device is visible, every op raises instead of falling back.
 from __future__ import annotations
 
 import ctypes
+import os
 from pathlib import Path
 
 import torch
 
 _CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = _CSRC / "libliuzhou_b200.so"
+LIB_PATH = Path(os.environ["LZB_LIB_PATH"]) if os.environ.get("LZB_LIB_PATH") else _CSRC / "libliuzhou_b200.so"
 
 STATE_FIELDS = (
     "board", "marks_black", "marks_white", "phase", "current_player",
