@@ -5,7 +5,9 @@ opening, Dirichlet noise every ply, no refill of finished games inside a wave).
 
 ``search_backend``:
   "root"  reference production semantics (root-PUCT over all children, V1RootMCTS.search_batch);
-  "tree"  full MCTS on the device tree (select / expand / backup kernels), the search north_star asks for.
+  "tree"  full MCTS on the device tree (select / expand / backup kernels), the search north_star asks for; mirrors
+          the reference's portable self-play (v1/python/portable_cpp_self_play.py): subtree reuse after every move
+          (``tree_reuse``), policy target temperature / prior pseudocount (``policy_target_*``, tree backend only).
 """
 from __future__ import annotations
 
@@ -96,6 +98,8 @@ def self_play_v1_gpu(
     search_backend: str = "root",
     leaves_per_wave: int = 1,
     tree_reuse: bool = True,
+    policy_target_temperature: Optional[float] = None,
+    policy_target_prior_pseudocount: float = 0.0,
 ) -> Tuple[TensorSelfPlayBatch, SelfPlayV1Stats]:
     if num_games <= 0:
         raise ValueError("num_games must be positive.")
@@ -141,7 +145,9 @@ def self_play_v1_gpu(
                 num_simulations=sims, exploration_weight=float(exploration_weight),
                 add_dirichlet_noise=bool(add_dirichlet_noise), dirichlet_alpha=float(dirichlet_alpha),
                 dirichlet_epsilon=float(dirichlet_epsilon), sample_moves=bool(sample_moves),
-                leaves_per_wave=int(leaves_per_wave), reuse_subtree=bool(tree_reuse)), dev)
+                leaves_per_wave=int(leaves_per_wave), reuse_subtree=bool(tree_reuse),
+                policy_target_temperature=policy_target_temperature,
+                policy_target_prior_pseudocount=float(policy_target_prior_pseudocount)), dev)
         if tree_mcts is not None:
             tree_mcts._advanced = False          # a new wave of games starts from reset roots
 

@@ -10,7 +10,8 @@ Differences in *how*, not *what*:
   * chunks leave the GPU through ``AsyncShardWriter`` (pinned staging on a copy stream, serialisation on a thread)
     while the next group of games is already being played;
   * ``search_backend``: ``cuda_root`` → our root-PUCT backend, ``portable`` → the device-resident tree search (there
-    is no python/cpp distinction; ``portable_mcts_backend`` / ``portable_cpp_threads`` are recorded, not used).
+    is no python/cpp distinction; ``portable_mcts_backend`` / ``portable_cpp_threads`` are recorded, not used;
+    ``policy_target_temperature`` / ``policy_target_prior_pseudocount`` act on the tree backend as in the reference).
 """
 from __future__ import annotations
 
@@ -201,7 +202,9 @@ def run_self_play_worker(
                     opening_random_moves=int(opening_random_moves), max_game_plies=int(max_game_plies),
                     sample_moves=bool(sample_moves), concurrent_games=n_games, sparse_ply=int(sparse_ply),
                     sparse_top_k=int(sparse_top_k), verbose=False,
-                    search_backend="root" if backend == "cuda_root" else "tree", leaves_per_wave=int(leaves_per_wave))
+                    search_backend="root" if backend == "cuda_root" else "tree", leaves_per_wave=int(leaves_per_wave),
+                    policy_target_temperature=policy_target_temperature,
+                    policy_target_prior_pseudocount=float(policy_target_prior_pseudocount))
                 stats_parts.append(stats)
                 summaries[0].append(summarize_scalar_targets(batch.value_targets))
                 summaries[1].append(summarize_scalar_targets(batch.soft_value_targets))

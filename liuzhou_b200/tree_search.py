@@ -32,13 +32,18 @@ class TreeMCTSConfig:
     # keep the played child's subtree between consecutive searches of a game (``advance()`` after every move), as the
     # reference's portable self-play does (portable_cpp_self_play.py:170, portable_mcts.cpp:739-768)
     reuse_subtree: bool = False
+    # policy TARGET (what the trajectory stores) = softmax(log(N + beta * P) / T_target); None keeps the legacy
+    # behaviour of reusing the per-game action-selection temperature (portable_cpp_mcts.py:340-354, train.py:2838-2856)
+    policy_target_temperature: Optional[float] = None
+    policy_target_prior_pseudocount: float = 0.0
 
 
 @dataclass
 class TreeSearchOutput:
     legal_mask: torch.Tensor          # bool[T,220]  (children of each root)
     visit_counts: torch.Tensor        # int32[T,220]
-    policy_dense: torch.Tensor        # f32[T,220]   visits^(1/T) normalised (one-hot argmax for T <= 1e-6)
+    policy_dense: torch.Tensor        # f32[T,220]   policy target: (N + beta P)^(1/T_target) normalised
+    selection_policy_dense: torch.Tensor  # f32[T,220] move-selection policy: N^(1/T) normalised (one-hot for T <= 1e-6)
     root_value: torch.Tensor          # f32[T]
     root_action_values: torch.Tensor  # f32[T,220]
     terminal_mask: torch.Tensor       # bool[T]      root is game-over / has no legal action / inactive
@@ -169,7 +174,9 @@ class TreeMCTS:
             else:
                 self._wave_step()
         self.evals += self.num_trees * (1 + self.waves * tree.k)
-        out = tree.root_outputs(with_priors=False)
+        beta = float(cfg.policy_target_prior_pseudocount)
+        do_sample = cfg.sample_moves if sample_moves is None else sample_moves
+        out = tree.root_outputs(with_priors=(beta > 0.0) or not do_sample)
         visits = out["visit_counts"]
         legal = out["legal_masks"]
         terminal = out["terminal"]
@@ -178,41 +185,71 @@ class TreeMCTS:
             temps = torch.full((t,), float(cfg.temperature), dtype=torch.float32, device=self.device)
         else:
             temps = torch.as_tensor(temperatures, dtype=torch.float32, device=self.device).view(-1)
-        policy = policy_from_visits(visits, temps)
-        do_sample = cfg.sample_moves if sample_moves is None else sample_moves
-        has_mass = policy.sum(dim=1) > 0
-        safe = torch.where(has_mass.view(-1, 1), policy, torch.full_like(policy, 1.0 / ACTION_DIM))
+        selection = policy_from_visits(visits, temps)
+        if cfg.policy_target_temperature is None and beta <= 0.0:
+            policy = selection
+        else:
+            t_target = temps if cfg.policy_target_temperature is None else torch.full_like(
+                temps, float(cfg.policy_target_temperature))
+            policy = policy_from_visits(visits, t_target, legal=legal, priors=out["root_priors"], prior_pseudocount=beta)
+        has_mass = selection.sum(dim=1) > 0
+        safe = torch.where(has_mass.view(-1, 1), selection, torch.full_like(selection, 1.0 / ACTION_DIM))
         if do_sample:
             chosen = torch.multinomial(safe, num_samples=1).view(-1)
         else:
-            chosen = deterministic_action(visits, out["root_action_values"], legal)
+            chosen = deterministic_action(visits, out["root_action_values"], legal, out["root_priors"])
         chosen = torch.where(has_mass & ~terminal, chosen, torch.full_like(chosen, -1))
+        dead = (terminal | ~has_mass).view(-1, 1)
+        policy = torch.where(dead, torch.zeros_like(policy), policy)
         return TreeSearchOutput(legal_mask=legal, visit_counts=visits, policy_dense=policy,
-                                root_value=out["root_values"], root_action_values=out["root_action_values"],
-                                terminal_mask=terminal | ~has_mass, chosen_action_indices=chosen)
+                                selection_policy_dense=selection, root_value=out["root_values"],
+                                root_action_values=out["root_action_values"], terminal_mask=terminal | ~has_mass,
+                                chosen_action_indices=chosen)
 
 
-def policy_from_visits(visits: torch.Tensor, temperatures: torch.Tensor) -> torch.Tensor:
-    """softmax(log(N) / T) over N > 0; one-hot argmax for T <= 1e-6 (portable_mcts.py:150-205, beta = 0)."""
+def policy_from_visits(visits: torch.Tensor, temperatures: torch.Tensor, legal: Optional[torch.Tensor] = None,
+                       priors: Optional[torch.Tensor] = None, prior_pseudocount: float = 0.0) -> torch.Tensor:
+    """Batched ``policy_from_visits_and_priors`` (portable_mcts.py:149-204) over rows of the 220-d action space:
+    scores = N (+ beta * P, P = root priors clamped at 1e-8 and normalised over the legal actions); policy =
+    softmax(log(scores) / T) over scores > 0; one-hot argmax(scores) for T <= 1e-6; rows without mass stay zero."""
     v = visits.to(torch.float32)
     temps = temperatures.view(-1, 1)
-    logits = torch.where(v > 0, torch.log(v.clamp_min(1e-30)) / temps.clamp_min(1e-6), torch.full_like(v, float("-inf")))
-    any_pos = (v > 0).any(dim=1, keepdim=True)
+    scores = v
+    beta = float(prior_pseudocount)
+    if beta > 0.0:
+        if priors is None or legal is None:
+            raise ValueError("prior_pseudocount > 0 needs the root priors and the legal mask")
+        lg = legal.to(torch.bool)
+        p = torch.where(lg, priors.to(torch.float32).clamp_min(1e-8), torch.zeros_like(v))
+        psum = p.sum(dim=1, keepdim=True)
+        uniform = lg.to(torch.float32) / lg.sum(dim=1, keepdim=True).clamp_min(1).to(torch.float32)
+        p = torch.where(torch.isfinite(psum) & (psum > 0), p / psum.clamp_min(1e-38), uniform)
+        scores = v + beta * p
+    pos = scores > 0
+    logits = torch.where(pos, torch.log(scores.clamp_min(1e-38)) / temps.clamp_min(1e-6), torch.full_like(v, float("-inf")))
+    any_pos = pos.any(dim=1, keepdim=True)
     soft = torch.softmax(torch.where(any_pos, logits, torch.zeros_like(logits)), dim=1)
     soft = torch.where(any_pos, soft, torch.zeros_like(soft))
     onehot = torch.zeros_like(v)
-    onehot.scatter_(1, v.argmax(dim=1, keepdim=True), 1.0)
+    onehot.scatter_(1, scores.argmax(dim=1, keepdim=True), 1.0)
     onehot = torch.where(any_pos, onehot, torch.zeros_like(onehot))
     return torch.where(temps <= 1e-6, onehot, soft)
 
 
-def deterministic_action(visits: torch.Tensor, action_values: torch.Tensor, legal: torch.Tensor) -> torch.Tensor:
-    """max N, then max Q (atol 1e-6), then lowest action index (portable_mcts.py:208-261; the prior tie-break only
-    matters between actions with identical N and Q, and is folded into the index order here)."""
+def deterministic_action(visits: torch.Tensor, action_values: torch.Tensor, legal: torch.Tensor,
+                         priors: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """max N, then max Q (atol 1e-6), then max P (atol 1e-8), then lowest action index
+    (``deterministic_action_from_search``, portable_mcts.py:207-261)."""
     v = torch.where(legal, visits.to(torch.float32), torch.full_like(action_values, -1.0))
     best_n = v.max(dim=1, keepdim=True).values
     cand = v == best_n
-    q = torch.where(cand, action_values, torch.full_like(action_values, float("-inf")))
+    q = torch.where(torch.isfinite(action_values), action_values, torch.full_like(action_values, float("-inf")))
+    q = torch.where(cand, q, torch.full_like(q, float("-inf")))
     best_q = q.max(dim=1, keepdim=True).values
-    cand = cand & ((q - best_q).abs() <= 1e-6)
+    cand = cand & (((q - best_q).abs() <= 1e-6) | (q == best_q))
+    if priors is not None:
+        p = torch.where(torch.isfinite(priors), priors.to(torch.float32), torch.full_like(q, float("-inf")))
+        p = torch.where(cand, p, torch.full_like(p, float("-inf")))
+        best_p = p.max(dim=1, keepdim=True).values
+        cand = cand & (((p - best_p).abs() <= 1e-8) | (p == best_p))
     return cand.to(torch.int8).argmax(dim=1)

@@ -61,6 +61,17 @@ def main():
         h.update(k.encode())
         h.update(v.detach().cpu().contiguous().numpy().tobytes())
     out["stable_init_sha256"] = h.hexdigest()
+    # policy targets / deterministic move choice of the portable search (v1/python/portable_mcts.py:149-261)
+    from tests.test_storage_formats import policy_cases
+    from v1.python.portable_mcts import deterministic_action_from_search, policy_from_visits_and_priors
+
+    pol = []
+    for visits, priors, legal, qv, temp, beta in policy_cases():
+        idx = torch.where(legal)[0]
+        dense = torch.zeros(220)
+        dense[idx] = policy_from_visits_and_priors(visits[idx].float(), priors[idx], temperature=temp, prior_pseudocount=beta)
+        pol.append({"policy": dense.tolist(), "choice": deterministic_action_from_search(visits, qv, priors, legal)})
+    out["policy_targets"] = pol
     (Path(__file__).resolve().parent / "storage_formats.json").write_text(json.dumps(out, indent=1, sort_keys=True))
     print("wrote storage_formats.json")
 

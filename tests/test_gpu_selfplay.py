@@ -416,3 +416,27 @@ def test_stepper_with_subtree_reuse_keeps_roots_in_sync():
     assert finished > 0                                                        # restarts were exercised
     used = sp.mcts.tree.stats()["nodes_used"]
     assert used < 256 * 24 * 40 * 3                                            # compaction bounds the arena
+
+
+def test_self_play_tree_backend_policy_target_options():
+    """policy_target_temperature / policy_target_prior_pseudocount (v1/train.py:2838-2856): with beta > 0 every legal
+    action of a stored position carries mass (N + beta * P > 0) and targets are distributions; move selection still
+    follows the visit policy (a played move always had visits or was the forced opening pick)."""
+    from liuzhou_b200.self_play import self_play_v1_gpu
+
+    torch.manual_seed(5)
+    batch, stats = self_play_v1_gpu(_small_net(), num_games=16, mcts_simulations=12, temperature_init=1.0,
+                                    temperature_final=0.1, temperature_threshold=6, exploration_weight=1.0, device=DEV,
+                                    add_dirichlet_noise=True, max_game_plies=60, sample_moves=True, concurrent_games=16,
+                                    search_backend="tree", policy_target_temperature=1.0,
+                                    policy_target_prior_pseudocount=2.0)
+    pol, legal = batch.policy_targets, batch.legal_masks
+    assert stats.num_positions == batch.num_samples > 16 * 20
+    assert torch.all((pol > 0) == legal)                               # full legal support, nothing outside
+    assert torch.allclose(pol.sum(1), torch.ones(batch.num_samples, device=pol.device), atol=1e-4)
+    torch.manual_seed(5)
+    base, _ = self_play_v1_gpu(_small_net(), num_games=16, mcts_simulations=12, temperature_init=1.0,
+                               temperature_final=0.1, temperature_threshold=6, exploration_weight=1.0, device=DEV,
+                               add_dirichlet_noise=True, max_game_plies=60, sample_moves=True, concurrent_games=16,
+                               search_backend="tree")
+    assert not torch.all((base.policy_targets > 0) == base.legal_masks)  # visit-only targets leave unvisited moves at 0

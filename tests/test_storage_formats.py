@@ -65,6 +65,48 @@ def target_vector(seed: int, n: int) -> torch.Tensor:
     return v
 
 
+def policy_cases():
+    """(visits i64[220], priors f32[220], legal bool[220], q f32[220], temperature, beta) -- seeded; ties included."""
+    g = torch.Generator().manual_seed(2024)
+    cases = []
+    for k, (temp, beta) in enumerate([(1.0, 0.0), (0.1, 0.0), (0.0, 0.0), (1.0, 2.0), (0.5, 8.0), (0.0, 3.0), (1.0, 0.5)]):
+        legal = torch.rand((220,), generator=g) < 0.12
+        legal[k] = True
+        visits = torch.randint(0, 6, (220,), generator=g) * legal
+        if k % 2 == 0:
+            visits[legal.nonzero()[0]] = 5                       # force ties at the maximum
+        priors = torch.rand((220,), generator=g) * legal
+        priors = priors / priors.sum()
+        qv = (torch.randint(-2, 3, (220,), generator=g).float() / 4.0) * (visits > 0)
+        cases.append((visits, priors.float(), legal, qv, temp, beta))
+    return cases
+
+
+def test_policy_targets_and_deterministic_choice_match_reference(golden):
+    """policy_from_visits (+ beta * priors, target temperature) and the N -> Q -> P -> index move choice of the tree
+    backend vs the reference's portable search functions (portable_mcts.py:149-261), batched over the 220-d space."""
+    from liuzhou_b200.tree_search import deterministic_action, policy_from_visits
+
+    cases = policy_cases()
+    visits = torch.stack([c[0] for c in cases])
+    priors = torch.stack([c[1] for c in cases])
+    legal = torch.stack([c[2] for c in cases])
+    qv = torch.stack([c[3] for c in cases])
+    for i, (_, _, _, _, temp, beta) in enumerate(cases):
+        got = policy_from_visits(visits[i:i + 1], torch.tensor([temp]), legal=legal[i:i + 1], priors=priors[i:i + 1],
+                                 prior_pseudocount=beta)[0]
+        want = torch.tensor(golden["policy_targets"][i]["policy"])
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-7), i
+        assert float(got[~legal[i]].abs().sum()) == 0.0
+    choice = deterministic_action(visits, qv, legal, priors)
+    assert choice.tolist() == [g["choice"] for g in golden["policy_targets"]]
+    # mixed temperatures in one batch (per-game temperature switch), beta = 0: rows equal their single-row results
+    temps = torch.tensor([c[4] for c in cases])
+    batch = policy_from_visits(visits, temps)
+    for i in range(len(cases)):
+        assert torch.equal(batch[i], policy_from_visits(visits[i:i + 1], temps[i:i + 1])[0])
+
+
 @pytest.fixture(scope="module")
 def golden():
     return json.loads(GOLDEN.read_text())
