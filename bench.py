@@ -702,6 +702,40 @@ def run_selfplay(args, world, rank, local_rank):
                      "what": "one full self_play_v1_gpu iteration, search_backend=root (reference production path), "
                              "same games / sims / net; see bench.py --search root"}
 
+    # the public entry end to end in tree mode: ONE full self_play_v1_gpu(search_backend="tree") iteration -- all games
+    # from the initial position to their end (wave semantics: no refill, so the last plies run with few live games),
+    # trajectory finalisation, and the finished TensorSelfPlayBatch copied to pinned host memory (N = 1 only)
+    full_line = None
+    if world == 1 and args.full_iteration:
+        from liuzhou_b200.self_play import self_play_v1_gpu
+
+        try:
+            del stepper
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        torch.manual_seed(SEED + 2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fb, fs = self_play_v1_gpu(net, num_games=games, mcts_simulations=sims, temperature_init=1.0,
+                                  temperature_final=0.1, temperature_threshold=10, exploration_weight=1.0,
+                                  device=str(dev), add_dirichlet_noise=True, concurrent_games=games,
+                                  search_backend="tree", leaves_per_wave=k, tree_reuse=bool(args.tree_reuse))
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in
+                (fb.state_tensors, fb.legal_masks, fb.policy_targets, fb.value_targets, fb.soft_value_targets)]
+        for dst, src in zip(host, (fb.state_tensors, fb.legal_masks, fb.policy_targets, fb.value_targets,
+                                   fb.soft_value_targets)):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        full_line = {"value": fb.num_samples / sec, "unit": "positions/s", "positions": fb.num_samples, "seconds": sec,
+                     "d2h_bytes": int(sum(h.numel() * h.element_size() for h in host)),
+                     "avg_game_length": fs.avg_game_length, "black_wins": fs.black_wins, "white_wins": fs.white_wins,
+                     "draws": fs.draws,
+                     "what": "one full self_play_v1_gpu(search_backend='tree') iteration, wall clock incl. CUDA-graph "
+                             "capture, trajectory finalisation and the D2H copy of the finished batch to pinned memory"}
+        del fb
+
     if rank != 0:
         return None
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
@@ -710,7 +744,7 @@ def run_selfplay(args, world, rank, local_rank):
         "metric": "selfplay_positions_per_sec", "value": value, "unit": "positions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
         "ms_per_step_by_rank": [m / args.steps for m in rank_ms],
-        "root_puct_backend": root_line,
+        "root_puct_backend": root_line, "tree_backend_full_iteration": full_line,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "mcts_sims_per_sec": value * sims, "network_evals_per_sec": evals * world / (elapsed_ms / 1e3),
         "config": {"workload": "v1 wave-batched MCTS self-play (BASELINE configs[2])", "games_per_gpu": games,
@@ -936,6 +970,8 @@ def main() -> int:
                     help="1: the played child's subtree is kept between moves (advance_roots, as the reference's "
                          "portable self-play does); 0: every search starts from a bare root")
     ap.add_argument("--no-root-line", action="store_true", help="skip the extra root-PUCT iteration in the default line")
+    ap.add_argument("--full-iteration", type=int, default=1,
+                    help="1: also time one full self_play_v1_gpu(search_backend='tree') iteration end to end (~30-40 s)")
     ap.add_argument("--search", choices=["tree", "root"], default="tree",
                     help="tree: device-resident full tree (north_star, default); root: the reference's root-PUCT backend")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
