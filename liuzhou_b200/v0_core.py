@@ -10,7 +10,6 @@ device and the current CUDA stream.  CUDA tensors only: there is deliberately no
 from __future__ import annotations
 
 import ctypes
-from enum import IntEnum
 
 import torch
 
@@ -25,30 +24,17 @@ __all__ = [
 ]
 
 
-class Phase(IntEnum):  # v0/include/v0/game_state.hpp:24-32
-    PLACEMENT = 1
-    MARK_SELECTION = 2
-    REMOVAL = 3
-    MOVEMENT = 4
-    CAPTURE_SELECTION = 5
-    FORCED_REMOVAL = 6
-    COUNTER_REMOVAL = 7
+# enums, GameState / MoveRecord / ActionCode and the scalar rule functions (module.cpp:877-1156): liuzhou_b200/scalar_api.py
+from .scalar_api import *  # noqa: E402,F401,F403
+from .scalar_api import ActionType, Phase, Player  # noqa: E402,F401
+from . import scalar_api as _scalar_api  # noqa: E402
 
+__all__ += [n for n in _scalar_api.__all__ if n not in __all__]
 
-class Player(IntEnum):  # game_state.hpp:34-37
-    BLACK = 1
-    WHITE = -1
-
-
-class ActionType(IntEnum):  # v0/include/v0/move_generator.hpp:13-22
-    PLACE = 1
-    MOVE = 2
-    MARK = 3
-    CAPTURE = 4
-    FORCED_REMOVAL = 5
-    COUNTER_REMOVAL = 6
-    NO_MOVES_REMOVAL = 7
-    PROCESS_REMOVAL = 8
+# pybind11's export_values(): enum members are also module attributes (v0_core.PLACEMENT, v0_core.BLACK, v0_core.PLACE, ...)
+for _e in (Phase, Player, ActionType):
+    for _m in _e:
+        globals().setdefault(_m.name, _m)
 
 
 def version() -> str:
