@@ -330,15 +330,15 @@ tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, con
 
 // AdvanceRoots (portable_mcts.cpp:739-768): the child reached by the played action becomes the root and keeps its whole
 // subtree (visit counts, value sums, priors, states); everything else of the old tree is dropped.  The reference
-// moves a unique_ptr; here the kept subtree is copied breadth-first into a scratch arena (children blocks stay
+// moves a unique_ptr; here the kept subtree is copied into a scratch arena (children blocks stay
 // contiguous, one atomicAdd on the scratch bump pointer per block), which is then copied back over the arena prefix --
-// a copying collector, so the arena never accumulates dead nodes over a game.  One warp per tree; the BFS queue
-// (src node, dst node) of a tree lives in its own slice of `queue`.
+// a copying collector, so the arena never accumulates dead nodes over a game.  One warp per tree, depth-first, no
+// work list.
 //   action < 0 or inactive tree : the tree is kept as it is (reference: early return), i.e. copied with its own root
 //   reset_mask[t]               : the tree is replaced by a fresh unexpanded root for reset_states[t] (a new game)
 //   action not among the root's children : counters[1] |= 2 (the reference throws), tree kept
-//   queue / scratch exhausted   : counters[1] |= 4 / |= 1, the affected node is kept as an unexpanded leaf
-constexpr int32_t kFlagArena = 1, kFlagIllegalAdvance = 2, kFlagQueue = 4;
+//   scratch exhausted           : counters[1] |= 1, the affected node is kept as an unexpanded leaf
+constexpr int32_t kFlagArena = 1, kFlagIllegalAdvance = 2;
 
 __global__ void tree_advance_begin_kernel(lzb_tree A, lzb_tree B) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -354,9 +354,30 @@ __device__ __forceinline__ void copy_node(const lzb_tree& A, int s, const lzb_tr
     store_packed(B.state, d, load_packed(A.state, s));
 }
 
+// Allocate the children block of node s (old arena) in the new arena and copy it under node d; returns the block's first
+// index, or -1 when the new arena is full (d then stays an unexpanded leaf and the sticky flag is raised).
+__device__ __forceinline__ int copy_children(const lzb_tree& A, const lzb_tree& B, int s, int d, uint32_t inf, int lane) {
+    const int n = info_nchild(inf), sfc = A.first_child[s];
+    int dfc = 0;
+    if (lane == 0) {
+        dfc = atomicAdd(&B.counters[0], n);
+        if ((int64_t)dfc + n > B.capacity) { atomicOr(&B.counters[1], kFlagArena); dfc = -1; }
+    }
+    dfc = __shfl_sync(0xffffffffu, dfc, 0);
+    if (dfc < 0) {
+        if (lane == 0) B.info[d] = B.info[d] & ~(kInfoExpanded | (0xFFu << 8));
+        __syncwarp();
+        return -1;
+    }
+    for (int i = lane; i < n; i += 32) copy_node(A, sfc + i, B, dfc + i, A.info[sfc + i] & ~kInfoPending, d);
+    if (lane == 0) B.first_child[d] = dfc;
+    __syncwarp();
+    return dfc;
+}
+
 __global__ void __launch_bounds__(kThreads)
 tree_advance_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ actions, const uint64_t* __restrict__ reset_states,
-                    const uint8_t* __restrict__ reset_mask, int64_t* __restrict__ queue, int queue_cap) {
+                    const uint8_t* __restrict__ reset_mask) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
@@ -398,50 +419,44 @@ tree_advance_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ actions,
             copy_node(A, src_root, B, (int)t, inf, -1);
             B.root_value[t] = src_root == (int)t ? A.root_value[t] : 0.0;
         }
-        int64_t* q = queue + t * (int64_t)queue_cap;
-        int head = 0, tail = 0;
+        // Depth-first walk of the kept subtree with O(1) state: (s, d) = current node in the old / new arena.  A node's
+        // children block is allocated and copied when the node is entered; then the walk descends into the first child
+        // that has children of its own, and on the way back up continues with the next such sibling (its position is
+        // recovered from the parent's first_child).  No work list, so there is no bound on the size of a kept subtree
+        // other than the arena itself (roots that inherit thousands of visits over forced move sequences are routine).
         if ((src_inf & kInfoExpanded) && info_nchild(src_inf) > 0) {
-            if (lane == 0) q[0] = ((int64_t)src_root << 32) | (uint32_t)t;
-            tail = 1;
-        }
-        __syncwarp();
-        while (head < tail) {
-            const int64_t e = q[head++];
-            const int s = (int)(e >> 32), d = (int)(e & 0xffffffff);
-            const uint32_t inf = A.info[s];
-            const int n = info_nchild(inf), sfc = A.first_child[s];
-            int dfc = 0;
-            if (lane == 0) {
-                dfc = atomicAdd(&B.counters[0], n);
-                if ((int64_t)dfc + n > B.capacity) { atomicOr(&B.counters[1], kFlagArena); dfc = -1; }
-            }
-            dfc = __shfl_sync(0xffffffffu, dfc, 0);
-            if (dfc < 0) {                                               // scratch exhausted: d stays an unexpanded leaf
-                if (lane == 0) B.info[d] = B.info[d] & ~(kInfoExpanded | (0xFFu << 8));
-                __syncwarp();
-                continue;
-            }
-            for (int base = 0; base < n; base += 32) {
-                const int i = base + lane;
-                uint32_t ci = 0;
-                bool grow = false;
-                if (i < n) {
-                    ci = A.info[sfc + i] & ~kInfoPending;
-                    grow = (ci & kInfoExpanded) && info_nchild(ci) > 0;
+            int s = src_root, d = (int)t, start = 0;
+            uint32_t inf = src_inf;
+            int dfc = copy_children(A, B, s, d, inf, lane);
+            while (dfc >= 0) {
+                const int n = info_nchild(inf), sfc = A.first_child[s];
+                int found = -1;
+                for (int base = start & ~31; base < n && found < 0; base += 32) {
+                    const int i = base + lane;
+                    bool grow = false;
+                    if (i < n && i >= start) {
+                        const uint32_t ci = A.info[sfc + i];
+                        grow = (ci & kInfoExpanded) && info_nchild(ci) > 0;
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, grow);
+                    if (m) found = base + __ffs(m) - 1;
                 }
-                const uint32_t m = __ballot_sync(0xffffffffu, grow);
-                const int pos = tail + __popc(m & ((1u << lane) - 1u));
-                if (grow && pos >= queue_cap) {                          // queue exhausted: keep as an unexpanded leaf
-                    ci &= ~(kInfoExpanded | (0xFFu << 8));
-                    atomicOr(&B.counters[1], kFlagQueue);
-                    grow = false;
+                if (found >= 0) {
+                    const int cs = sfc + found, cd = dfc + found;
+                    const uint32_t cinf = A.info[cs];
+                    const int cdfc = copy_children(A, B, cs, cd, cinf, lane);
+                    if (cdfc >= 0) { s = cs; d = cd; inf = cinf; dfc = cdfc; start = 0; }
+                    else start = found + 1;                      // arena exhausted: that child stays a leaf
+                } else {
+                    if (s == src_root) break;
+                    const int ps = A.parent[s];
+                    start = s - A.first_child[ps] + 1;
+                    d = B.parent[d];
+                    s = ps;
+                    inf = A.info[s];
+                    dfc = B.first_child[d];
                 }
-                if (i < n) copy_node(A, sfc + i, B, dfc + i, ci, d);
-                if (grow) q[pos] = ((int64_t)(sfc + i) << 32) | (uint32_t)(dfc + i);
-                tail = min(tail + __popc(m), queue_cap);
             }
-            if (lane == 0) B.first_child[d] = dfc;
-            __syncwarp();
         }
     }
 }
@@ -709,20 +724,18 @@ extern "C" int lzb_tree_prepare_roots(const lzb_tree* tree, int32_t* leaf_node, 
 }
 
 extern "C" int lzb_tree_advance_roots(const lzb_tree* tree, const lzb_tree* scratch, const int32_t* actions,
-                                      const uint64_t* reset_states, const uint8_t* reset_mask, int64_t* queue,
-                                      int32_t queue_cap, void* stream) {
+                                      const uint64_t* reset_states, const uint8_t* reset_mask, void* stream) {
     int rc = check_tree(tree);
     if (rc) return rc;
     rc = check_tree(scratch);
     if (rc) return rc;
     LZB_REQUIRE(scratch->num_trees == tree->num_trees && scratch->capacity >= tree->num_trees, "scratch arena mismatch");
     LZB_REQUIRE(scratch->visit != tree->visit && scratch->state != tree->state, "scratch arena must not alias the tree");
-    LZB_REQUIRE(actions && queue && queue_cap >= 1, "null actions / queue");
+    LZB_REQUIRE(actions, "null actions");
     LZB_REQUIRE((reset_states == nullptr) == (reset_mask == nullptr), "reset_states and reset_mask go together");
     cudaStream_t st = (cudaStream_t)stream;
     tree_advance_begin_kernel<<<1, 32, 0, st>>>(*tree, *scratch);
-    tree_advance_kernel<<<warp_grid(tree->num_trees), kThreads, 0, st>>>(*tree, *scratch, actions, reset_states, reset_mask,
-                                                                        queue, queue_cap);
+    tree_advance_kernel<<<warp_grid(tree->num_trees), kThreads, 0, st>>>(*tree, *scratch, actions, reset_states, reset_mask);
     tree_copy_back_kernel<<<148 * 8, 256, 0, st>>>(*scratch, *tree);
     return check_launch("tree_advance_kernel");
 }

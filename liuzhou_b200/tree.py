@@ -26,7 +26,7 @@ class _TreeStruct(ctypes.Structure):
 
 
 _ARENA_FIELDS = ("visit", "value_sum", "prior", "info", "first_child", "parent", "state", "root_value", "counters")
-FLAG_ARENA, FLAG_ILLEGAL_ADVANCE, FLAG_QUEUE = 1, 2, 4       # sticky bits of counters[1]
+FLAG_ARENA, FLAG_ILLEGAL_ADVANCE = 1, 2                      # sticky bits of counters[1]
 
 
 class DeviceTreeBatch:
@@ -34,7 +34,7 @@ class DeviceTreeBatch:
 
     def __init__(self, num_trees: int, device="cuda", *, exploration_weight: float = 1.0, leaves_per_wave: int = 1,
                  virtual_loss: float = 1.0, node_capacity: Optional[int] = None,
-                 nodes_per_tree_hint: int = 200 * 40, reuse_queue_per_tree: int = 4096) -> None:
+                 nodes_per_tree_hint: int = 200 * 40) -> None:
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("DeviceTreeBatch needs a CUDA device (no CPU path)")
@@ -79,11 +79,9 @@ class DeviceTreeBatch:
         self._struct.capacity = cap
         self._struct.num_trees = t
         self._pending_is_root = False
-        # second arena + BFS work lists for advance_roots (subtree reuse); allocated on first use
-        self.reuse_queue_per_tree = int(reuse_queue_per_tree)
+        # second arena for advance_roots (subtree reuse); allocated on first use
         self._scratch: Optional[dict] = None
         self._scratch_struct: Optional[_TreeStruct] = None
-        self._queue: Optional[torch.Tensor] = None
 
     # -- protocol ------------------------------------------------------------------------------------
     def reset(self, root_states: torch.Tensor, active: Optional[torch.Tensor] = None) -> None:
@@ -126,7 +124,6 @@ class DeviceTreeBatch:
                   "state": torch.empty((cap, 4), dtype=torch.int64, device=dev),
                   "root_value": torch.zeros((t,), dtype=torch.float64, device=dev),
                   "counters": torch.zeros((8,), dtype=torch.int32, device=dev)}
-            self._queue = torch.empty((t * self.reuse_queue_per_tree,), dtype=torch.int64, device=dev)
         st = _TreeStruct()
         for name in _ARENA_FIELDS:
             setattr(st, name, sc[name].data_ptr())
@@ -157,8 +154,7 @@ class DeviceTreeBatch:
         self._ensure_scratch()
         with torch.cuda.device(self.device):
             check(lib().lzb_tree_advance_roots(ctypes.byref(self._struct), ctypes.byref(self._scratch_struct), ptr(a),
-                                               ptr(rs), ptr(rm), ptr(self._queue),
-                                               ctypes.c_int32(self.reuse_queue_per_tree), stream_ptr(self.device)))
+                                               ptr(rs), ptr(rm), stream_ptr(self.device)))
 
     def deactivate(self, tree_indices) -> None:
         """``PortableTreeBatch.deactivate`` (:770-778): the listed trees are skipped by every later call."""
@@ -252,7 +248,7 @@ class DeviceTreeBatch:
 
     def stats(self) -> dict:
         c = self.counters.tolist()
-        return {"nodes_used": int(c[0]), "overflow": bool(c[1] & (FLAG_ARENA | FLAG_QUEUE)), "flags": int(c[1]),
+        return {"nodes_used": int(c[0]), "overflow": bool(c[1] & FLAG_ARENA), "flags": int(c[1]),
                 "expansions": int(c[2]), "terminal_hits": int(c[3]), "capacity": self.capacity,
                 "siblings_scanned": int(c[4]) & 0xFFFFFFFF, "levels_descended": int(c[5]) & 0xFFFFFFFF}
 
@@ -262,9 +258,7 @@ class DeviceTreeBatch:
             raise RuntimeError("selected action is not a child of the current root")       # the reference's message
         if flags & FLAG_ARENA:
             raise RuntimeError(f"tree node arena exhausted (capacity {self.capacity}); raise node_capacity")
-        if flags & FLAG_QUEUE:
-            raise RuntimeError(f"advance_roots work list exhausted ({self.reuse_queue_per_tree} per tree); "
-                               "raise reuse_queue_per_tree")
+
 
 
 def encode_inputs(packed: torch.Tensor, layout: str = "f32_nchw", out: Optional[torch.Tensor] = None) -> torch.Tensor:

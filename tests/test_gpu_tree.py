@@ -373,16 +373,3 @@ def test_tree_advance_roots_reset_deactivate_and_errors():
         tree.check_capacity()
     with pytest.raises(RuntimeError):
         tree.advance_roots(torch.zeros((n + 1,), dtype=torch.int32, device=DEV))
-    # a work list that is too small is reported, not silently truncated
-    small = DeviceTreeBatch(n, DEV, exploration_weight=1.0, nodes_per_tree_hint=(sims + 2) * 64, reuse_queue_per_tree=2)
-    small.reset(packed0)
-    small.prepare_roots()
-    rows, inputs, masks = _pending_from_device(small, native)
-    _complete(small, rows, *fake_net(inputs, masks, 0))
-    for _ in range(sims):
-        small.select_leaves()
-        rows, inputs, masks = _pending_from_device(small, native)
-        _complete(small, rows, *fake_net(inputs, masks, 1))
-    small.advance_roots(torch.full((n,), -1, dtype=torch.int32, device=DEV))
-    with pytest.raises(RuntimeError, match="work list"):
-        small.check_capacity()
