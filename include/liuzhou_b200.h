@@ -232,6 +232,12 @@ LZB_API int lzb_tree_init_roots(const lzb_tree *tree, const uint64_t *root_state
 LZB_API int lzb_tree_select(const lzb_tree *tree, int32_t K, double exploration_weight, double virtual_loss,
                             int32_t *leaf_node, int32_t *leaf_status, uint64_t *leaf_states, int32_t *leaf_path,
                             void *stream);
+/* lzb_tree_select (roots_only = 0) or lzb_tree_prepare_roots (roots_only = 1, K = 1) that ALSO writes the network input
+ * of every status-0 slot: inputs_c64 = bf16 [slots,6,6,64] channels-last, the planes of lzb_encode_inputs_packed
+ * layout 2 (rows of other slots are left untouched) -- saves the separate encoding launch in every simulation wave. */
+LZB_API int lzb_tree_select_encode(const lzb_tree *tree, int32_t K, double exploration_weight, double virtual_loss,
+                                   int32_t *leaf_node, int32_t *leaf_status, uint64_t *leaf_states, int32_t *leaf_path,
+                                   int32_t roots_only, void *inputs_c64, void *stream);
 /* prepare_roots proper (:483-513): one slot per tree; only an UNEXPANDED, non-terminal, active root becomes a pending
  * leaf (status 0) -- a root that kept its subtree through lzb_tree_advance_roots is left alone (status 1). */
 LZB_API int lzb_tree_prepare_roots(const lzb_tree *tree, int32_t *leaf_node, int32_t *leaf_status, uint64_t *leaf_states,

@@ -115,6 +115,30 @@ __device__ __forceinline__ void virtual_loss_path(const lzb_tree& A, int node, d
     }
 }
 
+// One state -> bf16 channels-last planes padded to 64 channels ([36 cells][64 ch] = 288 x 16 B), written by a warp.
+__device__ __forceinline__ void encode_c64_row(const Packed& p, uint4* __restrict__ out, int lane) {
+    State<int> s;
+    unpack(p, s);
+    const bool black = s.player == 1;
+    const uint64_t p0 = black ? s.black : s.white, p1 = black ? s.white : s.black;
+    const uint64_t p2 = black ? s.mb : s.mw, p3 = black ? s.mw : s.mb;
+    const int phase_plane = 3 + s.phase;
+    for (int e = lane; e < 288; e += 32) {
+        const int cell = e >> 3, oct = e & 7;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (oct < 2) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int plane = oct * 8 + c;
+                const uint64_t bits = plane == 0 ? p0 : plane == 1 ? p1 : plane == 2 ? p2 : p3;
+                const bool on = plane < 4 ? ((bits >> cell) & 1) : (plane < 11 && plane == phase_plane);
+                if (on) w[c >> 1] |= (c & 1) ? 0x3F800000u : 0x00003F80u;        // bf16 1.0
+            }
+        }
+        out[e] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // status codes written per leaf slot
 constexpr int kLeafEval = 0;       // needs a network evaluation, then expand (+ backup)
 constexpr int kLeafDone = 1;       // terminal / inactive: nothing to evaluate (backup already done)
@@ -123,7 +147,7 @@ constexpr int kLeafDuplicate = 2;  // K > 1 only: same leaf already pending in t
 __global__ void __launch_bounds__(kThreads, 4)      // 4 x 8 warps per SM: all 4,096 trees of a wave resident at once
 tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restrict__ leaf_node,
                    int32_t* __restrict__ leaf_status, uint64_t* __restrict__ leaf_states, int32_t* __restrict__ leaf_path,
-                   int roots_only) {
+                   int roots_only, uint4* __restrict__ enc_out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
@@ -206,10 +230,18 @@ tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restr
                 status = kLeafDuplicate;
             } else {
                 status = kLeafEval;
+                Packed leaf;
+                leaf.w[0] = leaf.w[1] = leaf.w[2] = leaf.w[3] = 0;
                 if (lane == 0) {
                     A.info[node] = inf | kInfoPending;
-                    store_packed(leaf_states, slot, load_packed(A.state, node));
+                    leaf = load_packed(A.state, node);
+                    store_packed(leaf_states, slot, leaf);
                     if (K > 1 && vl > 0.0) virtual_loss_path(A, node, vl, +1);
+                }
+                if (enc_out) {      // the network input of this leaf, written here instead of by a separate launch
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) leaf.w[k] = __shfl_sync(0xffffffffu, leaf.w[k], 0);
+                    encode_c64_row(leaf, enc_out + slot * 288, lane);
                 }
                 if (leaf_path) {                                     // the path travels to the expand / backup kernel
                     leaf_path[slot * kPathStride + lane] = path_node;
@@ -586,28 +618,7 @@ encode_inputs_c64_kernel(const uint64_t* __restrict__ states, int64_t n, uint4* 
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-    for (int64_t i = warp; i < n; i += nwarps) {
-        State<int> s;
-        unpack(load_packed(states, i), s);
-        const bool black = s.player == 1;
-        const uint64_t p0 = black ? s.black : s.white, p1 = black ? s.white : s.black;
-        const uint64_t p2 = black ? s.mb : s.mw, p3 = black ? s.mw : s.mb;
-        const int phase_plane = 3 + s.phase;
-        for (int e = lane; e < 288; e += 32) {
-            const int cell = e >> 3, oct = e & 7;
-            uint32_t w[4] = {0u, 0u, 0u, 0u};
-            if (oct < 2) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int plane = oct * 8 + c;
-                    const uint64_t bits = plane == 0 ? p0 : plane == 1 ? p1 : plane == 2 ? p2 : p3;
-                    const bool on = plane < 4 ? ((bits >> cell) & 1) : (plane < 11 && plane == phase_plane);
-                    if (on) w[c >> 1] |= (c & 1) ? 0x3F800000u : 0x00003F80u;        // bf16 1.0
-                }
-            }
-            out[i * 288 + e] = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-    }
+    for (int64_t i = warp; i < n; i += nwarps) encode_c64_row(load_packed(states, i), out + i * 288, lane);
 }
 
 // Policy heads -> dense priors over the legal actions of each leaf (masked softmax, fp32) and bucketed value
@@ -709,8 +720,24 @@ extern "C" int lzb_tree_select(const lzb_tree* tree, int32_t K, double c_puct, d
     LZB_REQUIRE(c_puct >= 0.0 && c_puct == c_puct, "exploration_weight must be finite and non-negative");
     LZB_REQUIRE(leaf_node && leaf_status && leaf_states, "null output");
     tree_select_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(
-        *tree, K, c_puct, virtual_loss, leaf_node, leaf_status, leaf_states, leaf_path, 0);
+        *tree, K, c_puct, virtual_loss, leaf_node, leaf_status, leaf_states, leaf_path, 0, nullptr);
     return check_launch("tree_select_kernel");
+}
+
+extern "C" int lzb_tree_select_encode(const lzb_tree* tree, int32_t K, double c_puct, double virtual_loss, int32_t* leaf_node,
+                                      int32_t* leaf_status, uint64_t* leaf_states, int32_t* leaf_path, int32_t roots_only,
+                                      void* inputs_c64, void* stream) {
+    int rc = check_tree(tree);
+    if (rc) return rc;
+    LZB_REQUIRE(K >= 1 && K <= 64, "leaves per tree per wave must be in [1, 64]");
+    LZB_REQUIRE(c_puct >= 0.0 && c_puct == c_puct, "exploration_weight must be finite and non-negative");
+    LZB_REQUIRE(leaf_node && leaf_status && leaf_states && inputs_c64, "null output");
+    LZB_REQUIRE(!roots_only || K == 1, "prepare_roots uses one slot per tree");
+    LZB_REQUIRE((reinterpret_cast<uintptr_t>(inputs_c64) & 15) == 0, "inputs must be 16-byte aligned");
+    tree_select_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(
+        *tree, K, c_puct, roots_only ? 0.0 : virtual_loss, leaf_node, leaf_status, leaf_states, roots_only ? nullptr : leaf_path,
+        roots_only ? 1 : 0, reinterpret_cast<uint4*>(inputs_c64));
+    return check_launch("tree_select_kernel(+encode)");
 }
 
 extern "C" int lzb_tree_prepare_roots(const lzb_tree* tree, int32_t* leaf_node, int32_t* leaf_status,
@@ -719,7 +746,7 @@ extern "C" int lzb_tree_prepare_roots(const lzb_tree* tree, int32_t* leaf_node, 
     if (rc) return rc;
     LZB_REQUIRE(leaf_node && leaf_status && leaf_states, "null output");
     tree_select_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(
-        *tree, 1, 0.0, 0.0, leaf_node, leaf_status, leaf_states, nullptr, 1);
+        *tree, 1, 0.0, 0.0, leaf_node, leaf_status, leaf_states, nullptr, 1, nullptr);
     return check_launch("tree_select_kernel(roots)");
 }
 

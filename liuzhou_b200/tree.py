@@ -94,20 +94,35 @@ class DeviceTreeBatch:
         with torch.cuda.device(self.device):
             check(lib().lzb_tree_init_roots(ctypes.byref(self._struct), ptr(rs), ptr(act), stream_ptr(self.device)))
 
-    def _select(self, k: int) -> None:
+    def _select(self, k: int, roots_only: bool, encode_out: Optional[torch.Tensor]) -> None:
+        node, status, states = ((self.root_leaf_node, self.root_leaf_status, self.root_leaf_states) if roots_only
+                                else (self.leaf_node, self.leaf_status, self.leaf_states))
         with torch.cuda.device(self.device):
-            check(lib().lzb_tree_select(ctypes.byref(self._struct), ctypes.c_int32(k),
-                                        ctypes.c_double(self.exploration_weight), ctypes.c_double(self.virtual_loss),
-                                        ptr(self.leaf_node), ptr(self.leaf_status), ptr(self.leaf_states),
-                                        ptr(self.leaf_path), stream_ptr(self.device)))
+            if encode_out is not None:
+                # fused: the kernel also writes the bf16 [slots,6,6,64] network input of every pending leaf
+                slots = self.num_trees * k
+                if (encode_out.dtype != torch.bfloat16 or tuple(encode_out.shape) != (slots, 64, 6, 6)
+                        or not encode_out.is_contiguous(memory_format=torch.channels_last)):
+                    raise RuntimeError(f"encode_out must be bfloat16 [{slots},64,6,6] in channels_last memory format")
+                check(lib().lzb_tree_select_encode(
+                    ctypes.byref(self._struct), ctypes.c_int32(k), ctypes.c_double(self.exploration_weight),
+                    ctypes.c_double(self.virtual_loss), ptr(node), ptr(status), ptr(states),
+                    ptr(None if roots_only else self.leaf_path), ctypes.c_int32(1 if roots_only else 0), ptr(encode_out),
+                    stream_ptr(self.device)))
+            elif roots_only:
+                check(lib().lzb_tree_prepare_roots(ctypes.byref(self._struct), ptr(node), ptr(status), ptr(states),
+                                                   stream_ptr(self.device)))
+            else:
+                check(lib().lzb_tree_select(ctypes.byref(self._struct), ctypes.c_int32(k),
+                                            ctypes.c_double(self.exploration_weight), ctypes.c_double(self.virtual_loss),
+                                            ptr(node), ptr(status), ptr(states), ptr(self.leaf_path),
+                                            stream_ptr(self.device)))
 
-    def prepare_roots(self) -> None:
+    def prepare_roots(self, encode_out: Optional[torch.Tensor] = None) -> None:
         """Unexpanded, non-terminal, active roots become the pending leaves (one slot per tree, whatever K is);
-        roots that kept their subtree through advance_roots() need no evaluation (portable_mcts.cpp:483-513)."""
-        with torch.cuda.device(self.device):
-            check(lib().lzb_tree_prepare_roots(ctypes.byref(self._struct), ptr(self.root_leaf_node),
-                                               ptr(self.root_leaf_status), ptr(self.root_leaf_states),
-                                               stream_ptr(self.device)))
+        roots that kept their subtree through advance_roots() need no evaluation (portable_mcts.cpp:483-513).
+        ``encode_out`` (bf16 [T,64,6,6] channels-last): also write the pending roots' network input in the same launch."""
+        self._select(1, True, encode_out)
         self._pending_is_root = True
 
     def _ensure_scratch(self) -> None:
@@ -189,8 +204,9 @@ class DeviceTreeBatch:
                 "move_counts": ((meta >> 14) & 255).to(torch.int32),
                 "moves_since_capture": ((meta >> 22) & 63).to(torch.int32), "game_over": over}
 
-    def select_leaves(self) -> None:
-        self._select(self.k)
+    def select_leaves(self, encode_out: Optional[torch.Tensor] = None) -> None:
+        """One descent per leaf slot; ``encode_out`` (bf16 [T*K,64,6,6] channels-last) fuses the input encoding in."""
+        self._select(self.k, False, encode_out)
         self._pending_is_root = False
 
     @property

@@ -7,6 +7,7 @@ evaluate -> expand + backup) -> root outputs -> policy from visit counts.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -78,23 +79,31 @@ class TreeMCTS:
         self.root_graph_launches = self.wave_graph_launches = 0
         self.evals = 0
 
-    # one network evaluation of the pending leaves + expansion (+ backup)
-    def _eval_pending(self, root: bool) -> None:
+    # one network evaluation of the pending leaves + expansion (+ backup).  On the tcgen05 path the network input is
+    # the channel-padded bf16 [n,64,6,6] tensor and the select kernel writes it itself (one launch less per wave).
+    def _fused_encode(self, x: torch.Tensor) -> bool:
+        return (x.dim() == 4 and x.size(1) == 64 and x.dtype == torch.bfloat16
+                and os.environ.get("LZB_FUSED_ENCODE", "1") != "0")
+
+    def _eval_pending(self, root: bool, encoded: bool) -> None:
         tree = self.tree
         x = self._root_in if root else self._wave_in
         pri = self._root_pri if root else self._wave_pri
         val = self._root_val if root else self._wave_val
-        encode_inputs(tree.pending_states, "bf16_nhwc", out=x)
+        if not encoded:
+            encode_inputs(tree.pending_states, "bf16_nhwc", out=x)
         self.net.forward_priors(x, tree.pending_states, priors_out=pri, values_out=val)
         tree.complete_pending(pri, val)
 
     def _root_step(self) -> None:
-        self.tree.prepare_roots()
-        self._eval_pending(True)
+        fused = self._fused_encode(self._root_in)
+        self.tree.prepare_roots(self._root_in if fused else None)
+        self._eval_pending(True, fused)
 
     def _wave_step(self) -> None:
-        self.tree.select_leaves()
-        self._eval_pending(False)
+        fused = self._fused_encode(self._wave_in)
+        self.tree.select_leaves(self._wave_in if fused else None)
+        self._eval_pending(False, fused)
 
     def _capture(self) -> None:
         dev = self.device

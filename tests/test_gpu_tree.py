@@ -373,3 +373,40 @@ def test_tree_advance_roots_reset_deactivate_and_errors():
         tree.check_capacity()
     with pytest.raises(RuntimeError):
         tree.advance_roots(torch.zeros((n + 1,), dtype=torch.int32, device=DEV))
+
+
+def test_select_with_fused_input_encoding():
+    """select_leaves / prepare_roots with encode_out: the rows of the pending (status 0) slots equal the separate
+    lzb_encode_inputs_packed launch bit for bit, other rows are left untouched, tree statistics are unaffected."""
+    from liuzhou_b200 import native
+    from liuzhou_b200.tree import DeviceTreeBatch, encode_inputs
+
+    st = _playout_states(3, 21, every=9)
+    n = st["board"].shape[0]
+    packed = native.pack_states(to_torch(st, DEV))
+    trees = [DeviceTreeBatch(n, DEV, exploration_weight=1.0, nodes_per_tree_hint=40 * 64) for _ in range(2)]
+    sentinel = 0.25
+    buf = torch.full((n, 64, 6, 6), sentinel, dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last)
+    for t in trees:
+        t.reset(packed)
+    trees[0].prepare_roots()
+    trees[1].prepare_roots(encode_out=buf)
+    for wave in range(12):
+        status = _np(trees[1].pending_status)
+        assert np.array_equal(status, _np(trees[0].pending_status))
+        want = encode_inputs(trees[1].pending_states, "bf16_nhwc",
+                             out=torch.empty_like(buf).contiguous(memory_format=torch.channels_last))
+        live = torch.from_numpy(status == 0).to(DEV)
+        assert torch.equal(buf[live], want[live])
+        if wave == 0 and (~live).any():
+            assert bool((buf[~live] == sentinel).all())                 # untouched rows
+        rows, inputs, masks = _pending_from_device(trees[1], native)
+        pri, val = fake_net(inputs, masks, 1)
+        for t in trees:
+            _complete(t, rows, pri, val)
+        trees[0].select_leaves()
+        trees[1].select_leaves(encode_out=buf)
+    a, b = trees[0].root_outputs(), trees[1].root_outputs()
+    assert torch.equal(a["visit_counts"], b["visit_counts"]) and torch.equal(a["root_values"], b["root_values"])
+    with pytest.raises(RuntimeError):
+        trees[1].select_leaves(encode_out=torch.zeros((n, 11, 6, 6), dtype=torch.bfloat16, device=DEV))
