@@ -113,6 +113,96 @@ apply_moves_kernel(lzb_states_in in, int64_t B, const int32_t* __restrict__ code
     }
 }
 
+// Thread-per-action variant for large batches.  A warp per action keeps only 64 actions in flight per SM and one
+// action's dependent loads cost ~9 us, i.e. ~1 action/ns for the whole chip (6 % of the HBM roof at 384 B/action);
+// with one THREAD per action 2,048 actions per SM are in flight.  Each thread gathers its parent's 3 x 36 bytes as
+// 27 aligned 32-bit words, builds the bitboards with byte tests, applies the action with the same apply_action()
+// and writes the child's bytes back as words (children of consecutive threads are contiguous in memory).
+__device__ __forceinline__ void words_to_boards(const uint32_t (&bw)[9], uint64_t& black, uint64_t& white, uint64_t& other) {
+    black = white = other = 0;
+#pragma unroll
+    for (int w = 0; w < 9; ++w)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t byte = (bw[w] >> (8 * k)) & 0xFFu;
+            const uint64_t bit = 1ULL << (4 * w + k);
+            if (byte == 1u) black |= bit;
+            else if (byte == 0xFFu) white |= bit;
+            else if (byte != 0u) other |= bit;
+        }
+}
+__device__ __forceinline__ uint64_t words_to_marks(const uint32_t (&mw)[9]) {
+    uint64_t m = 0;
+#pragma unroll
+    for (int w = 0; w < 9; ++w)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((mw[w] >> (8 * k)) & 0xFFu) m |= 1ULL << (4 * w + k);
+    return m;
+}
+
+template <bool kInplace>
+__global__ void __launch_bounds__(kThreads, 3)
+apply_moves_thread_kernel(lzb_states_in in, int64_t B, const int32_t* __restrict__ codes, const int64_t* __restrict__ parents,
+                          int64_t N, lzb_states_out out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+        const int64_t p = parents[i];
+        if (p < 0 || p >= B) continue;                         // :584-587 / :770-773
+        uint32_t bw[9];                                        // kept: bytes outside -1 / 0 / +1 are carried over
+        State<long long> s;
+        {
+            uint32_t mbw[9], mww[9];
+            const uint32_t* bp = reinterpret_cast<const uint32_t*>(in.board + p * 36);
+            const uint32_t* mbp = reinterpret_cast<const uint32_t*>(in.marks_black + p * 36);
+            const uint32_t* mwp = reinterpret_cast<const uint32_t*>(in.marks_white + p * 36);
+#pragma unroll
+            for (int w = 0; w < 9; ++w) { bw[w] = bp[w]; mbw[w] = mbp[w]; mww[w] = mwp[w]; }
+            s.mb = words_to_marks(mbw);
+            s.mw = words_to_marks(mww);
+        }
+        s.phase = in.phase[p]; s.player = in.current_player[p];
+        s.pm_req = in.pending_marks_required[p]; s.pm_rem = in.pending_marks_remaining[p];
+        s.pc_req = in.pending_captures_required[p]; s.pc_rem = in.pending_captures_remaining[p];
+        s.forced = in.forced_removals_done[p];
+        s.move_count = in.move_count ? in.move_count[p] : 0;
+        s.msc = in.moves_since_capture ? in.moves_since_capture[p] : 0;
+        const int4 code = reinterpret_cast<const int4*>(codes)[i];
+        words_to_boards(bw, s.black, s.white, s.other);
+        apply_action(s, code.x, code.y, code.z);
+        const int64_t o = kInplace ? p : i;
+        uint32_t* ob = reinterpret_cast<uint32_t*>(out.board + o * 36);
+        uint32_t* omb = reinterpret_cast<uint32_t*>(out.marks_black + o * 36);
+        uint32_t* omw = reinterpret_cast<uint32_t*>(out.marks_white + o * 36);
+#pragma unroll
+        for (int w = 0; w < 9; ++w) {
+            uint32_t vb = 0, vmb = 0, vmw = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int cell = 4 * w + k;
+                const uint64_t bit = 1ULL << cell;
+                const uint32_t orig = (bw[w] >> (8 * k)) & 0xFFu;      // bytes that are not -1 / 0 / +1 are carried over
+                const uint32_t byte = (s.black & bit) ? 1u : (s.white & bit) ? 0xFFu : (s.other & bit) ? orig : 0u;
+                vb |= byte << (8 * k);
+                vmb |= (uint32_t)((s.mb >> cell) & 1) << (8 * k);
+                vmw |= (uint32_t)((s.mw >> cell) & 1) << (8 * k);
+            }
+            ob[w] = vb; omb[w] = vmb; omw[w] = vmw;
+        }
+        out.phase[o] = s.phase; out.current_player[o] = s.player;
+        out.pending_marks_required[o] = s.pm_req; out.pending_marks_remaining[o] = s.pm_rem;
+        out.pending_captures_required[o] = s.pc_req; out.pending_captures_remaining[o] = s.pc_rem;
+        out.forced_removals_done[o] = s.forced; out.move_count[o] = s.move_count; out.moves_since_capture[o] = s.msc;
+    }
+}
+
+// word access needs 4-byte aligned byte tensors (always true for whole torch tensors; a sliced view may not be)
+inline bool words_ok(const void* a, const void* b, const void* c, const void* d, const void* e, const void* f) {
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+             reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(f)) & 3) == 0;
+}
+constexpr int64_t kThreadApplyMin = 8192;      // below this the warp-per-action kernel's latency is as good
+
 // ------------------------------------------------------------------------------------------------------
 // (a6) states_to_model_input -- encoding.cpp:26-79 : f32[B,11,6,6]
 // ------------------------------------------------------------------------------------------------------
@@ -330,6 +420,12 @@ extern "C" int lzb_batch_apply_moves(const lzb_states_in* parents, int64_t B, co
     LZB_REQUIRE(codes && parent_indices, "null action arrays");
     LZB_REQUIRE(parents->move_count && parents->moves_since_capture, "move_count / moves_since_capture required");
     LZB_REQUIRE((reinterpret_cast<uintptr_t>(codes) & 15) == 0, "action_codes must be 16-byte aligned");
+    if (N >= kThreadApplyMin && words_ok(parents->board, parents->marks_black, parents->marks_white, children->board,
+                                         children->marks_black, children->marks_white)) {
+        apply_moves_thread_kernel<false><<<thread_grid(N), kThreads, 0, (cudaStream_t)stream>>>(*parents, B, codes,
+                                                                                                 parent_indices, N, *children);
+        return check_launch("apply_moves_thread_kernel");
+    }
     apply_moves_kernel<false><<<warp_grid(N), kThreads, 0, (cudaStream_t)stream>>>(*parents, B, codes, parent_indices,
                                                                                   N, *children);
     return check_launch("apply_moves_kernel");
@@ -341,6 +437,12 @@ extern "C" int lzb_batch_apply_moves_inplace(const lzb_states_out* states, int64
     if (N == 0) return LZB_OK;
     LZB_REQUIRE(codes && slot_indices, "null action arrays");
     LZB_REQUIRE((reinterpret_cast<uintptr_t>(codes) & 15) == 0, "action_codes must be 16-byte aligned");
+    if (N >= kThreadApplyMin && words_ok(states->board, states->marks_black, states->marks_white, states->board,
+                                         states->marks_black, states->marks_white)) {
+        apply_moves_thread_kernel<true><<<thread_grid(N), kThreads, 0, (cudaStream_t)stream>>>(as_in(states), B, codes,
+                                                                                                slot_indices, N, *states);
+        return check_launch("apply_moves_inplace_thread_kernel");
+    }
     apply_moves_kernel<true><<<warp_grid(N), kThreads, 0, (cudaStream_t)stream>>>(as_in(states), B, codes,
                                                                                  slot_indices, N, *states);
     return check_launch("apply_moves_inplace_kernel");

@@ -107,6 +107,58 @@ def test_batch_apply_moves_vs_oracle(v0):
         _cmp_states(out, oracle.batch_apply_moves(st, codes, parents))
 
 
+def test_batch_apply_moves_thread_kernel_large_batches(v0):
+    """N >= 8,192 runs the thread-per-action kernel (word loads / stores), smaller N the warp-per-action one: both must
+    give the oracle's children on garbage states x garbage codes (bytes outside -1/0/1 carried over, illegal actions and
+    out-of-range parents ignored), on every legal child of reachable states, in place, and on a 2-byte-misaligned view
+    (which has to fall back to the byte kernel)."""
+    rng = np.random.default_rng(12)
+    st = sparse_random_states(6000, 9)
+    st["board"] = st["board"].copy()
+    st["board"].reshape(-1)[rng.integers(0, st["board"].size, 3000)] = rng.integers(-5, 6, 3000).astype(np.int8)   # garbage bytes
+    n = 40_000
+    codes = np.stack([rng.integers(0, 10, n), rng.integers(-2, 38, n), rng.integers(-1, 5, n), rng.integers(-1, 36, n)],
+                     1).astype(np.int32)
+    parents = rng.integers(-2, 6003, n).astype(np.int64)                    # a few out of range
+    t = to_torch(st, DEV)
+    big = v0.batch_apply_moves(*t, torch.from_numpy(codes).to(DEV), torch.from_numpy(parents).to(DEV))
+    small = v0.batch_apply_moves(*t, torch.from_numpy(codes[:4000]).to(DEV), torch.from_numpy(parents[:4000]).to(DEV))
+    ok = (parents >= 0) & (parents < 6000)
+    want = oracle.batch_apply_moves(st, codes, np.where(ok, parents, 0))
+    for k, b_, s_ in zip(STATE_FIELDS, big, small):
+        e = np.asarray(want[k]).reshape(_np(b_).shape)
+        assert np.array_equal(_np(b_)[ok], e[ok]), k                         # rows of skipped parents are unspecified
+        assert np.array_equal(_np(s_)[ok[:4000]], e[:4000][ok[:4000]]), k
+    # all legal children of reachable states (> 8,192 rows)
+    ps = _playout_states(12, 33)
+    m, meta = oracle.encode_actions_fast(ps)
+    rows, cols = np.nonzero(m)
+    assert rows.size > 8192
+    out = v0.batch_apply_moves(*to_torch(ps, DEV), torch.from_numpy(meta[rows, cols]).to(DEV),
+                               torch.from_numpy(rows.astype(np.int64)).to(DEV))
+    _cmp_states(out, oracle.batch_apply_moves(ps, meta[rows, cols], rows.astype(np.int64)))
+    # in place, one legal action per slot, > 8,192 slots
+    big_ps = concat_states([ps] * 8)
+    nb = big_ps["board"].shape[0]
+    mb_, metab = oracle.encode_actions_fast(big_ps)
+    has = mb_.any(1)
+    slots = np.nonzero(has)[0].astype(np.int64)
+    assert slots.size > 8192
+    pick = np.array([np.nonzero(mb_[i])[0][(7 * i) % mb_[i].sum()] for i in slots])
+    codes_i = metab[slots, pick]
+    ti = to_torch(big_ps, DEV)
+    v0.batch_apply_moves_inplace(*ti, torch.from_numpy(codes_i).to(DEV), torch.from_numpy(slots).to(DEV))
+    _cmp_states(ti, oracle.batch_apply_moves_inplace(big_ps, codes_i, slots))
+    # a byte-misaligned board view -> byte kernel, same result
+    raw = torch.zeros((nb * 36 + 2,), dtype=torch.int8, device=DEV)
+    view = raw[2:].view(nb, 6, 6)
+    tv = to_torch(big_ps, DEV)
+    view.copy_(tv[0])
+    tv[0] = view
+    out_v = v0.batch_apply_moves(*tv, torch.from_numpy(codes_i).to(DEV), torch.from_numpy(slots).to(DEV))
+    _cmp_states(out_v, oracle.batch_apply_moves(big_ps, codes_i, slots))
+
+
 def test_batch_apply_moves_golden(v0):
     z = load_golden("apply_moves")
     out = v0.batch_apply_moves(*to_torch(golden_states(z, "in_"), DEV), torch.from_numpy(z["codes"]).to(DEV),
