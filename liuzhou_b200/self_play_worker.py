@@ -326,6 +326,11 @@ def run_self_play_iteration(model: torch.nn.Module, *, num_games: int, iteration
         return None
     manifests = [os.path.join(workspace, f"worker_manifest_{int(iteration_seed):06d}_{r:02d}.pt")
                  for r in range(world) if games[r] > 0]
-    return merge_worker_manifests(manifests, output_path=str(output_path), metadata_base=dict(metadata_base or {}),
-                                  target_samples_per_shard=int(target_samples_per_shard),
-                                  chunk_target_bytes=int(chunk_target_bytes), elapsed_sec=time.perf_counter() - started)
+    result = merge_worker_manifests(manifests, output_path=str(output_path), metadata_base=dict(metadata_base or {}),
+                                    target_samples_per_shard=int(target_samples_per_shard),
+                                    chunk_target_bytes=int(chunk_target_bytes), elapsed_sec=time.perf_counter() - started)
+    if not shard_dir:                      # the auto-created workspace only held the per-rank manifests (v1/train.py:1165)
+        import shutil
+
+        shutil.rmtree(workspace, ignore_errors=True)
+    return result
