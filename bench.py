@@ -429,6 +429,34 @@ def cpu_selfplay_baseline(budget_s: float = 20.0, trees: int = 32, sims: int = S
                       f"+ fp32 PyTorch ChessNet on {cores} host threads (subtree reuse as in the reference)"}
 
 
+def sustained_replay_ms(replay, stream, seconds: float = 1.0, warm_seconds: float = 0.6, max_reps: int = 0) -> float:
+    """Average duration of `replay()` over a LONG back-to-back run (default 1 s after 0.6 s of warm-up), so that the
+    clocks are the power-capped steady-state ones the real step runs at -- a 30-replay burst after an idle period runs
+    ~10 % faster (measured) and would overstate the fraction of the *sustained* peak."""
+    import torch
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    replay()
+    e0.record(stream)
+    for _ in range(10):
+        replay()
+    e1.record(stream)
+    e1.synchronize()
+    per = max(1e-3, e0.elapsed_time(e1) / 10)
+    warm = max(10, int(warm_seconds * 1e3 / per))
+    reps = max(20, int(seconds * 1e3 / per))
+    if max_reps:
+        warm, reps = min(warm, max_reps), min(reps, max_reps)
+    for _ in range(warm):
+        replay()
+    e0.record(stream)
+    for _ in range(reps):
+        replay()
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def time_trunk_conv(net, n, stream, reps: int = 30) -> dict:
     """One trunk layer of the network = one launch of conv_tc_kernel<9,2>; both epilogue variants (conv1: bias +
     ReLU; conv2: residual + BatchNorm + ReLU, two outputs), each timed with CUDA events over graph replays."""
@@ -454,14 +482,7 @@ def time_trunk_conv(net, n, stream, reps: int = 30) -> dict:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g.replay()
-        e0.record(stream)
-        for _ in range(reps):
-            g.replay()
-        e1.record(stream)
-        e1.synchronize()
-        return e0.elapsed_time(e1) / reps
+        return sustained_replay_ms(g.replay, stream, seconds=0.7, warm_seconds=0.4)
 
     ms1 = replay_ms(lambda: conv_bf16(a, t["wp1_0"], bias=t["bf1_0"], relu1=True, out1=o1))
     ms2 = replay_ms(lambda: conv_bf16(a, t["wp2_0"], residual=res, scale=t["s1_1"], shift=t["t1_1"], want_out2=True,
@@ -528,13 +549,34 @@ def time_tree_kernels(stepper, peaks, reps: int = 20) -> dict:
     exp_bytes = expansions * (32 + 880 + 4) + new_nodes * 64 + (levels + sims) * 24 + sims * 136
     sel_gbs = sel_bytes / reps / (sel_ms / 1e3) / 1e9
     exp_gbs = exp_bytes / reps / (exp_ms / 1e3) / 1e9
+    # the kernel the wave actually runs: expand + backup of wave w and select (+ input encoding) of wave w + 1 fused,
+    # timed in a sustained stream of [network, fused kernel] pairs
+    fused_ms = None
+    if m._fused_encode(m._wave_in):
+        tree.select_leaves(m._wave_in)
+        fe = []
+        for i in range(3 * reps):
+            m.net.forward_priors(m._wave_in, tree.pending_states, priors_out=m._wave_pri, values_out=m._wave_val)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            tree.complete_and_select(m._wave_pri, m._wave_val, m._wave_in)
+            b.record(stream)
+            fe.append((a, b))
+        m.net.forward_priors(m._wave_in, tree.pending_states, priors_out=m._wave_pri, values_out=m._wave_val)
+        tree.complete_pending(m._wave_pri, m._wave_val)
+        torch.cuda.synchronize()
+        fused_ms = sum(a.elapsed_time(b) for a, b in fe[reps:]) / (2 * reps)
+    per_wave_bytes = (sel_bytes + exp_bytes) / reps + tree.num_trees * tree.k * 4608          # + the encoded inputs
     return {"bound": "hbm (latency-limited: one dependent HBM round trip per tree level, one warp per tree)",
+            "expand_select_fused_ms": fused_ms,
+            "expand_select_fused_gbs": None if not fused_ms else per_wave_bytes / (fused_ms / 1e3) / 1e9,
+            "expand_select_fused_frac": None if not fused_ms else per_wave_bytes / (fused_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
             "select_ms": sel_ms, "expand_backup_ms": exp_ms, "select_gbs": sel_gbs, "expand_backup_gbs": exp_gbs,
             "peak_gbs": peaks["hbm_gbs"], "select_frac": sel_gbs / peaks["hbm_gbs"],
             "expand_backup_frac": exp_gbs / peaks["hbm_gbs"],
             "bytes_per_simulation": (sel_bytes + exp_bytes) / max(1, sims), "avg_depth": levels / max(1, sims),
             "avg_siblings_per_level": sibs / max(1, levels), "children_per_expansion": new_nodes / max(1, expansions),
-            "ncu": "profiles/r01_tree_heads_ncu_full.csv (DRAM bytes, occupancy, issue utilisation of both kernels)"}
+            "ncu": "profiles/r01_tree_kernels_ncu_full_v2.csv (DRAM bytes, occupancy, issue utilisation)"}
 
 
 def run_selfplay(args, world, rank, local_rank):
@@ -609,7 +651,8 @@ def run_selfplay(args, world, rank, local_rank):
     # graph replays re-launch the captured kernels: our kernels inside the root / wave graphs were counted at capture
     waves = stepper.mcts.waves
     launches = (_lib.launch_count() - launches0) + args.steps * (waves * stepper.mcts.wave_graph_launches
-                                                                 + stepper.mcts.root_graph_launches)
+                                                                 + stepper.mcts.root_graph_launches
+                                                                 + stepper.mcts.search_extra_launches)
     rank_ms = all_ranks(e0.elapsed_time(e1), world)
     elapsed_ms = max(rank_ms)                                         # max over ranks, device-timed
     positions = sum_over_ranks(float(games * args.steps), world)
@@ -626,23 +669,12 @@ def run_selfplay(args, world, rank, local_rank):
     torch.cuda.synchronize()
     with torch.cuda.graph(g):
         net._forward_eager(x)
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 50
-    g.replay()
-    f0.record(stream)
-    for _ in range(reps):
-        g.replay()
-    f1.record(stream)
-    f1.synchronize()
-    fwd_ms = f0.elapsed_time(f1) / reps
-    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stepper.mcts._wave_graph.replay()
-    w0.record(stream)
-    for _ in range(reps):
-        stepper.mcts._wave_graph.replay()
-    w1.record(stream)
-    w1.synchronize()
-    wave_ms = w0.elapsed_time(w1) / reps
+    # sustained (power-capped) clocks: 1 s of forward replays, then -- without a pause -- 200 wave replays (one ply's
+    # worth; more would overrun the node arena)
+    fwd_ms = sustained_replay_ms(g.replay, stream, seconds=1.0, warm_seconds=0.6)
+    stepper.mcts._first_graph.replay()           # the wave graph is [network, expand + next select]: it needs a select first
+    wave_ms = sustained_replay_ms(stepper.mcts._wave_graph.replay, stream, max_reps=100)
+    stepper.mcts._last_graph.replay()            # ... and the last network + expand leaves nothing pending
     tflops = slots * net.flops_per_state / (fwd_ms / 1e3) / 1e12
     tree_roof = time_tree_kernels(stepper, peaks)
     tree_stats = stepper.mcts.tree.stats()

@@ -257,6 +257,13 @@ LZB_API int lzb_tree_advance_roots(const lzb_tree *tree, const lzb_tree *scratch
 LZB_API int lzb_tree_expand_backup(const lzb_tree *tree, int32_t K, const int32_t *leaf_node, const int32_t *leaf_status,
                                    const float *priors, const float *values, int32_t do_backup, double virtual_loss,
                                    const int32_t *leaf_path, void *stream);
+/* complete_pending of wave w + select_leaves of wave w + 1 in ONE launch (trees are independent, so each warp expands,
+ * backs up and descends again without a grid-wide barrier): same arguments as the two calls; leaf_node / leaf_status /
+ * leaf_states / leaf_path are read (wave w) and then rewritten (wave w + 1); inputs_c64 (optional, may be NULL) receives
+ * the new leaves' network input as in lzb_tree_select_encode. */
+LZB_API int lzb_tree_expand_select(const lzb_tree *tree, int32_t K, int32_t *leaf_node, int32_t *leaf_status,
+                                   const float *priors, const float *values, double exploration_weight, double virtual_loss,
+                                   uint64_t *leaf_states, int32_t *leaf_path, void *inputs_c64, void *stream);
 /* root_outputs + root_priors (:592-624,:664-737); any output pointer may be NULL. */
 LZB_API int lzb_tree_root_outputs(const lzb_tree *tree, int32_t *visit_counts, float *root_action_values,
                                   float *root_values, uint8_t *legal_masks, uint8_t *terminal, float *root_priors,

@@ -144,14 +144,12 @@ constexpr int kLeafEval = 0;       // needs a network evaluation, then expand (+
 constexpr int kLeafDone = 1;       // terminal / inactive: nothing to evaluate (backup already done)
 constexpr int kLeafDuplicate = 2;  // K > 1 only: same leaf already pending in this wave (simulation dropped)
 
-__global__ void __launch_bounds__(kThreads, 4)      // 4 x 8 warps per SM: all 4,096 trees of a wave resident at once
-tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restrict__ leaf_node,
-                   int32_t* __restrict__ leaf_status, uint64_t* __restrict__ leaf_states, int32_t* __restrict__ leaf_path,
-                   int roots_only, uint4* __restrict__ enc_out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-    for (int64_t t = warp; t < A.num_trees; t += nwarps) {
+// The K descents of one tree, by one warp (SelectLeaves / SelectPath / SelectChild, portable_mcts.cpp:515-552,832-874).
+__device__ __forceinline__ void select_tree(const lzb_tree& A, int64_t t, int K, double c_puct, double vl,
+                                            int32_t* __restrict__ leaf_node, int32_t* __restrict__ leaf_status,
+                                            uint64_t* __restrict__ leaf_states, int32_t* __restrict__ leaf_path,
+                                            int roots_only, uint4* __restrict__ enc_out, int lane) {
+    {
         for (int k = 0; k < K; ++k) {
             const int64_t slot = t * K + k;
             int node = (int)t;
@@ -257,20 +255,28 @@ tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restr
     }
 }
 
+__global__ void __launch_bounds__(kThreads, 4)      // 4 x 8 warps per SM: all 4,096 trees of a wave resident at once
+tree_select_kernel(lzb_tree A, int K, double c_puct, double vl, int32_t* __restrict__ leaf_node,
+                   int32_t* __restrict__ leaf_status, uint64_t* __restrict__ leaf_states, int32_t* __restrict__ leaf_path,
+                   int roots_only, uint4* __restrict__ enc_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t t = warp; t < A.num_trees; t += nwarps)
+        select_tree(A, t, K, c_puct, vl, leaf_node, leaf_status, leaf_states, leaf_path, roots_only, enc_out, lane);
+}
+
 #ifndef LZB_EXPAND_MIN_BLOCKS
-#define LZB_EXPAND_MIN_BLOCKS 1
+#define LZB_EXPAND_MIN_BLOCKS 3
 #endif
 // Expand (portable_mcts.cpp:894-939) + Backup for every evaluated leaf slot of a tree, sequentially in slot
 // order (deterministic).  priors f32[slots,220] dense over the 220-d action space, values f32[slots].
-__global__ void __launch_bounds__(kThreads, LZB_EXPAND_MIN_BLOCKS)
-tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, const int32_t* __restrict__ leaf_status,
-                   const float* __restrict__ priors, const float* __restrict__ values, int do_backup, double vl,
-                   const int32_t* __restrict__ leaf_path) {
-    __shared__ float s_pri[kWarpsPerBlock][kActionDim];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + w;
-    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-    for (int64_t t = warp; t < A.num_trees; t += nwarps) {
+// (spri = this warp's 220-float staging row in shared memory)
+__device__ __forceinline__ void expand_tree(const lzb_tree& A, int64_t t, int K, const int32_t* __restrict__ leaf_node,
+                                            const int32_t* __restrict__ leaf_status, const float* __restrict__ priors,
+                                            const float* __restrict__ values, int do_backup, double vl,
+                                            const int32_t* __restrict__ leaf_path, float* spri, int lane) {
+    {
         for (int k = 0; k < K; ++k) {
             const int64_t slot = t * K + k;
             if (leaf_status[slot] != kLeafEval) continue;
@@ -301,22 +307,22 @@ tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, con
                 }
             } else {
                 __syncwarp();
-                for (int a = lane; a < kActionDim; a += 32) s_pri[w][a] = priors[slot * kActionDim + a];
+                for (int a = lane; a < kActionDim; a += 32) spri[a] = priors[slot * kActionDim + a];
                 __syncwarp();
                 // prior_sum accumulated sequentially in ascending action order, in fp64 (:909-918)
                 double prior_sum = 0.0;
                 int fc = 0;
                 if (lane == 0) {
                     // one ascending pass over the legal set: placement cells, then (from, dir) moves, then selections
-                    for (uint64_t m = L.place; m; m &= m - 1) prior_sum = __dadd_rn(prior_sum, (double)s_pri[w][ctz64(m)]);
+                    for (uint64_t m = L.place; m; m &= m - 1) prior_sum = __dadd_rn(prior_sum, (double)spri[ctz64(m)]);
                     for (uint64_t u = L.mv[0] | L.mv[1] | L.mv[2] | L.mv[3]; u; u &= u - 1) {
                         const int from = ctz64(u);
 #pragma unroll
                         for (int d = 0; d < 4; ++d)
-                            if ((L.mv[d] >> from) & 1) prior_sum = __dadd_rn(prior_sum, (double)s_pri[w][36 + from * 4 + d]);
+                            if ((L.mv[d] >> from) & 1) prior_sum = __dadd_rn(prior_sum, (double)spri[36 + from * 4 + d]);
                     }
-                    for (uint64_t m = L.sel; m; m &= m - 1) prior_sum = __dadd_rn(prior_sum, (double)s_pri[w][180 + ctz64(m)]);
-                    if (L.process) prior_sum = __dadd_rn(prior_sum, (double)s_pri[w][216]);
+                    for (uint64_t m = L.sel; m; m &= m - 1) prior_sum = __dadd_rn(prior_sum, (double)spri[180 + ctz64(m)]);
+                    if (L.process) prior_sum = __dadd_rn(prior_sum, (double)spri[216]);
                     fc = atomicAdd(&A.counters[0], n);
                     if ((int64_t)fc + n > A.capacity) { atomicOr(&A.counters[1], 1); fc = -1; }
                     else atomicAdd(&A.counters[2], 1);
@@ -333,7 +339,7 @@ tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, con
                             apply_index(cs, a);
                             store_packed(A.state, c, pack(cs));
                             A.visit[c] = 0; A.value_sum[c] = 0.0;
-                            A.prior[c] = uniform ? __ddiv_rn(1.0, (double)n) : __ddiv_rn((double)s_pri[w][a], prior_sum);
+                            A.prior[c] = uniform ? __ddiv_rn(1.0, (double)n) : __ddiv_rn((double)spri[a], prior_sum);
                             A.first_child[c] = -1; A.parent[c] = node;
                             uint32_t ci = (uint32_t)a;
                             if (game_over(cs)) ci |= kInfoTerminal;
@@ -357,6 +363,37 @@ tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, con
             }
             __syncwarp();
         }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, LZB_EXPAND_MIN_BLOCKS)
+tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, const int32_t* __restrict__ leaf_status,
+                   const float* __restrict__ priors, const float* __restrict__ values, int do_backup, double vl,
+                   const int32_t* __restrict__ leaf_path) {
+    __shared__ float s_pri[kWarpsPerBlock][kActionDim];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + w;
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t t = warp; t < A.num_trees; t += nwarps)
+        expand_tree(A, t, K, leaf_node, leaf_status, priors, values, do_backup, vl, leaf_path, s_pri[w], lane);
+}
+
+// Expand + backup of wave w FOLLOWED BY the descent of wave w + 1, tree by tree: the trees are independent, so the two
+// latency chains of a warp run back to back without a grid-wide barrier between them, and a simulation wave needs one
+// tree kernel instead of two (select -> network -> expand becomes network -> expand+select).  The warp's own writes
+// (children, statistics along the path) are ordered before its reads by __syncwarp().
+__global__ void __launch_bounds__(kThreads, LZB_EXPAND_MIN_BLOCKS)
+tree_expand_select_kernel(lzb_tree A, int K, int32_t* __restrict__ leaf_node, int32_t* __restrict__ leaf_status,
+                          const float* __restrict__ priors, const float* __restrict__ values, double c_puct, double vl,
+                          uint64_t* __restrict__ leaf_states, int32_t* __restrict__ leaf_path, uint4* __restrict__ enc_out) {
+    __shared__ float s_pri[kWarpsPerBlock][kActionDim];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + w;
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t t = warp; t < A.num_trees; t += nwarps) {
+        expand_tree(A, t, K, leaf_node, leaf_status, priors, values, 1, vl, leaf_path, s_pri[w], lane);
+        __syncwarp();
+        select_tree(A, t, K, c_puct, vl, leaf_node, leaf_status, leaf_states, leaf_path, 0, enc_out, lane);
     }
 }
 
@@ -777,6 +814,21 @@ extern "C" int lzb_tree_expand_backup(const lzb_tree* tree, int32_t K, const int
     tree_expand_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(
         *tree, K, leaf_node, leaf_status, priors, values, do_backup, virtual_loss, leaf_path);
     return check_launch("tree_expand_kernel");
+}
+
+extern "C" int lzb_tree_expand_select(const lzb_tree* tree, int32_t K, int32_t* leaf_node, int32_t* leaf_status,
+                                      const float* priors, const float* values, double c_puct, double virtual_loss,
+                                      uint64_t* leaf_states, int32_t* leaf_path, void* inputs_c64, void* stream) {
+    int rc = check_tree(tree);
+    if (rc) return rc;
+    LZB_REQUIRE(K >= 1 && K <= 64, "leaves per tree per wave must be in [1, 64]");
+    LZB_REQUIRE(c_puct >= 0.0 && c_puct == c_puct, "exploration_weight must be finite and non-negative");
+    LZB_REQUIRE(leaf_node && leaf_status && priors && values && leaf_states && leaf_path, "null pointer");
+    LZB_REQUIRE((reinterpret_cast<uintptr_t>(inputs_c64) & 15) == 0, "inputs must be 16-byte aligned");
+    tree_expand_select_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(
+        *tree, K, leaf_node, leaf_status, priors, values, c_puct, virtual_loss, leaf_states, leaf_path,
+        reinterpret_cast<uint4*>(inputs_c64));
+    return check_launch("tree_expand_select_kernel");
 }
 
 extern "C" int lzb_tree_root_outputs(const lzb_tree* tree, int32_t* visits, float* qvalues, float* root_values,

@@ -236,6 +236,29 @@ class DeviceTreeBatch:
                                                ctypes.c_double(self.virtual_loss), ptr(None if root else self.leaf_path),
                                                stream_ptr(self.device)))
 
+    def complete_and_select(self, priors: torch.Tensor, values: torch.Tensor,
+                            encode_out: Optional[torch.Tensor] = None) -> None:
+        """``complete_pending`` of the current wave followed by ``select_leaves`` of the next one in ONE launch
+        (``lzb_tree_expand_select``): trees are independent, so every warp expands, backs up and descends again without a
+        grid-wide barrier in between.  Only after ``select_leaves`` (not after ``prepare_roots``)."""
+        if self._pending_is_root:
+            raise RuntimeError("complete_and_select follows select_leaves, not prepare_roots")
+        slots = self.num_trees * self.k
+        if tuple(priors.shape) != (slots, ACTION_DIM) or values.numel() != slots:
+            raise RuntimeError(f"priors must be [{slots}, 220] and values [{slots}]")
+        require_cuda(priors, "priors")
+        p = priors.to(torch.float32).contiguous()
+        v = values.to(torch.float32).contiguous()
+        if encode_out is not None and (encode_out.dtype != torch.bfloat16 or tuple(encode_out.shape) != (slots, 64, 6, 6)
+                                       or not encode_out.is_contiguous(memory_format=torch.channels_last)):
+            raise RuntimeError(f"encode_out must be bfloat16 [{slots},64,6,6] in channels_last memory format")
+        with torch.cuda.device(self.device):
+            check(lib().lzb_tree_expand_select(ctypes.byref(self._struct), ctypes.c_int32(self.k), ptr(self.leaf_node),
+                                               ptr(self.leaf_status), ptr(p), ptr(v),
+                                               ctypes.c_double(self.exploration_weight), ctypes.c_double(self.virtual_loss),
+                                               ptr(self.leaf_states), ptr(self.leaf_path), ptr(encode_out),
+                                               stream_ptr(self.device)))
+
     def root_outputs(self, with_priors: bool = True) -> dict:
         t, dev = self.num_trees, self.device
         with torch.cuda.device(dev):

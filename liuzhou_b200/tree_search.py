@@ -76,7 +76,9 @@ class TreeMCTS:
         self._wave_val = self._root_val if k == 1 else torch.zeros((slots,), dtype=torch.float32, device=dev)
         self._wave_graph: Optional[torch.cuda.CUDAGraph] = None
         self._root_graph: Optional[torch.cuda.CUDAGraph] = None
-        self.root_graph_launches = self.wave_graph_launches = 0
+        self.root_graph_launches = self.wave_graph_launches = self.search_extra_launches = 0
+        self._first_graph: Optional[torch.cuda.CUDAGraph] = None
+        self._last_graph: Optional[torch.cuda.CUDAGraph] = None
         self.evals = 0
 
     # one network evaluation of the pending leaves + expansion (+ backup).  On the tcgen05 path the network input is
@@ -100,10 +102,32 @@ class TreeMCTS:
         self.tree.prepare_roots(self._root_in if fused else None)
         self._eval_pending(True, fused)
 
-    def _wave_step(self) -> None:
+    # A search is: root step, noise, FIRST select, then waves - 1 times [network -> expand+backup -> next select] and
+    # one last [network -> expand+backup].  The bracketed parts are one CUDA graph each; expand of wave w and select of
+    # wave w + 1 are ONE kernel (lzb_tree_expand_select), so a wave has a single tree kernel.
+    def _first_select(self) -> None:
         fused = self._fused_encode(self._wave_in)
         self.tree.select_leaves(self._wave_in if fused else None)
-        self._eval_pending(False, fused)
+        if not fused:
+            encode_inputs(self.tree.pending_states, "bf16_nhwc", out=self._wave_in)
+
+    def _wave_mid(self) -> None:
+        tree = self.tree
+        fused = self._fused_encode(self._wave_in)
+        self.net.forward_priors(self._wave_in, tree.pending_states, priors_out=self._wave_pri, values_out=self._wave_val)
+        tree.complete_and_select(self._wave_pri, self._wave_val, self._wave_in if fused else None)
+        if not fused:
+            encode_inputs(tree.pending_states, "bf16_nhwc", out=self._wave_in)
+
+    def _wave_last(self) -> None:
+        tree = self.tree
+        self.net.forward_priors(self._wave_in, tree.pending_states, priors_out=self._wave_pri, values_out=self._wave_val)
+        tree.complete_pending(self._wave_pri, self._wave_val)
+
+    def _wave_step(self) -> None:
+        """One stand-alone wave (select -> network -> expand + backup); used by tools and the tree-kernel timing."""
+        self._first_select()
+        self._wave_last()
 
     def _capture(self) -> None:
         dev = self.device
@@ -111,7 +135,9 @@ class TreeMCTS:
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):          # warm up (cuDNN autotune / workspace) outside the capture
             self._root_step()
-            self._wave_step()
+            self._first_select()
+            self._wave_mid()
+            self._wave_last()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         from ._lib import launch_count
@@ -122,10 +148,20 @@ class TreeMCTS:
         with torch.cuda.graph(self._root_graph):
             self._root_step()
         c1 = launch_count()
+        self._first_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._first_graph, pool=self._root_graph.pool()):
+            self._first_select()
+        c2 = launch_count()
         self._wave_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._wave_graph, pool=self._root_graph.pool()):
-            self._wave_step()
-        self.root_graph_launches, self.wave_graph_launches = c1 - c0, launch_count() - c1
+            self._wave_mid()
+        c3 = launch_count()
+        self._last_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._last_graph, pool=self._root_graph.pool()):
+            self._wave_last()
+        c4 = launch_count()
+        self.root_graph_launches, self.wave_graph_launches = c1 - c0, c3 - c2
+        self.search_extra_launches = (c2 - c1) + (c4 - c3) - (c3 - c2)     # per search, on top of waves x wave_graph
 
     def _apply_root_noise(self) -> None:
         """Dirichlet(alpha) over each root's legal actions mixed with weight epsilon (portable_cpp_mcts.py:180-199,
@@ -177,11 +213,16 @@ class TreeMCTS:
             self._root_step()
         if cfg.add_dirichlet_noise if add_dirichlet_noise is None else add_dirichlet_noise:
             self._apply_root_noise()
-        for _ in range(self.waves):
-            if use_graph:
+        if use_graph:
+            self._first_graph.replay()
+            for _ in range(self.waves - 1):
                 self._wave_graph.replay()
-            else:
-                self._wave_step()
+            self._last_graph.replay()
+        else:
+            self._first_select()
+            for _ in range(self.waves - 1):
+                self._wave_mid()
+            self._wave_last()
         self.evals += self.num_trees * (1 + self.waves * tree.k)
         beta = float(cfg.policy_target_prior_pseudocount)
         do_sample = cfg.sample_moves if sample_moves is None else sample_moves

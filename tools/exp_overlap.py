@@ -72,6 +72,7 @@ for groups in (1, 2, 4):
         m._capture()
         m.tree.reset(st, None)
         m._root_graph.replay()
+        m._first_graph.replay()          # the wave graph is [network, expand + next select]: it needs a select first
         searchers.append(m)
     torch.cuda.synchronize()
     streams = [torch.cuda.Stream(device=dev) for _ in range(groups)]
