@@ -245,13 +245,13 @@ LZB_API int lzb_tree_prepare_roots(const lzb_tree *tree, int32_t *leaf_node, int
 /* advance_roots (:739-768) + the start of new games, with subtree reuse: for every tree the child reached by
  * actions[t] (i32, an action index in [0,220)) becomes the root and keeps its subtree; actions[t] < 0 or an inactive
  * tree keeps the tree unchanged; reset_mask[t] != 0 (optional, with reset_states u64[T,4]) replaces the tree by a
- * fresh unexpanded root.  The kept subtrees are compacted (depth-first walk, one warp per tree, no work list) into
- * `scratch` (a second arena with its own arrays, capacity >= the nodes kept) and copied back, so the arena holds no
- * dead nodes afterwards.
+ * fresh unexpanded root.  The kept subtrees are compacted into `scratch` (a second arena with its own arrays,
+ * capacity >= the nodes kept) by node-parallel passes and copied back, so the arena holds no dead nodes afterwards.
+ * work: i32[num_trees + capacity] temporary (new root per tree, children-block remap per old node).
  * Sticky flags in counters[1]: 1 arena/scratch exhausted (the node is kept as an unexpanded leaf), 2 action is not a
  * child of the root (the reference throws). */
 LZB_API int lzb_tree_advance_roots(const lzb_tree *tree, const lzb_tree *scratch, const int32_t *actions,
-                                   const uint64_t *reset_states, const uint8_t *reset_mask, void *stream);
+                                   const uint64_t *reset_states, const uint8_t *reset_mask, int32_t *work, void *stream);
 /* complete_pending (:554-590): expand every status-0 leaf with dense priors f32[T*K,220] / values f32[T*K],
  * then back up (do_backup = 0 for roots, :575). */
 LZB_API int lzb_tree_expand_backup(const lzb_tree *tree, int32_t K, const int32_t *leaf_node, const int32_t *leaf_status,

@@ -401,8 +401,10 @@ tree_expand_select_kernel(lzb_tree A, int K, int32_t* __restrict__ leaf_node, in
 // subtree (visit counts, value sums, priors, states); everything else of the old tree is dropped.  The reference
 // moves a unique_ptr; here the kept subtree is copied into a scratch arena (children blocks stay
 // contiguous, one atomicAdd on the scratch bump pointer per block), which is then copied back over the arena prefix --
-// a copying collector, so the arena never accumulates dead nodes over a game.  One warp per tree, depth-first, no
-// work list.
+// a copying collector, so the arena never accumulates dead nodes over a game.  Three passes: (1) one warp per tree
+// finds the child that becomes the root and writes the new root; (2) one thread per old NODE decides whether it is kept
+// and reserves its children block; (3) one thread per old node copies itself to its new place.  Nothing walks a tree,
+// so the cost does not depend on the size of the largest kept subtree.
 //   action < 0 or inactive tree : the tree is kept as it is (reference: early return), i.e. copied with its own root
 //   reset_mask[t]               : the tree is replaced by a fresh unexpanded root for reset_states[t] (a new game)
 //   action not among the root's children : counters[1] |= 2 (the reference throws), tree kept
@@ -423,30 +425,9 @@ __device__ __forceinline__ void copy_node(const lzb_tree& A, int s, const lzb_tr
     store_packed(B.state, d, load_packed(A.state, s));
 }
 
-// Allocate the children block of node s (old arena) in the new arena and copy it under node d; returns the block's first
-// index, or -1 when the new arena is full (d then stays an unexpanded leaf and the sticky flag is raised).
-__device__ __forceinline__ int copy_children(const lzb_tree& A, const lzb_tree& B, int s, int d, uint32_t inf, int lane) {
-    const int n = info_nchild(inf), sfc = A.first_child[s];
-    int dfc = 0;
-    if (lane == 0) {
-        dfc = atomicAdd(&B.counters[0], n);
-        if ((int64_t)dfc + n > B.capacity) { atomicOr(&B.counters[1], kFlagArena); dfc = -1; }
-    }
-    dfc = __shfl_sync(0xffffffffu, dfc, 0);
-    if (dfc < 0) {
-        if (lane == 0) B.info[d] = B.info[d] & ~(kInfoExpanded | (0xFFu << 8));
-        __syncwarp();
-        return -1;
-    }
-    for (int i = lane; i < n; i += 32) copy_node(A, sfc + i, B, dfc + i, A.info[sfc + i] & ~kInfoPending, d);
-    if (lane == 0) B.first_child[d] = dfc;
-    __syncwarp();
-    return dfc;
-}
-
 __global__ void __launch_bounds__(kThreads)
 tree_advance_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ actions, const uint64_t* __restrict__ reset_states,
-                    const uint8_t* __restrict__ reset_mask) {
+                    const uint8_t* __restrict__ reset_mask, int32_t* __restrict__ src_root_out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
@@ -464,6 +445,7 @@ tree_advance_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ actions,
                 if (s.player == -1) inf |= kInfoWhite;
                 B.info[t] = inf;
                 B.root_value[t] = 0.0;
+                src_root_out[t] = -1;                                       // every node of the old tree is dropped
             }
             continue;
         }
@@ -488,45 +470,87 @@ tree_advance_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ actions,
             copy_node(A, src_root, B, (int)t, inf, -1);
             B.root_value[t] = src_root == (int)t ? A.root_value[t] : 0.0;
         }
-        // Depth-first walk of the kept subtree with O(1) state: (s, d) = current node in the old / new arena.  A node's
-        // children block is allocated and copied when the node is entered; then the walk descends into the first child
-        // that has children of its own, and on the way back up continues with the next such sibling (its position is
-        // recovered from the parent's first_child).  No work list, so there is no bound on the size of a kept subtree
-        // other than the arena itself (roots that inherit thousands of visits over forced move sequences are routine).
-        if ((src_inf & kInfoExpanded) && info_nchild(src_inf) > 0) {
-            int s = src_root, d = (int)t, start = 0;
-            uint32_t inf = src_inf;
-            int dfc = copy_children(A, B, s, d, inf, lane);
-            while (dfc >= 0) {
-                const int n = info_nchild(inf), sfc = A.first_child[s];
-                int found = -1;
-                for (int base = start & ~31; base < n && found < 0; base += 32) {
-                    const int i = base + lane;
-                    bool grow = false;
-                    if (i < n && i >= start) {
-                        const uint32_t ci = A.info[sfc + i];
-                        grow = (ci & kInfoExpanded) && info_nchild(ci) > 0;
-                    }
-                    const uint32_t m = __ballot_sync(0xffffffffu, grow);
-                    if (m) found = base + __ffs(m) - 1;
-                }
-                if (found >= 0) {
-                    const int cs = sfc + found, cd = dfc + found;
-                    const uint32_t cinf = A.info[cs];
-                    const int cdfc = copy_children(A, B, cs, cd, cinf, lane);
-                    if (cdfc >= 0) { s = cs; d = cd; inf = cinf; dfc = cdfc; start = 0; }
-                    else start = found + 1;                      // arena exhausted: that child stays a leaf
-                } else {
-                    if (s == src_root) break;
-                    const int ps = A.parent[s];
-                    start = s - A.first_child[ps] + 1;
-                    d = B.parent[d];
-                    s = ps;
-                    inf = A.info[s];
-                    dfc = B.first_child[d];
-                }
+        if (lane == 0) src_root_out[t] = src_root;
+    }
+}
+
+// Pass 2 (one THREAD per old node): is the node kept?  It walks its parent chain to the depth-1 ancestor x and the tree t
+// (a handful of dependent loads, all 10-20 M nodes in flight at once instead of one latency chain per tree); it is kept
+// iff the whole tree is kept (src_root[t] == t) or x is the child that becomes the root.  A kept node with children
+// reserves its children block in the new arena (one atomicAdd) and publishes it in remap[]:
+//   remap[i] = -2 dropped | -1 kept, no children block | >= 0 first index of its children block in the new arena.
+constexpr int kDropped = -2, kNoBlock = -1;
+
+__device__ __forceinline__ bool node_kept(const lzb_tree& A, const int32_t* __restrict__ src_root, int i, int& tree_out) {
+    const int T = (int)A.num_trees;
+    int x = i, p = A.parent[x];
+    while (p >= T) { x = p; p = A.parent[x]; }
+    tree_out = p;
+    const int sr = src_root[p];
+    return sr == p || sr == x;
+}
+
+__global__ void __launch_bounds__(256)
+tree_advance_mark_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ src_root, int32_t* __restrict__ remap) {
+    const int64_t top = min((int64_t)A.counters[0], A.capacity);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int T = (int)A.num_trees;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < top; i += stride) {
+        bool kept;
+        if (i < T) kept = src_root[i] == (int)i;                        // an old root survives only if its tree is kept whole
+        else { int t; kept = node_kept(A, src_root, (int)i, t); }
+        int r = kDropped;
+        if (kept) {
+            const uint32_t inf = A.info[i];
+            const int n = (inf & kInfoExpanded) ? info_nchild(inf) : 0;
+            r = kNoBlock;
+            if (n > 0) {
+                const int fc = atomicAdd(&B.counters[0], n);
+                if ((int64_t)fc + n > B.capacity) atomicOr(&B.counters[1], kFlagArena);   // node stays a leaf
+                else r = fc;
             }
         }
+        remap[i] = r;
+    }
+}
+
+// Pass 3 (one thread per old node): a kept node copies itself to  remap[parent] + (its position among its siblings)
+// with its parent's and its children's new indices; the node that becomes the root only hands its block to slot t.
+__global__ void __launch_bounds__(256)
+tree_advance_copy_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ src_root, const int32_t* __restrict__ remap) {
+    const int64_t top = min((int64_t)A.counters[0], A.capacity);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int T = (int)A.num_trees;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < top; i += stride) {
+        const int r = remap[i];
+        if (r == kDropped) continue;
+        if (i < T) {                                   // root of a tree that is kept as it is (already copied by pass 1)
+            B.first_child[i] = r;
+            if (r == kNoBlock && (A.info[i] & kInfoExpanded) && info_nchild(A.info[i]) > 0)
+                B.info[i] = B.info[i] & ~(kInfoExpanded | (0xFFu << 8));
+            continue;
+        }
+        int t;
+        node_kept(A, src_root, (int)i, t);
+        const int sr = src_root[t];
+        uint32_t inf = A.info[i] & ~kInfoPending;
+        if (r == kNoBlock && (inf & kInfoExpanded) && info_nchild(inf) > 0) inf &= ~(kInfoExpanded | (0xFFu << 8));   // arena full
+        if ((int)i == sr) {                            // the new root itself lives in slot t (pass 1); just link its block
+            B.first_child[t] = r;
+            if (r == kNoBlock && (A.info[i] & kInfoExpanded) && info_nchild(A.info[i]) > 0)
+                B.info[t] = B.info[t] & ~(kInfoExpanded | (0xFFu << 8));
+            continue;
+        }
+        const int p = A.parent[i];
+        const int pblock = remap[p];
+        if (pblock < 0) continue;                      // the parent lost its block (arena full): unreachable, drop
+        int p_new;
+        if (p == sr) p_new = t;
+        else if (p < T) p_new = p;
+        else { const int gp = A.parent[p]; p_new = remap[gp] + (p - A.first_child[gp]); }
+        const int d = pblock + ((int)i - A.first_child[p]);
+        copy_node(A, (int)i, B, d, inf, p_new);
+        B.first_child[d] = r;                          // -1 (kNoBlock) or the children block
     }
 }
 
@@ -788,18 +812,24 @@ extern "C" int lzb_tree_prepare_roots(const lzb_tree* tree, int32_t* leaf_node, 
 }
 
 extern "C" int lzb_tree_advance_roots(const lzb_tree* tree, const lzb_tree* scratch, const int32_t* actions,
-                                      const uint64_t* reset_states, const uint8_t* reset_mask, void* stream) {
+                                      const uint64_t* reset_states, const uint8_t* reset_mask, int32_t* work,
+                                      void* stream) {
     int rc = check_tree(tree);
     if (rc) return rc;
     rc = check_tree(scratch);
     if (rc) return rc;
     LZB_REQUIRE(scratch->num_trees == tree->num_trees && scratch->capacity >= tree->num_trees, "scratch arena mismatch");
     LZB_REQUIRE(scratch->visit != tree->visit && scratch->state != tree->state, "scratch arena must not alias the tree");
-    LZB_REQUIRE(actions, "null actions");
+    LZB_REQUIRE(actions && work, "null actions / work array");
     LZB_REQUIRE((reset_states == nullptr) == (reset_mask == nullptr), "reset_states and reset_mask go together");
     cudaStream_t st = (cudaStream_t)stream;
     tree_advance_begin_kernel<<<1, 32, 0, st>>>(*tree, *scratch);
-    tree_advance_kernel<<<warp_grid(tree->num_trees), kThreads, 0, st>>>(*tree, *scratch, actions, reset_states, reset_mask);
+    int32_t* src_root = work;                          // [num_trees]
+    int32_t* remap = work + tree->num_trees;           // [capacity]
+    tree_advance_kernel<<<warp_grid(tree->num_trees), kThreads, 0, st>>>(*tree, *scratch, actions, reset_states, reset_mask,
+                                                                        src_root);
+    tree_advance_mark_kernel<<<148 * 8, 256, 0, st>>>(*tree, *scratch, src_root, remap);
+    tree_advance_copy_kernel<<<148 * 8, 256, 0, st>>>(*tree, *scratch, src_root, remap);
     tree_copy_back_kernel<<<148 * 8, 256, 0, st>>>(*scratch, *tree);
     return check_launch("tree_advance_kernel");
 }

@@ -139,6 +139,7 @@ class DeviceTreeBatch:
                   "state": torch.empty((cap, 4), dtype=torch.int64, device=dev),
                   "root_value": torch.zeros((t,), dtype=torch.float64, device=dev),
                   "counters": torch.zeros((8,), dtype=torch.int32, device=dev)}
+            self._work = torch.empty((t + cap,), dtype=torch.int32, device=dev)
         st = _TreeStruct()
         for name in _ARENA_FIELDS:
             setattr(st, name, sc[name].data_ptr())
@@ -169,7 +170,7 @@ class DeviceTreeBatch:
         self._ensure_scratch()
         with torch.cuda.device(self.device):
             check(lib().lzb_tree_advance_roots(ctypes.byref(self._struct), ctypes.byref(self._scratch_struct), ptr(a),
-                                               ptr(rs), ptr(rm), stream_ptr(self.device)))
+                                               ptr(rs), ptr(rm), ptr(self._work), stream_ptr(self.device)))
 
     def deactivate(self, tree_indices) -> None:
         """``PortableTreeBatch.deactivate`` (:770-778): the listed trees are skipped by every later call."""
