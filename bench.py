@@ -471,7 +471,9 @@ def time_trunk_conv(net, n, stream, reps: int = 30) -> dict:
                 "flops_per_state": 0.0, "traffic_bytes": None}
     dev = net.device
     cl = torch.channels_last
-    a = torch.randn((n, 128, 6, 6), device=dev, dtype=torch.bfloat16).contiguous(memory_format=cl)
+    # post-ReLU statistics like the real activations (half zeros): tensor-core power, and with it the clock under the
+    # power cap, depends on the operand data
+    a = torch.relu(torch.randn((n, 128, 6, 6), device=dev, dtype=torch.bfloat16)).contiguous(memory_format=cl)
     res = torch.randn_like(a)
     o1, o2 = torch.empty_like(a), torch.empty_like(a)
 
@@ -663,6 +665,11 @@ def run_selfplay(args, world, rank, local_rank):
     # timed alone with CUDA events on its stream; the tree kernels are the remainder of the wave.
     slots = games * k
     x = net.new_input(slots)
+    # real positions as input: tensor-core power (hence the clock under the power cap) depends on the data -- an
+    # all-zero input runs the same forward ~15 % faster and would not describe the forward inside a wave
+    from liuzhou_b200.tree import encode_inputs as _encode_inputs
+
+    _encode_inputs(stepper.states.repeat(k, 1) if k > 1 else stepper.states, "bf16_nhwc", out=x)
     g = torch.cuda.CUDAGraph()
     for _ in range(3):
         net._forward_eager(x)
