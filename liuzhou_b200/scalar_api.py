@@ -332,6 +332,10 @@ def _apply(state: GameState, move: MoveRecord, count_move: bool) -> GameState:
         raise RuntimeError("Move phase does not match state phase.")                   # move_generator.cpp:362
     if move.action_type not in _PHASE_KIND[Phase(state.phase)]:
         raise RuntimeError(f"{Phase(state.phase).name} phase does not allow '{move.action_type_name}'.")   # :368-408
+    cells = (move.primary, move.secondary) if move.action_type == ActionType.MOVE else (
+        () if move.action_type == ActionType.PROCESS_REMOVAL else (move.primary,))
+    if any(not (0 <= r < BOARD_SIZE and 0 <= c < BOARD_SIZE) for r, c in cells):
+        raise RuntimeError(f"position outside the board: {move.to_dict()}")             # rule_engine.cpp bounds checks
     a = move.action_index()
     if a not in _legal_indices(state, ignore_game_over=True):
         raise RuntimeError(f"illegal move for the current state: {move.to_dict()}")    # rule_engine.cpp:229-666
@@ -375,6 +379,8 @@ def generate_movement_moves(state):
 
 
 def has_legal_movement_moves(state) -> bool:
+    if Phase(state.phase) != Phase.MOVEMENT:
+        raise RuntimeError("当前不是走子阶段")                                           # rule_engine.cpp:422-424
     return len(generate_movement_moves(state)) > 0
 
 
@@ -426,6 +432,45 @@ def handle_no_moves_phase3(state, stucked_player_removes, quiet: bool = False):
 
 def apply_counter_removal_phase3(state, opponent_removes, quiet: bool = False):
     return _apply(state, MoveRecord.counter_removal(opponent_removes), False)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# composite phase-1 / phase-3 calls (rule_engine.cpp:682-728, bound at module.cpp:1050-1084): the API the reference's
+# hand-built rule cases drive (tests/check_rule_engine_cases.py)
+# ----------------------------------------------------------------------------------------------------------------------
+def generate_legal_moves_phase1(state):
+    return generate_placement_positions(state)
+
+
+def apply_move_phase1(state, move, mark_positions=None):
+    """Placement followed by the mark selections it earned; marks passed for a placement that formed no shape raise."""
+    new_state = apply_placement_move(state, move)
+    if mark_positions:
+        if Phase(new_state.phase) != Phase.MARK_SELECTION:
+            raise RuntimeError("当前状态不需要标记，但传入了 mark_positions")          # rule_engine.cpp:693
+        for pos in mark_positions:
+            new_state = apply_mark_selection(new_state, pos)
+    return new_state
+
+
+def generate_legal_moves_phase3(state):
+    return generate_movement_moves(state)
+
+
+def has_legal_moves_phase3(state) -> bool:
+    return has_legal_movement_moves(state)
+
+
+def apply_move_phase3(state, move, capture_positions=None, quiet: bool = False):
+    """Movement followed by the captures it earned (without them the state stays in CAPTURE_SELECTION, as in the v0
+    C++ engine -- the legacy python engine raises there instead, src/rule_engine.py:621)."""
+    new_state = apply_movement_move(state, move, quiet)
+    if capture_positions:
+        if Phase(new_state.phase) != Phase.CAPTURE_SELECTION:
+            raise RuntimeError("当前状态不需要提子，但传入了 capture_positions")        # rule_engine.cpp:719
+        for pos in capture_positions:
+            new_state = apply_capture_selection(new_state, pos, quiet)
+    return new_state
 
 
 __all__ = [n for n in dir() if not n.startswith("_") and n not in ("annotations", "enum", "torch", "native", "List",
