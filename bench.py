@@ -167,6 +167,83 @@ class L2Flusher:
         self.buf.add_(1)
 
 
+def reference_gpu_line(games: int, sims: int, device_index: int, timeout_s: float = 600.0) -> dict:
+    """The v1 REFERENCE on the same GPU, same games / sims / network: the reference's own unmodified python
+    (`self_play_v1_gpu`, v1/python/self_play_gpu_runner.py:21-307 -> `V1RootMCTS.search_batch`, mcts_gpu.py:1249-1457)
+    over its own `v0_core` CUDA extension (oracle/_ref: its three .cu kernels compiled for sm_100 from the unmodified
+    sources) with its own PyTorch ChessNet under fp16 autocast -- run by oracle/ref_runner.py in a process of its own
+    (a process holds one module named v0_core).  This is the denominator of north_star's ">= 100x the v1 reference's
+    positions/s per GPU" and is reported next to our drop-in of the same backend (`root_puct_backend`)."""
+    runner = ROOT / "oracle" / "ref_runner.py"
+    if not (ROOT / "oracle" / "_ref" / "pysrc").is_dir() or not list((ROOT / "oracle" / "_ref").glob("v0_core*.so")):
+        return {"unavailable": "oracle/_ref (reference binaries + python copy) not present on this box"}
+    cmd = [sys.executable, str(runner), "selfplay", "--v0core", "ref", "--games", str(games), "--sims", str(sims),
+           "--device", f"cuda:{device_index}", "--warmup-games", str(min(256, games)), "--seed", str(SEED + 1)]
+    try:
+        res = subprocess.run(cmd, cwd=str(ROOT), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                             timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"reference run exceeded {timeout_s:.0f}s"}
+    if res.returncode != 0:
+        return {"unavailable": "reference run failed: " + res.stderr.strip().splitlines()[-1][:300] if res.stderr.strip() else "rc != 0"}
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    return {"value": out["positions_per_sec"], "unit": "positions/s", "positions": out["positions"],
+            "seconds": out["seconds"], "e2e": {"value": out["e2e_positions_per_sec"], "unit": "positions/s",
+                                               "d2h_bytes_per_step": out["d2h_bytes"]},
+            "avg_game_length": out["avg_game_length"], "draws": out["draws"],
+            "what": "UNMODIFIED reference python + reference v0_core CUDA (sm_100) + reference ChessNet (PyTorch eager, fp16 "
+                    f"autocast), {games} games x {sims} sims, search_backend=cuda_root, same GPU, separate process"}
+
+
+def legacy_cpu_line(timeout_s: float = 180.0) -> dict:
+    """BASELINE configs[0]: the legacy `src/` python rule engine + `src/mcts.py::self_play`, 1 game, 64 sims/move, the
+    reference tests' small random-init net, on ONE host core (the code is single-threaded python)."""
+    runner = ROOT / "oracle" / "ref_runner.py"
+    if not (ROOT / "oracle" / "_ref" / "pysrc" / "src" / "mcts.py").exists():
+        return {"unavailable": "oracle/_ref/pysrc not present on this box"}
+    try:
+        res = subprocess.run([sys.executable, str(runner), "legacy", "--games", "1", "--sims", "64"], cwd=str(ROOT),
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"legacy run exceeded {timeout_s:.0f}s"}
+    if res.returncode != 0:
+        return {"unavailable": "legacy run failed"}
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    return {"value": out["positions_per_sec"], "unit": "positions/s", "sims_per_sec": out["sims_per_sec"],
+            "positions": out["positions"], "seconds": out["seconds"], "cores": 1, "kind": "reference",
+            "what": "BASELINE configs[0]: legacy src/ rule engine + src/mcts.py self_play, 1 game x 64 sims, tiny net, CPU"}
+
+
+def ncu_dram_traffic(kernel_substr: str):
+    """(bytes per launch, csv name): dram__bytes_read.sum + dram__bytes_write.sum of the newest committed
+    `profiles/r*_ncu_full.csv` summary that has a row for the kernel (ncu --set full capture of the bench command)."""
+    import csv
+    import re
+
+    best = None
+    for f in sorted((ROOT / "profiles").glob("r*ncu_full*.csv")):
+        try:
+            rows = list(csv.reader(f.open()))
+        except Exception:
+            continue
+        if len(rows) < 3 or "Kernel Name" not in rows[0]:
+            continue
+        h = rows[0]
+        try:
+            ki, ri, wi = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = [(float(r[ri]) * unit.get(rows[1][ri], 1.0) + float(r[wi]) * unit.get(rows[1][wi], 1.0))
+                for r in rows[2:] if len(r) > max(ki, ri, wi) and kernel_substr in r[ki]]
+        if vals:
+            rnd = int(re.match(r"r(\d+)", f.name).group(1)) if re.match(r"r(\d+)", f.name) else 0
+            cand = (rnd, f.stat().st_mtime, sum(vals) / len(vals), f.name)
+            if best is None or cand[:2] > best[:2]:
+                best = cand
+    return (best[2], "profiles/" + best[3]) if best else (None, None)
+
+
 # ----------------------------------------------------------------------------------------------------
 # workload: config 2 -- rule-engine-only random playouts, 65,536 concurrent games per GPU
 # ----------------------------------------------------------------------------------------------------
@@ -337,50 +414,52 @@ def _default_model():
     return ChessNet()
 
 
-def cpu_selfplay_baseline(budget_s: float = 20.0, trees: int = 32, sims: int = SELFPLAY_SIMS,
-                          threads: int | None = None) -> dict:
-    """The reference's own CPU tree search (oracle/_ref/_liuzhou_portable_cpp, threaded C++) + fp32 PyTorch network
-    on all host cores, on a bounded sample of the same workload: `trees` games, `sims` simulations per move, as
-    many plies as fit the budget.  Falls back to the oracle's C port of the tree when oracle/_ref is absent."""
-    import numpy as np
-    import torch
+class CpuSelfPlaySession:
+    """The reference's own CPU tree search (oracle/_ref/_liuzhou_portable_cpp: threaded C++ `PortableTreeBatch`, the
+    reference's `--search_backend portable --portable_mcts_backend cpp`) + the fp32 PyTorch network on all host cores,
+    as ONE continuous self-play session: `trees` concurrent games (every network call is a batch of up to `trees`
+    leaves), `sims` simulations per move, subtree reuse as in the reference; finished games are restarted so the batch
+    stays full (steady state, like the GPU arm).  `ply()` = one move of every game.  Falls back to the oracle's C port of
+    the tree when oracle/_ref is absent."""
 
-    import oracle
-    from liuzhou_b200.net import bucket_logits_to_scalar
+    def __init__(self, trees: int = 256, sims: int = SELFPLAY_SIMS, threads: int | None = None):
+        import numpy as np
+        import torch
 
-    cores = threads or os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    model = _default_model().eval()
-    kind = "port"
-    portable = None
-    ref_dir = ROOT / "oracle" / "_ref"
-    if list(ref_dir.glob("_liuzhou_portable_cpp*.so")):
-        try:
-            sys.path.insert(0, str(ref_dir))
-            import _liuzhou_portable_cpp as portable  # noqa: F811
-            kind = "reference"
-        except Exception:
-            portable = None
-    states = oracle.initial_states(trees)
-    # diversify like the GPU arm: game i advanced by a different number of uniform-random plies
-    for i in range(trees):
-        tr = oracle.random_playout(SEED, i, (120 * i) // max(1, trees - 1), want_trace=False)
-        if not oracle.is_game_over(tr["final"]):
-            for k in oracle.STATE_FIELDS:
-                states[k][i] = np.asarray(tr["final"][k])[0]
+        import oracle
 
-    def evaluate(inputs, masks):
-        with torch.inference_mode():
-            lp1, lp2, lpm, vl = model(torch.from_numpy(inputs))
-            pri, _ = oracle.project_policy_logits_fast(lp1.numpy(), lp2.numpy(), lpm.numpy(), masks != 0)
-            return pri.astype(np.float32), bucket_logits_to_scalar(vl).numpy().astype(np.float32)
+        self.np, self.torch, self.oracle = np, torch, oracle
+        self.cores = threads or os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.model = _default_model().eval()
+        self.trees, self.sims = int(trees), int(sims)
+        self.kind, self.portable = "port", None
+        ref_dir = ROOT / "oracle" / "_ref"
+        if list(ref_dir.glob("_liuzhou_portable_cpp*.so")):
+            try:
+                sys.path.insert(0, str(ref_dir))
+                import _liuzhou_portable_cpp as portable
 
-    def new_tree(st):
-        if portable is not None:
+                self.portable, self.kind = portable, "reference"
+            except Exception:
+                self.portable = None
+        states = oracle.initial_states(self.trees)
+        # diversify like the GPU arm: game i advanced by a different number of uniform-random plies
+        for i in range(self.trees):
+            tr = oracle.random_playout(SEED, i, (120 * i) // max(1, self.trees - 1), want_trace=False)
+            if not oracle.is_game_over(tr["final"]):
+                for k in oracle.STATE_FIELDS:
+                    states[k][i] = np.asarray(tr["final"][k])[0]
+        self.tb = self._new_tree(states)
+        self.positions = self.evals = 0
+
+    def _new_tree(self, st):
+        np = self.np
+        if self.portable is not None:
             from types import SimpleNamespace
 
             objs = []
-            for i in range(trees):
+            for i in range(st["board"].shape[0]):
                 objs.append(SimpleNamespace(
                     board=[[int(v) for v in row] for row in st["board"][i].reshape(6, 6)], phase=int(st["phase"][i]),
                     current_player=int(st["current_player"][i]),
@@ -392,41 +471,67 @@ def cpu_selfplay_baseline(budget_s: float = 20.0, trees: int = 32, sims: int = S
                     pending_captures_required=int(st["pending_captures_required"][i]),
                     pending_captures_remaining=int(st["pending_captures_remaining"][i]),
                     moves_since_capture=int(st["moves_since_capture"][i])))
-            return portable.PortableTreeBatch(objs, exploration_weight=1.0, num_threads=cores)
-        return oracle.TreeBatch(st, 1.0)
+            return self.portable.PortableTreeBatch(objs, exploration_weight=1.0, num_threads=self.cores)
+        return self.oracle.TreeBatch(st, 1.0)
 
-    t0 = time.perf_counter()
-    positions = evals = 0
-    tb = new_tree(states)
-    while True:
-        pend = tb.prepare_roots()
-        if len(pend["tree_indices"]):
-            tb.complete_pending(*evaluate(pend["model_inputs"], pend["legal_masks"]))
-            evals += len(pend["tree_indices"])
+    def _evaluate(self, inputs, masks):
+        from liuzhou_b200.net import bucket_logits_to_scalar
+
+        np, torch = self.np, self.torch
+        with torch.inference_mode():
+            lp1, lp2, lpm, vl = self.model(torch.from_numpy(inputs))
+            pri, _ = self.oracle.project_policy_logits_fast(lp1.numpy(), lp2.numpy(), lpm.numpy(), masks != 0)
+            return pri.astype(np.float32), bucket_logits_to_scalar(vl).numpy().astype(np.float32)
+
+    def _complete(self, pend):
+        np = self.np
+        n = len(pend["tree_indices"])
+        if n:
+            self.tb.complete_pending(*self._evaluate(pend["model_inputs"], pend["legal_masks"]))
         else:
-            tb.complete_pending(np.zeros((0, 220), np.float32), np.zeros((0,), np.float32))
-        for _ in range(sims):
-            pend = tb.select_leaves()
-            n = len(pend["tree_indices"])
-            if n:
-                tb.complete_pending(*evaluate(pend["model_inputs"], pend["legal_masks"]))
-            else:
-                tb.complete_pending(np.zeros((0, 220), np.float32), np.zeros((0,), np.float32))
-            evals += n
+            self.tb.complete_pending(np.zeros((0, 220), np.float32), np.zeros((0,), np.float32))
+        self.evals += n
+
+    def ply(self) -> int:
+        """One move of every live game (sims simulations each); returns the positions produced."""
+        np, tb = self.np, self.tb
+        self._complete(tb.prepare_roots())
+        for _ in range(self.sims):
+            self._complete(tb.select_leaves())
         out = tb.root_outputs()
-        visits = out["visit_counts"]
         live = out["terminal"] == 0
-        positions += int(live.sum())
-        actions = np.where(live, visits.argmax(1), -1).astype(np.int32)
-        tb.advance_roots([int(a) for a in actions] if portable is not None else actions)
-        if time.perf_counter() - t0 > budget_s or not live.any():
+        n = int(live.sum())
+        self.positions += n
+        actions = np.where(live, out["visit_counts"].argmax(1), -1).astype(np.int32)
+        tb.advance_roots([int(a) for a in actions] if self.portable is not None else actions)
+        if n < self.trees:        # steady state: a session whose games have all ended starts over from fresh positions
+            if n == 0:
+                self.tb = self._new_tree(self.oracle.initial_states(self.trees))
+        return n
+
+    def describe(self) -> str:
+        tree = "reference _liuzhou_portable_cpp tree" if self.kind == "reference" else "oracle C tree port"
+        return (f"{tree} + fp32 PyTorch ChessNet on {self.cores} host threads, {self.trees} concurrent games "
+                f"(network batches of up to {self.trees}), subtree reuse as in the reference")
+
+
+def cpu_selfplay_baseline(budget_s: float = 20.0, trees: int = 256, sims: int = SELFPLAY_SIMS,
+                          threads: int | None = None) -> dict:
+    """Bounded sample of the same workload on the host cores: one continuous CpuSelfPlaySession, as many plies as start
+    within the budget (at least one)."""
+    sess = CpuSelfPlaySession(trees=trees, sims=sims, threads=threads)
+    t0 = time.perf_counter()
+    plies = 0
+    while True:
+        sess.ply()
+        plies += 1
+        if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return {"value": positions / dt, "unit": "positions/s", "cores": cores, "kind": kind,
-            "sims_per_sec": positions * sims / dt, "network_evals_per_sec": evals / dt,
-            "sample": f"{trees} games x {sims} sims/move, {positions} positions in {dt:.1f}s; "
-                      f"{'reference _liuzhou_portable_cpp tree' if kind == 'reference' else 'oracle C tree port'} "
-                      f"+ fp32 PyTorch ChessNet on {cores} host threads (subtree reuse as in the reference)"}
+    return {"value": sess.positions / dt, "unit": "positions/s", "cores": sess.cores, "kind": sess.kind,
+            "sims_per_sec": sess.positions * sims / dt, "network_evals_per_sec": sess.evals / dt,
+            "sample": f"{trees} games x {sims} sims/move, {plies} plies = {sess.positions} positions in {dt:.1f}s, "
+                      f"one continuous session; {sess.describe()}"}
 
 
 def sustained_replay_ms(replay, stream, seconds: float = 1.0, warm_seconds: float = 0.6, max_reps: int = 0) -> float:
@@ -468,7 +573,7 @@ def time_trunk_conv(net, n, stream, reps: int = 30) -> dict:
     if not (net.trunk is not None and net.trunk.use_tc and n % 64 == 0):
         return {"ms": float("nan"), "ms_conv1": float("nan"), "ms_conv2": float("nan"), "tflops": float("nan"),
                 "ms_in_chain": float("nan"), "tflops_in_chain": float("nan"), "launches_in_chain": 0,
-                "flops_per_state": 0.0, "traffic_bytes": None}
+                "flops_per_state": 0.0, "traffic_bytes": None, "traffic_source": None}
     dev = net.device
     cl = torch.channels_last
     # post-ReLU statistics like the real activations (half zeros): tensor-core power, and with it the clock under the
@@ -504,11 +609,13 @@ def time_trunk_conv(net, n, stream, reps: int = 30) -> dict:
     ms_chain = replay_ms(chain) / max(1, 2 * nb)
     flops_per_state = 2.0 * 36 * 128 * 128 * 9
     ms = 0.5 * (ms1 + ms2)
-    # per-launch DRAM traffic of the 4,096-state launch measured by ncu (38.07 MB read + 2.78 MB written), scaled by n
-    traffic = (38.074e6 + 2.776e6) * n / 4096.0
+    # per-launch DRAM traffic: read from the committed ncu --set full summary of this kernel (4,096-state launch), scaled by n
+    t4096, traffic_src = ncu_dram_traffic("conv_tc_kernel<9, 2>")
+    traffic = None if t4096 is None else t4096 * n / 4096.0
     return {"ms": ms, "ms_conv1": ms1, "ms_conv2": ms2, "tflops": n * flops_per_state / (ms / 1e3) / 1e12,
             "ms_in_chain": ms_chain, "tflops_in_chain": n * flops_per_state / (ms_chain / 1e3) / 1e12,
-            "launches_in_chain": 2 * nb, "flops_per_state": flops_per_state, "traffic_bytes": traffic}
+            "launches_in_chain": 2 * nb, "flops_per_state": flops_per_state, "traffic_bytes": traffic,
+            "traffic_source": traffic_src}
 
 
 def time_tree_kernels(stepper, peaks, reps: int = 20) -> dict:
@@ -533,7 +640,7 @@ def time_tree_kernels(stepper, peaks, reps: int = 20) -> dict:
         tree.select_leaves()
         e[1].record(stream)
         encode_inputs(tree.pending_states, "bf16_nhwc", out=m._wave_in)
-        m.net.forward_priors(m._wave_in, tree.pending_states, priors_out=m._wave_pri, values_out=m._wave_val)
+        m._wave_forward(None)
         e[2].record(stream)
         tree.complete_pending(m._wave_pri, m._wave_val)
         e[3].record(stream)
@@ -558,13 +665,13 @@ def time_tree_kernels(stepper, peaks, reps: int = 20) -> dict:
         tree.select_leaves(m._wave_in)
         fe = []
         for i in range(3 * reps):
-            m.net.forward_priors(m._wave_in, tree.pending_states, priors_out=m._wave_pri, values_out=m._wave_val)
+            m._wave_forward(None)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             tree.complete_and_select(m._wave_pri, m._wave_val, m._wave_in)
             b.record(stream)
             fe.append((a, b))
-        m.net.forward_priors(m._wave_in, tree.pending_states, priors_out=m._wave_pri, values_out=m._wave_val)
+        m._wave_forward(None)
         tree.complete_pending(m._wave_pri, m._wave_val)
         torch.cuda.synchronize()
         fused_ms = sum(a.elapsed_time(b) for a, b in fe[reps:]) / (2 * reps)
@@ -687,33 +794,62 @@ def run_selfplay(args, world, rank, local_rank):
     tree_stats = stepper.mcts.tree.stats()
     conv = time_trunk_conv(net, slots, stream)
 
-    # e2e: the same ply through host buffers -- states (reference byte layout) H2D from pinned memory, search +
-    # step on the device, new states + this ply's trajectory rows (2,692 B/position) D2H into pinned memory.
-    from liuzhou_b200 import native
+    # e2e: the PUBLIC ENTRY end to end -- one full self_play_v1_gpu(search_backend="tree") iteration per rank from a HOST
+    # model (weights H2D, BatchNorm folding, arenas, graph capture inside the timed region), all games from the initial
+    # position to their end with the reference's wave semantics (no refill), value-target finalisation, and the finished
+    # TensorSelfPlayBatch copied to pinned host memory (D2H).  N > 1: every rank plays its own iteration (weights
+    # broadcast from rank 0 first) and the compact trajectory gather to rank 0 is inside the timed region too.
+    from liuzhou_b200.self_play import self_play_v1_gpu
 
-    st_host = [t.cpu().pin_memory() for t in native.unpack_states(stepper.states)]
-    st_out = [torch.empty_like(t).pin_memory() for t in st_host]
-    blk = stepper.trajectory_block()
-    traj_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in blk]
-    h2d = sum(t.numel() * t.element_size() for t in st_host)
-    d2h = h2d + sum(t.numel() * t.element_size() for t in traj_host)
-    e2e_times = []
-    for it in range(2 + args.steps):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        dev_st = [t.to(dev, non_blocking=True) for t in st_host]
-        stepper.states = native.pack_states(dev_st)
-        stepper.step()
-        for dst, src in zip(st_out, native.unpack_states(stepper.states)):
+    del stepper
+    torch.cuda.empty_cache()
+    host_model = _default_model()
+    h2d = int(sum(t.numel() * t.element_size() for t in list(host_model.parameters()) + list(host_model.buffers())))
+    torch.manual_seed(SEED * 10007 + (rank + 1) * 9973 + 17)
+    barrier_sync(world)
+    t0 = time.perf_counter()
+    if world > 1:
+        import torch.distributed as dist
+        from liuzhou_b200 import dist as lzdist
+
+        dev_model = host_model.to(dev)
+        lzdist.broadcast_model(dev_model, src=0)
+        e2e_net = InferenceNet(dev_model, dev)
+    else:
+        e2e_net = InferenceNet(host_model, dev)
+    fb, fs = self_play_v1_gpu(e2e_net, num_games=games, mcts_simulations=sims, temperature_init=1.0,
+                              temperature_final=0.1, temperature_threshold=10, exploration_weight=1.0,
+                              device=str(dev), add_dirichlet_noise=True, concurrent_games=games,
+                              search_backend="tree", leaves_per_wave=k, tree_reuse=bool(args.tree_reuse))
+    gathered_positions = None
+    if world > 1:
+        merged = lzdist.gather_trajectories_compact(fb, dst=0)
+        out_b = merged if rank == 0 else None
+        gathered_positions = merged.num_samples if rank == 0 else 0
+    else:
+        out_b = fb
+    d2h = 0
+    if out_b is not None:
+        fields = (out_b.state_tensors, out_b.legal_masks, out_b.policy_targets, out_b.value_targets,
+                  out_b.soft_value_targets)
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in fields]
+        for dst, src in zip(host, fields):
             dst.copy_(src, non_blocking=True)
-        for dst, src in zip(traj_host, stepper.trajectory_block()):
-            dst.copy_(src, non_blocking=True)
-        torch.cuda.synchronize()
-        if it >= 2:
-            e2e_times.append(time.perf_counter() - t0)
-        st_host, st_out = st_out, st_host
-    e2e_elapsed = max_over_ranks(sum(e2e_times), world)
-    e2e_value = sum_over_ranks(float(games * len(e2e_times)), world) / e2e_elapsed
+        d2h = int(sum(h.numel() * h.element_size() for h in host))
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_elapsed = max_over_ranks(e2e_s, world)
+    e2e_positions = sum_over_ranks(float(fb.num_samples), world)
+    e2e_value = e2e_positions / e2e_elapsed
+    full_line = {"positions": int(e2e_positions), "seconds": e2e_elapsed, "plies_to_last_game_end": None,
+                 "avg_game_length": fs.avg_game_length, "black_wins": fs.black_wins, "white_wins": fs.white_wins,
+                 "draws": fs.draws, "gathered_positions_on_rank0": gathered_positions,
+                 "what": "one full self_play_v1_gpu(search_backend='tree') iteration per rank, wall clock incl. weight "
+                         "H2D, CUDA-graph capture, trajectory finalisation"
+                         + (", NCCL weight broadcast + compact trajectory gather to rank 0" if world > 1 else "")
+                         + " and the D2H copy of the finished batch to pinned memory"}
+    del fb, out_b
+    net = e2e_net
 
     # the same workload on the reference's production backend (root-only PUCT through the drop-in v0_core ops): one
     # warm-up + one timed full self_play_v1_gpu iteration; reported next to the tree-search headline (N = 1 only)
@@ -728,7 +864,6 @@ def run_selfplay(args, world, rank, local_rank):
                                     device=str(dev), add_dirichlet_noise=True, concurrent_games=games,
                                     search_backend="root")
 
-        del stepper
         torch.cuda.empty_cache()
         root_iteration(SEED)
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -741,39 +876,13 @@ def run_selfplay(args, world, rank, local_rank):
                      "what": "one full self_play_v1_gpu iteration, search_backend=root (reference production path), "
                              "same games / sims / net; see bench.py --search root"}
 
-    # the public entry end to end in tree mode: ONE full self_play_v1_gpu(search_backend="tree") iteration -- all games
-    # from the initial position to their end (wave semantics: no refill, so the last plies run with few live games),
-    # trajectory finalisation, and the finished TensorSelfPlayBatch copied to pinned host memory (N = 1 only)
-    full_line = None
-    if world == 1 and args.full_iteration:
-        from liuzhou_b200.self_play import self_play_v1_gpu
-
-        try:
-            del stepper
-        except NameError:
-            pass
+    # the v1 REFERENCE itself on this GPU (its python + its v0_core CUDA + its PyTorch network), same games / sims:
+    # the denominator of north_star's ">= 100x the v1 reference per GPU" (N = 1 only; own process, after ours has finished)
+    ref_gpu = None
+    if world == 1 and args.ref_gpu:
         torch.cuda.empty_cache()
-        torch.manual_seed(SEED + 2)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        fb, fs = self_play_v1_gpu(net, num_games=games, mcts_simulations=sims, temperature_init=1.0,
-                                  temperature_final=0.1, temperature_threshold=10, exploration_weight=1.0,
-                                  device=str(dev), add_dirichlet_noise=True, concurrent_games=games,
-                                  search_backend="tree", leaves_per_wave=k, tree_reuse=bool(args.tree_reuse))
-        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in
-                (fb.state_tensors, fb.legal_masks, fb.policy_targets, fb.value_targets, fb.soft_value_targets)]
-        for dst, src in zip(host, (fb.state_tensors, fb.legal_masks, fb.policy_targets, fb.value_targets,
-                                   fb.soft_value_targets)):
-            dst.copy_(src, non_blocking=True)
-        torch.cuda.synchronize()
-        sec = time.perf_counter() - t0
-        full_line = {"value": fb.num_samples / sec, "unit": "positions/s", "positions": fb.num_samples, "seconds": sec,
-                     "d2h_bytes": int(sum(h.numel() * h.element_size() for h in host)),
-                     "avg_game_length": fs.avg_game_length, "black_wins": fs.black_wins, "white_wins": fs.white_wins,
-                     "draws": fs.draws,
-                     "what": "one full self_play_v1_gpu(search_backend='tree') iteration, wall clock incl. CUDA-graph "
-                             "capture, trajectory finalisation and the D2H copy of the finished batch to pinned memory"}
-        del fb
+        ref_gpu = reference_gpu_line(games, sims, local_rank)
+    legacy = legacy_cpu_line() if (world == 1 and rank == 0 and args.legacy_cpu) else None
 
     if rank != 0:
         return None
@@ -783,7 +892,8 @@ def run_selfplay(args, world, rank, local_rank):
         "metric": "selfplay_positions_per_sec", "value": value, "unit": "positions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
         "ms_per_step_by_rank": [m / args.steps for m in rank_ms],
-        "root_puct_backend": root_line, "tree_backend_full_iteration": full_line,
+        "root_puct_backend": root_line, "tree_backend_full_iteration": full_line, "reference_gpu": ref_gpu,
+        "config1_legacy_cpu": legacy,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "mcts_sims_per_sec": value * sims, "network_evals_per_sec": evals * world / (elapsed_ms / 1e3),
         "config": {"workload": "v1 wave-batched MCTS self-play (BASELINE configs[2])", "games_per_gpu": games,
@@ -795,9 +905,21 @@ def run_selfplay(args, world, rank, local_rank):
                    "convolutions per forward are our tcgen05 kernel, no cuDNN on the path",
                    "step": "one ply of every game; finished games refilled; batch pre-diversified by 0..120 random plies",
                    "dirichlet_noise": True, "temperature": "1.0 -> 0.1 at ply 10", "exploration_weight": 1.0,
-                   "l2": "working set per step (node arena > 1 GB) exceeds the 126 MB L2"},
+                   "l2": "working set per step (node arena > 1 GB) exceeds the 126 MB L2",
+                   "comparisons": {
+                       "public_entry_full_iteration_positions_per_sec": e2e_value,
+                       "public_entry_vs_stepper": e2e_value / value if value else None,
+                       "ours_root_puct_backend_positions_per_sec": None if not root_line else root_line["value"],
+                       "reference_gpu_root_puct_positions_per_sec": None if not ref_gpu else ref_gpu.get("value"),
+                       "ours_root_vs_reference_gpu": (root_line["value"] / ref_gpu["value"])
+                       if (root_line and ref_gpu and ref_gpu.get("value")) else None,
+                       "ours_tree_sims_per_sec_vs_reference_gpu_sims_per_sec": (value / ref_gpu["value"])
+                       if (ref_gpu and ref_gpu.get("value")) else None,
+                       "config1_legacy_cpu_positions_per_sec": None if not legacy else legacy.get("value")}},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "positions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": "positions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": 1, "step": "one full self_play_v1_gpu(search_backend='tree') iteration per rank (public entry): "
+                                    f"{int(e2e_positions)} positions in {e2e_elapsed:.2f} s", "detail": full_line},
         "gpu_launches": int(launches),
         # dominant kernel: our tcgen05 implicit-GEMM convolution (20 of the 22 launches per forward are this 3x3
         # 128->128 instance); achieved = algorithmic FLOPs of one launch / its CUDA-event duration in a graph replay
@@ -813,9 +935,9 @@ def run_selfplay(args, world, rank, local_rank):
                      "kernel_ms": conv["ms"], "kernel_ms_conv1_epilogue": conv["ms_conv1"],
                      "kernel_ms_conv2_epilogue": conv["ms_conv2"], "units_per_launch": slots,
                      "flops_per_unit": conv["flops_per_state"], "launches_per_forward": 20,
-                     "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r01_conv_tc_ncu_full.csv",
+                     "traffic_source": f"ncu --set full dram__bytes_read+write per launch, {conv['traffic_source']}",
                      "forward_ms": fwd_ms, "forward_tflops": tflops, "forward_frac_of_peak": tflops / peak,
-                     "wave_ms": wave_ms, "tree_kernels_ms_per_wave": max(0.0, wave_ms - fwd_ms),
+                     "wave_ms": wave_ms,
                      "share_of_step": 20 * conv["ms_in_chain"] * (waves + 1) / (elapsed_ms / args.steps)},
         "tree": tree_stats,
         "tree_roofline": tree_roof,
@@ -885,6 +1007,11 @@ def run_selfplay_root(args, world, rank, local_rank):
     e2e_s = time.perf_counter() - t0
     e2e_value = sum_over_ranks(float(host.num_samples), world) / max_over_ranks(e2e_s, world)
     conv = time_trunk_conv(net, 4096, stream)
+    ref_gpu = None
+    if world == 1 and args.ref_gpu:
+        del net
+        torch.cuda.empty_cache()
+        ref_gpu = reference_gpu_line(games, sims, local_rank)
     if rank != 0:
         return None
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
@@ -902,7 +1029,13 @@ def run_selfplay_root(args, world, rank, local_rank):
                    "temperature": "1.0 -> 0.1 at ply 10",
                    "l2": "activations of a child batch (>= 100 MB per tensor) exceed the 126 MB L2",
                    "published_reference": "4,995.8 positions/s on 1 x H20 at sims=1024, 64 concurrent games "
-                                          "(v1/Design.md:1528; other hardware / config, so vs_baseline stays null)"},
+                                          "(v1/Design.md:1528; other hardware / config, so vs_baseline stays null)",
+                   "comparisons": {
+                       "reference_gpu_root_puct_positions_per_sec": None if not ref_gpu else ref_gpu.get("value"),
+                       "ours_vs_reference_gpu": (value / ref_gpu["value"]) if (ref_gpu and ref_gpu.get("value")) else None,
+                       "ours_e2e_vs_reference_gpu_e2e": (e2e_value / ref_gpu["e2e"]["value"])
+                       if (ref_gpu and ref_gpu.get("value")) else None}},
+        "reference_gpu": ref_gpu,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "positions/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": int(host.nbytes())},
@@ -922,23 +1055,123 @@ def run_selfplay_root(args, world, rank, local_rank):
     }
 
 
+def run_config4(args, world, rank, local_rank):
+    """BASELINE configs[3]: self-play sharded by game over the GPUs of one box -- 4,096 games per GPU (32,768 on 8) x 800
+    sims/move through `liuzhou_b200.dist.self_play_sharded`: NCCL weight broadcast from rank 0, per-rank seeds
+    (iteration_seed * 10007 + (rank + 1) * 9973), one full `self_play_v1_gpu(search_backend="tree")` iteration per rank,
+    the compact trajectory gather to rank 0 and the stats all-reduce -- ALL inside the timed region (one step = one
+    training iteration's self-play stage, v1/train.py:129-135,932-1171).  e2e adds the D2H copy of the merged batch."""
+    import torch
+
+    from liuzhou_b200 import _lib
+    from liuzhou_b200 import dist as lzdist
+
+    dev = torch.device("cuda", local_rank)
+    games, sims = args.games, args.sims
+    total = games * world
+    model = _default_model()
+    kw = dict(mcts_simulations=sims, temperature_init=1.0, temperature_final=0.1, temperature_threshold=10,
+              exploration_weight=1.0, add_dirichlet_noise=True, soft_value_k=2.0, max_game_plies=512,
+              sample_moves=True, concurrent_games=games, search_backend="tree")
+    # warm-up: CUDA context, NCCL communicator, allocator (a tiny sharded iteration)
+    lzdist.self_play_sharded(_default_model(), 64 * world, iteration_seed=1, device=dev,
+                             **{**kw, "mcts_simulations": 8, "concurrent_games": 64})
+    barrier_sync(world)
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    timings: dict = {}
+    merged, summary = lzdist.self_play_sharded(model, total, iteration_seed=SEED, device=dev, timings=timings, **kw)
+    torch.cuda.synchronize()
+    t_dev = time.perf_counter() - t0
+    d2h = 0
+    if merged is not None:
+        fields = (merged.state_tensors, merged.legal_masks, merged.policy_targets, merged.value_targets,
+                  merged.soft_value_targets)
+        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in fields]
+        for dst, src in zip(host, fields):
+            dst.copy_(src, non_blocking=True)
+        d2h = int(sum(h.numel() * h.element_size() for h in host))
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier_sync(world)
+    clocks = sampler.stop() if rank == 0 else {}
+    play_ms = all_ranks(timings["self_play_s"] * 1e3, world)
+    elapsed = max_over_ranks(t_dev, world)
+    e2e_elapsed = max_over_ranks(t_e2e, world)
+    handoff_ms = max_over_ranks(timings["handoff_s"] * 1e3, world)
+    bcast_ms = max_over_ranks(timings["broadcast_s"] * 1e3, world)
+    launches = _lib.launch_count() - launches0
+    if rank != 0:
+        return None
+    tot = [summary["num_games"], summary["num_positions"], summary["black_wins"], summary["white_wins"], summary["draws"]]
+    positions = tot[1]
+    value = positions / elapsed
+    h2d = int(sum(t.numel() * t.element_size() for t in list(model.parameters()) + list(model.buffers())))
+    return {
+        "metric": "selfplay_positions_per_sec", "value": value, "unit": "positions/s", "n_gpus": world, "steps": 1,
+        "warmup": 1, "ms_per_step": elapsed * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "mcts_sims_per_sec": value * sims,
+        "config": {"workload": "self-play sharded by game with NCCL weight broadcast + trajectory gather (BASELINE "
+                               "configs[3])", "games_total": total, "games_per_gpu": games, "sims_per_move": sims,
+                   "search": "full tree on device", "step": "one training iteration's self-play stage, end to end",
+                   "net": "ChessNet 128ch x 10 blocks, random init, seed 20260314",
+                   "l2": "working set per step (node arena > 1 GB) exceeds the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": positions / e2e_elapsed, "unit": "positions/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "iteration": {"positions": int(positions), "games": int(tot[0]), "black_wins": int(tot[2]),
+                      "white_wins": int(tot[3]), "draws": int(tot[4]), "seconds": elapsed,
+                      "self_play_ms_by_rank": play_ms, "weight_broadcast_ms": bcast_ms,
+                      "handoff_ms (compact gather + stats all-reduce)": handoff_ms,
+                      "merged_positions_on_rank0": None if merged is None else int(merged.num_samples)},
+    }
+
+
 def run_reference_selfplay(args):
-    per_step = max(5.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
-    vals, last = [], None
-    for it in range(args.warmup + args.steps):
-        last = cpu_selfplay_baseline(budget_s=per_step, sims=args.sims)
-        if it >= args.warmup:
-            vals.append(last["value"])
-    value = sum(vals) / len(vals)
-    last["value"] = value
+    """--impl reference: the reference's CPU implementation of the path on all host cores, ONE continuous session (no
+    restarts between steps); a step = one move of every game of the session, its duration is measured.  The session is
+    a bounded sample of the workload: `--ref-trees` concurrent games (default 256, so the CPU network sees batches of
+    256), shrunk once -- before the timed region -- if the first ply shows that K + W plies would not fit ~4 minutes."""
+    trees = int(args.ref_trees)
+    sess = CpuSelfPlaySession(trees=trees, sims=args.sims)
+    t0 = time.perf_counter()
+    sess.ply()
+    first = time.perf_counter() - t0
+    plies_needed = args.warmup + args.steps
+    budget = float(args.ref_budget)
+    if first * plies_needed > budget and trees > 32:
+        trees = max(32, int(trees * budget / (first * plies_needed)) // 32 * 32)
+        sess = CpuSelfPlaySession(trees=trees, sims=args.sims)
+        sess.ply()
+    for _ in range(max(0, args.warmup - 1)):
+        sess.ply()
+    p0, e0 = sess.positions, sess.evals
+    step_s = []
+    for _ in range(args.steps):
+        t = time.perf_counter()
+        sess.ply()
+        step_s.append(time.perf_counter() - t)
+    dt = sum(step_s)
+    positions = sess.positions - p0
+    value = positions / dt
+    cpu = {"value": value, "unit": "positions/s", "cores": sess.cores, "kind": sess.kind,
+           "sims_per_sec": value * args.sims, "network_evals_per_sec": (sess.evals - e0) / dt,
+           "sample": f"{trees} games x {args.sims} sims/move, {args.steps} timed plies = {positions} positions in "
+                     f"{dt:.1f}s after {args.warmup} warm-up plies, one continuous session; {sess.describe()}"}
     return {
         "impl": "reference", "metric": "selfplay_positions_per_sec", "value": value, "unit": "positions/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "mcts_sims_per_sec": value * args.sims,
         "config": {"workload": "v1 wave-batched MCTS self-play (BASELINE configs[2])", "sims_per_move": args.sims,
-                   "search": "reference CPU tree (portable C++) + fp32 network on host cores"},
-        "cpu_baseline": last,
+                   "games": trees, "same_config": False,
+                   "search": "reference CPU tree (portable C++) + fp32 network on host cores",
+                   "step": "one move of every game of one continuous session (measured, not a fixed budget)"},
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -1009,16 +1242,19 @@ def main() -> int:
                     help="1: the played child's subtree is kept between moves (advance_roots, as the reference's "
                          "portable self-play does); 0: every search starts from a bare root")
     ap.add_argument("--no-root-line", action="store_true", help="skip the extra root-PUCT iteration in the default line")
-    ap.add_argument("--full-iteration", type=int, default=1,
-                    help="1: also time one full self_play_v1_gpu(search_backend='tree') iteration end to end (~30-40 s)")
     ap.add_argument("--search", choices=["tree", "root"], default="tree",
                     help="tree: device-resident full tree (north_star, default); root: the reference's root-PUCT backend")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--ref-trees", type=int, default=256, help="--impl reference: concurrent games of the CPU session")
+    ap.add_argument("--ref-budget", type=float, default=240.0, help="--impl reference: target wall time of the whole run (s)")
+    ap.add_argument("--ref-gpu", type=int, default=1,
+                    help="1: also time the UNMODIFIED v1 reference (its python + its v0_core CUDA) on the same GPU (N = 1)")
+    ap.add_argument("--legacy-cpu", type=int, default=1, help="1: also time BASELINE configs[0] (legacy src/ self-play, CPU)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["playout", "selfplay", "eval"], default="selfplay")
+    ap.add_argument("--workload", choices=["playout", "selfplay", "eval", "config4"], default="selfplay")
     ap.add_argument("--eval-games", type=int, default=2000)
     ap.add_argument("--eval-sims", type=int, default=64)
     ap.add_argument("--eval-rr-games", type=int, default=256)
@@ -1033,8 +1269,10 @@ def main() -> int:
         return 0
 
     world, rank, local_rank = dist_setup(args.gpus)
+    if args.workload == "config4" and args.sims == SELFPLAY_SIMS:
+        args.sims = 800
     fn = {"selfplay": run_selfplay_root if args.search == "root" else run_selfplay, "playout": run_playout,
-          "eval": run_eval}[args.workload]
+          "eval": run_eval, "config4": run_config4}[args.workload]
     line = fn(args, world, rank, local_rank)
     if rank == 0:
         print(json.dumps(line), flush=True)

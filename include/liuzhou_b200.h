@@ -204,7 +204,7 @@ LZB_API int lzb_playout_run(uint64_t *packed, int32_t *plies, int8_t *result, ui
  *   visit i32 | value_sum f64 | prior f64 | info u32 (action:8 | nchild:8 | flags) | first_child i32 |
  *   parent i32 | state u64[4] | root_value f64[num_trees] | counters i32[8] = {top, sticky flags
  *   (see lzb_tree_advance_roots), expansions, terminal hits, sibling records scanned by select, levels descended,
- *   2 x reserved}.
+ *   arena index of the first failed allocation (INT32_MAX if none: nodes above it were never written), reserved}.
  * One warp per tree; K leaves per tree per wave (K = 1 reproduces the reference exactly).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -219,6 +219,12 @@ typedef struct {
     int32_t *counters;
     int64_t capacity;
     int64_t num_trees;
+    /* optional i32[num_trees] (NULL = identity): leaf-batch row of tree t in the simulation waves (slots
+     * tree_rows[t]*K .. +K-1 of leaf_node / leaf_status / leaf_states / leaf_path / inputs / priors / values);
+     * tree_rows[t] < 0 = the tree sits this wave out (a finished game).  The live trees' leaves then form a dense prefix
+     * of the batch, so the network runs on ceil64(live) rows instead of num_trees.  prepare_roots and the root expansion
+     * (do_backup = 0) always use row t. */
+    const int32_t *tree_rows;
 } lzb_tree;
 
 /* Reset the arena to `num_trees` unexpanded roots (PortableTreeBatch ctor, :443-459). active u8[T] or NULL. */
@@ -249,7 +255,8 @@ LZB_API int lzb_tree_prepare_roots(const lzb_tree *tree, int32_t *leaf_node, int
  * capacity >= the nodes kept) by node-parallel passes and copied back, so the arena holds no dead nodes afterwards.
  * work: i32[num_trees + capacity] temporary (new root per tree, children-block remap per old node).
  * Sticky flags in counters[1]: 1 arena/scratch exhausted (the node is kept as an unexpanded leaf), 2 action is not a
- * child of the root (the reference throws). */
+ * child of the root (the reference throws), 4 a network value was NaN/Inf or a legal prior negative/NaN/Inf (the
+ * reference throws in CompletePending / Expand; here the leaf stays unexpanded and nothing is backed up). */
 LZB_API int lzb_tree_advance_roots(const lzb_tree *tree, const lzb_tree *scratch, const int32_t *actions,
                                    const uint64_t *reset_states, const uint8_t *reset_mask, int32_t *work, void *stream);
 /* complete_pending (:554-590): expand every status-0 leaf with dense priors f32[T*K,220] / values f32[T*K],

@@ -441,16 +441,21 @@ int launch_conv(const void* x, const void* w, const ConvParams& P, cudaStream_t 
     }
     constexpr size_t smem = 1024 + (size_t)kStages * KCH * (kChunkBytes + kWSlotBytes) +
                             8 * (2 * kStages + 2 * kAccStages) + 32 + 3 * kCout * sizeof(float) + 8 * 32 * 128;
-    static bool configured = false;
-    if (!configured) {
+    // the dynamic shared memory opt-in and the SM count are per DEVICE (a process may drive several GPUs)
+    static int sm_count[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("lzb_conv: bad current device"); return LZB_ERR_CUDA; }
+    if (sm_count[dev] == 0) {
         if (cudaFuncSetAttribute(conv_tc_kernel<TAPS, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             set_error("lzb_conv: cannot raise dynamic shared memory to %zu", smem);
             return LZB_ERR_CUDA;
         }
-        configured = true;
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 2) n = kNumSMs;
+        sm_count[dev] = n;
     }
     const int64_t pair_tiles = P.rows / (2 * kTileM);
-    const int clusters = (int)(pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2);
+    const int clusters = (int)(pair_tiles < sm_count[dev] / 2 ? pair_tiles : sm_count[dev] / 2);
     static const bool pdl = !(getenv("LZB_CONV_PDL") && atoi(getenv("LZB_CONV_PDL")) == 0);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);

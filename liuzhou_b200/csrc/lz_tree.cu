@@ -25,6 +25,7 @@ using namespace lz;
 namespace lzb {
 namespace {
 
+constexpr int32_t kFlagArena = 1, kFlagIllegalAdvance = 2, kFlagBadNetwork = 4;   // sticky bits of counters[1]
 constexpr uint32_t kInfoActionMask = 0xFFu;
 constexpr uint32_t kInfoTerminal = 1u << 16;
 constexpr uint32_t kInfoExpanded = 1u << 17;
@@ -71,6 +72,7 @@ tree_init_kernel(lzb_tree A, const uint64_t* __restrict__ roots, const uint8_t* 
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         A.counters[0] = (int32_t)T; A.counters[1] = 0; A.counters[2] = 0; A.counters[3] = 0;
         A.counters[4] = 0; A.counters[5] = 0;      // [4] sibling records scanned by select, [5] levels descended
+        A.counters[6] = 0x7fffffff;                // [6] arena index of the FIRST failed allocation (nothing above it is valid)
     }
 }
 
@@ -150,8 +152,16 @@ __device__ __forceinline__ void select_tree(const lzb_tree& A, int64_t t, int K,
                                             uint64_t* __restrict__ leaf_states, int32_t* __restrict__ leaf_path,
                                             int roots_only, uint4* __restrict__ enc_out, int lane) {
     {
+        // leaf-batch rows of this tree: identity, or (waves only) the compacted row A.tree_rows[t]; a negative row
+        // means the tree takes no part in this wave (finished game): nothing is read or written for it
+        int64_t base = t;
+        if (A.tree_rows && !roots_only) {
+            const int r = A.tree_rows[t];
+            if (r < 0) return;
+            base = r;
+        }
         for (int k = 0; k < K; ++k) {
-            const int64_t slot = t * K + k;
+            const int64_t slot = base * K + k;
             int node = (int)t;
             uint32_t inf = A.info[node];
             // SelectLeaves :519-521; PrepareRoots (:483-513) only ever evaluates an unexpanded root -- a root that
@@ -277,8 +287,14 @@ __device__ __forceinline__ void expand_tree(const lzb_tree& A, int64_t t, int K,
                                             const float* __restrict__ values, int do_backup, double vl,
                                             const int32_t* __restrict__ leaf_path, float* spri, int lane) {
     {
+        int64_t base = t;
+        if (A.tree_rows && do_backup) {           // waves use the compacted rows; the root step (no backup) never does
+            const int r = A.tree_rows[t];
+            if (r < 0) return;
+            base = r;
+        }
         for (int k = 0; k < K; ++k) {
-            const int64_t slot = t * K + k;
+            const int64_t slot = base * K + k;
             if (leaf_status[slot] != kLeafEval) continue;
             const int node = leaf_node[slot];
             // the descent's path (for the one-round-trip backup): fetched up front, used at the end
@@ -298,6 +314,24 @@ __device__ __forceinline__ void expand_tree(const lzb_tree& A, int64_t t, int K,
             const uint32_t inf = A.info[node] & ~kInfoPending;
             if (lane == 0 && K > 1 && vl > 0.0) virtual_loss_path(A, node, vl, -1);
             __syncwarp();
+            // CompletePending / Expand throw on a non-finite value or a negative / non-finite prior
+            // (portable_mcts.cpp: "model value is NaN or Inf", "model prior is negative, NaN, or Inf"); here: sticky
+            // flag, the leaf stays unexpanded and nothing is backed up, so the tree statistics stay clean
+            bool bad = !isfinite(value);
+            if (n > 0) {                          // the prior row is staged in shared memory once, checked, then used
+                for (int a = lane; a < kActionDim; a += 32) {
+                    const float pv = priors[slot * kActionDim + a];
+                    spri[a] = pv;
+                    if (legal_test(L, a) && (!(pv >= 0.0f) || isinf(pv))) bad = true;
+                }
+            }
+            __syncwarp();                         // staging writes visible to lane 0's sequential sum below
+            bad = __any_sync(0xffffffffu, bad);
+            if (bad) {
+                if (lane == 0) { A.info[node] = inf; atomicOr(&A.counters[1], kFlagBadNetwork); }
+                __syncwarp();
+                continue;
+            }
             if (n == 0) {                                             // :900-907
                 const bool over = game_over(s);
                 value = over ? terminal_value(s) : -1.0;
@@ -306,9 +340,6 @@ __device__ __forceinline__ void expand_tree(const lzb_tree& A, int64_t t, int K,
                     if (node < A.num_trees) A.root_value[node] = value;
                 }
             } else {
-                __syncwarp();
-                for (int a = lane; a < kActionDim; a += 32) spri[a] = priors[slot * kActionDim + a];
-                __syncwarp();
                 // prior_sum accumulated sequentially in ascending action order, in fp64 (:909-918)
                 double prior_sum = 0.0;
                 int fc = 0;
@@ -324,7 +355,9 @@ __device__ __forceinline__ void expand_tree(const lzb_tree& A, int64_t t, int K,
                     for (uint64_t m = L.sel; m; m &= m - 1) prior_sum = __dadd_rn(prior_sum, (double)spri[180 + ctz64(m)]);
                     if (L.process) prior_sum = __dadd_rn(prior_sum, (double)spri[216]);
                     fc = atomicAdd(&A.counters[0], n);
-                    if ((int64_t)fc + n > A.capacity) { atomicOr(&A.counters[1], 1); fc = -1; }
+                    // the bump pointer only grows: after the first failure every later allocation fails too, so
+                    // [num_trees, first failed index) is exactly the set of valid nodes (advance_roots relies on it)
+                    if ((int64_t)fc + n > A.capacity) { atomicOr(&A.counters[1], 1); atomicMin(&A.counters[6], fc); fc = -1; }
                     else atomicAdd(&A.counters[2], 1);
                 }
                 prior_sum = __shfl_sync(0xffffffffu, prior_sum, 0);
@@ -409,13 +442,13 @@ tree_expand_select_kernel(lzb_tree A, int K, int32_t* __restrict__ leaf_node, in
 //   reset_mask[t]               : the tree is replaced by a fresh unexpanded root for reset_states[t] (a new game)
 //   action not among the root's children : counters[1] |= 2 (the reference throws), tree kept
 //   scratch exhausted           : counters[1] |= 1, the affected node is kept as an unexpanded leaf
-constexpr int32_t kFlagArena = 1, kFlagIllegalAdvance = 2;
 
 __global__ void tree_advance_begin_kernel(lzb_tree A, lzb_tree B) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         B.counters[0] = (int32_t)A.num_trees; B.counters[1] = A.counters[1];
         B.counters[2] = A.counters[2]; B.counters[3] = A.counters[3];
         B.counters[4] = A.counters[4]; B.counters[5] = A.counters[5];
+        B.counters[6] = 0x7fffffff;
     }
 }
 
@@ -481,6 +514,11 @@ tree_advance_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ actions,
 //   remap[i] = -2 dropped | -1 kept, no children block | >= 0 first index of its children block in the new arena.
 constexpr int kDropped = -2, kNoBlock = -1;
 
+// nodes [0, valid_top) have been written: the bump pointer, cut at the first failed allocation and the capacity
+__device__ __forceinline__ int64_t valid_top(const lzb_tree& A) {
+    return min(min((int64_t)A.counters[0], (int64_t)A.counters[6]), A.capacity);
+}
+
 __device__ __forceinline__ bool node_kept(const lzb_tree& A, const int32_t* __restrict__ src_root, int i, int& tree_out) {
     const int T = (int)A.num_trees;
     int x = i, p = A.parent[x];
@@ -492,7 +530,7 @@ __device__ __forceinline__ bool node_kept(const lzb_tree& A, const int32_t* __re
 
 __global__ void __launch_bounds__(256)
 tree_advance_mark_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ src_root, int32_t* __restrict__ remap) {
-    const int64_t top = min((int64_t)A.counters[0], A.capacity);
+    const int64_t top = valid_top(A);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int T = (int)A.num_trees;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < top; i += stride) {
@@ -506,7 +544,7 @@ tree_advance_mark_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ src
             r = kNoBlock;
             if (n > 0) {
                 const int fc = atomicAdd(&B.counters[0], n);
-                if ((int64_t)fc + n > B.capacity) atomicOr(&B.counters[1], kFlagArena);   // node stays a leaf
+                if ((int64_t)fc + n > B.capacity) { atomicOr(&B.counters[1], kFlagArena); atomicMin(&B.counters[6], fc); }   // stays a leaf
                 else r = fc;
             }
         }
@@ -518,7 +556,7 @@ tree_advance_mark_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ src
 // with its parent's and its children's new indices; the node that becomes the root only hands its block to slot t.
 __global__ void __launch_bounds__(256)
 tree_advance_copy_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ src_root, const int32_t* __restrict__ remap) {
-    const int64_t top = min((int64_t)A.counters[0], A.capacity);
+    const int64_t top = valid_top(A);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int T = (int)A.num_trees;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < top; i += stride) {
@@ -557,7 +595,7 @@ tree_advance_copy_kernel(lzb_tree A, lzb_tree B, const int32_t* __restrict__ src
 // scratch prefix [0, counters[0]) -> arena (the scratch never holds more nodes than the arena did)
 __global__ void __launch_bounds__(256)
 tree_copy_back_kernel(lzb_tree B, lzb_tree A) {
-    const int64_t n = min((int64_t)B.counters[0], min(A.capacity, B.capacity));
+    const int64_t n = min(valid_top(B), A.capacity);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t i = tid; i < n; i += stride) {
@@ -568,7 +606,7 @@ tree_copy_back_kernel(lzb_tree B, lzb_tree A) {
     ulonglong2* as = reinterpret_cast<ulonglong2*>(A.state);
     for (int64_t i = tid; i < 2 * n; i += stride) as[i] = bs[i];
     for (int64_t i = tid; i < A.num_trees; i += stride) A.root_value[i] = B.root_value[i];
-    if (tid < 6) A.counters[tid] = tid == 0 ? (int32_t)n : B.counters[tid];
+    if (tid < 7) A.counters[tid] = tid == 0 ? (int32_t)n : tid == 6 ? 0x7fffffff : B.counters[tid];
 }
 
 // RootOutputs (portable_mcts.cpp:664-737) + RootPriors (:592-624)

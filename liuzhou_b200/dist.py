@@ -162,16 +162,30 @@ def all_reduce_stats(values: List[float], device=None, group=None) -> List[float
 
 
 def self_play_sharded(model, total_games: int, *, iteration_seed: int, device, group=None, compact_gather: bool = True,
-                      **self_play_kwargs):
+                      timings: Optional[dict] = None, **self_play_kwargs):
     """Config-4 style entry: every rank plays its share of `total_games` (split_games) with the per-rank seed
     rule, weights come from rank 0, trajectories and statistics return to rank 0.
-    Returns (merged TensorSelfPlayBatch or None, summed stats dict)."""
+    Returns (merged TensorSelfPlayBatch or None, summed stats dict).  ``timings`` (optional dict) receives this rank's
+    wall-clock seconds of the three stages (broadcast_s, self_play_s, handoff_s), each closed by a device synchronise."""
+    import time
+
     from .self_play import self_play_v1_gpu
+
+    def mark(key, t_prev):
+        if timings is None:
+            return t_prev
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize(device)
+        now = time.perf_counter()
+        timings[key] = now - t_prev
+        return now
 
     world, rank = _world(group), _rank(group)
     games = split_games(total_games, world)[rank]
+    t_mark = time.perf_counter()
     model = model.to(device)
     broadcast_model(model, src=0, group=group)
+    t_mark = mark("broadcast_s", t_mark)
     torch.manual_seed(rank_seed(iteration_seed, rank))
     if games > 0:
         batch, stats = self_play_v1_gpu(model, num_games=games, device=str(device), **self_play_kwargs)
@@ -183,8 +197,10 @@ def self_play_sharded(model, total_games: int, *, iteration_seed: int, device, g
                                     torch.empty((0, 220), device=dev), torch.empty((0,), device=dev),
                                     torch.empty((0,), device=dev))
         vec = [0.0] * 7
+    t_mark = mark("self_play_s", t_mark)
     merged = (gather_trajectories_compact if compact_gather else gather_trajectories)(batch, dst=0, group=group)
     tot = all_reduce_stats(vec, device=device, group=group)
+    mark("handoff_s", t_mark)
     summary = {"num_games": tot[0], "num_positions": tot[1], "black_wins": tot[2], "white_wins": tot[3],
                "draws": tot[4], "avg_game_length": tot[5] / max(1.0, tot[0]), "sum_elapsed_sec": tot[6]}
     return merged, summary

@@ -223,10 +223,12 @@ class FusedTrunk:
         self._t = {}
         self.use_cudnn_fused = True
         # our tcgen05 implicit-GEMM conv covers the 128-channel trunk; other widths keep the cuDNN path
-        self.use_tc = (model.stem_conv.out_channels == 128 and model.stem_conv.weight.dtype == torch.bfloat16
+        self.use_tc = (model.stem_conv.out_channels == 128 and model.stem_conv.in_channels <= 64 and len(model.blocks) > 0
+                       and model.stem_conv.weight.dtype == torch.bfloat16
                        and os.environ.get("LZB_DISABLE_TC_CONV", "0") != "1")
         self.refresh()
-        self._probe()
+        if not self.use_tc:
+            self._probe()
 
     def _set(self, name: str, value: torch.Tensor) -> None:
         if name in self._t:
@@ -308,11 +310,13 @@ class FusedTrunk:
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         m, t = self.model, self._t
         nb = len(m.blocks)
-        if x.size(1) == 64 and m.stem_conv.in_channels != 64:
-            # channel-padded input (InferenceNet.new_input on the tcgen05 path): stem conv + stem_bn + ReLU and the
-            # first block's bn1 + ReLU in ONE launch (x0 and a0 are the two outputs of the epilogue)
-            if not (self.use_tc and "stem_wp" in t and nb > 0 and x.size(0) % 64 == 0):
-                raise RuntimeError("64-channel padded inputs need the tcgen05 conv path (128-channel trunk, batch % 64 == 0)")
+        if self.use_tc:
+            # ONE convolution path for the 128-channel network: our tcgen05 kernel, on channel-padded inputs
+            # (InferenceNet.new_input) in whole 64-board tiles.  No library fallback: callers pad, or this raises.
+            if not (x.size(1) == 64 and "stem_wp" in t and nb > 0 and x.size(0) % 64 == 0):
+                raise RuntimeError("the tcgen05 network path takes bf16 [n,64,6,6] channel-padded inputs with n % 64 == 0 "
+                                   f"(got {tuple(x.shape)}); use InferenceNet.new_input / InferenceNet.forward, which pad")
+            # stem conv + stem_bn + ReLU and the first block's bn1 + ReLU in ONE launch (x0 and a0 = the two outputs)
             xr, a = conv_bf16(x, t["stem_wp"], bias=t["stem_bf"], relu1=True, scale=t["s1_0"], shift=t["t1_0"],
                               want_out2=True)
         else:
@@ -320,7 +324,7 @@ class FusedTrunk:
             if nb == 0:
                 return self._bn_relu(xr, None, t["trunk_s"], t["trunk_t"], False)[1]
             _, a = self._bn_relu(xr, None, t["s1_0"], t["t1_0"], False)                       # a0 = relu(bn1_0(x0))
-        if self.use_tc and x.size(0) % 64 == 0:
+        if self.use_tc:
             # 2 launches per residual block, no elementwise pass: the residual add, the next BatchNorm and the
             # ReLU are the epilogue of conv2; BatchNorm + ReLU after conv1 are folded weights + the epilogue of conv1
             for i in range(nb):
@@ -398,7 +402,9 @@ class FusedHeads:
         t = self._t
         n = a.size(0)
         dev = a.device
-        if self.use_tc and n % 64 == 0:
+        if self.use_tc:
+            if n % 64 != 0:
+                raise RuntimeError("the tcgen05 network path works on whole 64-board tiles (n % 64 == 0)")
             pv, _ = conv_bf16(a, t["conv_wp"], bias=t["conv_bias"], relu1=True)
         else:
             c = F.conv2d(a, t["conv_w"], None, 1, 0)
@@ -434,7 +440,12 @@ class InferenceNet:
     and returns fp32 (log_p1, log_p2, log_pmc, value_logits).  For batch sizes registered with ``capture``
     the forward is a graph replay on static buffers (returned tensors alias those buffers)."""
 
-    def __init__(self, model: ChessNet, device, dtype: torch.dtype = torch.bfloat16, fused: bool = True):
+    def __init__(self, model: ChessNet, device, dtype: torch.dtype = torch.bfloat16, fused: bool = True,
+                 allow_library_convs: bool = False):
+        """``allow_library_convs``: the product network path is our tcgen05 convolution kernel, which covers the
+        reference's default architecture (128-channel trunk, 64 + 64 head channels, bf16).  Any other ChessNet shape
+        (the tiny nets of unit tests, fp32 parity runs, ``fused=False``) can only run on PyTorch's library convolutions;
+        that is refused unless the caller opts in explicitly -- there is no silent dispatch between the two."""
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("InferenceNet needs a CUDA device")
@@ -449,7 +460,16 @@ class InferenceNet:
         self.heads = FusedHeads(self.model) if self.fused else None
         if self.heads is not None and not self.heads.supported:
             self.heads = None
+        if self.trunk is not None and self.trunk.use_tc and not (self.heads is not None and self.heads.use_tc):
+            self.trunk.use_tc = False            # the tcgen05 path is all or nothing (trunk and heads convolutions)
+            self.trunk._probe()
         self.flops_per_state = flops_per_state(self.model)
+        self.library_convs = not self._tc_ready()
+        if self.library_convs and not allow_library_convs:
+            raise RuntimeError(
+                "liuzhou_b200.InferenceNet: this ChessNet shape / dtype is not covered by the tcgen05 convolution kernel "
+                "(needs trunk_channels = 128, policy_channels + value_channels = 128, >= 1 block, bf16, fused=True); "
+                "pass allow_library_convs=True to run it on PyTorch's cuDNN convolutions instead (tests / parity only)")
         self._graphs: Dict[int, Tuple[torch.cuda.CUDAGraph, torch.Tensor, Tuple[torch.Tensor, ...]]] = {}
 
     @staticmethod
@@ -505,8 +525,10 @@ class InferenceNet:
         """Input buffer for ``encode_inputs(..., "bf16_nhwc", out=...)``: [n,11,6,6] channels-last, or -- when the
         whole network runs on our tcgen05 convs -- the same planes zero-padded to 64 channels ([n,64,6,6])."""
         c = self.model.num_input_channels
-        if (self.trunk is not None and self.trunk.use_tc and "stem_wp" in self.trunk._t and len(self.model.blocks) > 0
-                and n % 64 == 0):
+        if self._tc_ready():
+            if n % 64 != 0:
+                raise RuntimeError(f"the tcgen05 network path works on whole 64-board tiles: pad the batch ({n}) to a "
+                                   "multiple of 64")
             c = 64
         return torch.empty((n, c, 6, 6), dtype=self.dtype, device=self.device,
                            memory_format=torch.channels_last).zero_()
@@ -531,7 +553,7 @@ class InferenceNet:
 
     def _tc_ready(self) -> bool:
         return (self.trunk is not None and self.trunk.use_tc and "stem_wp" in self.trunk._t
-                and len(self.model.blocks) > 0 and self.heads is not None)
+                and len(self.model.blocks) > 0 and self.heads is not None and self.heads.use_tc)
 
     @torch.no_grad()
     def _forward_chunked(self, inputs: torch.Tensor, chunk: int = 16384):
@@ -563,8 +585,11 @@ class InferenceNet:
         n = inputs.size(0)
         entry = self._graphs.get(n)
         if entry is None:
-            if n > 0 and self._tc_ready() and inputs.size(1) == self.model.num_input_channels:
-                return self._forward_chunked(inputs.to(self.device))
+            if self._tc_ready():
+                if n > 0 and inputs.size(1) == self.model.num_input_channels:
+                    return self._forward_chunked(inputs.to(self.device))      # pads rows to 64 and channels to 64
+                x = inputs.to(device=self.device, dtype=self.dtype).contiguous(memory_format=torch.channels_last)
+                return self._forward_eager(x)                                 # already padded, or raises
             x = inputs.to(device=self.device, dtype=self.dtype).contiguous(memory_format=torch.channels_last)
             return self._forward_eager(x)
         g, x, outs = entry

@@ -203,6 +203,26 @@ class AsyncShardWriter:
         self._slots.acquire()
         s, e = int(start), int(end)
         staged, event = [], None
+        try:
+            self._stage_rows(samples, s, e, staged)
+            if self._cuda:
+                event = torch.cuda.Event()
+                event.record(self._stream)
+        except BaseException:
+            self._recycle(staged)             # staging failed (e.g. pinned allocation): give the slot back
+            self._slots.release()
+            raise
+        self._q.put((str(path), staged, e - s, event, dict(stats_payload), dict(metadata)))
+
+    def flush(self) -> None:
+        """Block until every submitted shard file is on disk (re-raises the first failure); the writer stays usable."""
+        done = threading.Event()
+        self._q.put(done)
+        done.wait()
+        if self._error is not None:
+            raise RuntimeError("AsyncShardWriter: shard write failed") from self._error
+
+    def _stage_rows(self, samples: TensorSelfPlayBatch, s: int, e: int, staged: list) -> None:
         if self._cuda:
             self._stream.wait_stream(torch.cuda.current_stream(self._dev))
             with torch.cuda.stream(self._stream):
@@ -212,21 +232,21 @@ class AsyncShardWriter:
                     buf[: e - s].copy_(src, non_blocking=True)
                     src.record_stream(self._stream)
                     staged.append(buf)
-                event = torch.cuda.Event()
-                event.record(self._stream)
         else:
             for f in _FIELDS:
                 src = getattr(samples, f)[s:e]
                 buf = self._stage(src)
                 buf[: e - s].copy_(src)
                 staged.append(buf)
-        self._q.put((str(path), staged, e - s, event, dict(stats_payload), dict(metadata)))
 
     def _run(self) -> None:
         while True:
             item = self._q.get()
             if item is None:
                 return
+            if isinstance(item, threading.Event):       # flush(): everything queued before it has been written
+                item.set()
+                continue
             path, staged, rows, event, stats_payload, metadata = item
             try:
                 if event is not None:
@@ -297,9 +317,13 @@ def save_self_play_payload_sharded(*, path: str, samples: TensorSelfPlayBatch, s
     finally:
         if own:
             w.close()
+    if not own:
+        w.flush()           # the manifest must not appear before the shard files it lists
+    tmp = f"{path}.tmp.{os.getpid()}"
     torch.save({"payload_format": "v1_sharded_manifest", "version": 1, "num_samples": n, "num_shards": len(names),
                 "shard_files": names, "shard_sizes": sizes, "chunk_target_bytes": int(chunk_target_bytes),
-                "avg_bytes_per_sample": int(bps), "stats": dict(stats_payload), "metadata": dict(metadata)}, path)
+                "avg_bytes_per_sample": int(bps), "stats": dict(stats_payload), "metadata": dict(metadata)}, tmp)
+    os.replace(tmp, path)
     return len(names)
 
 

@@ -175,6 +175,12 @@ def run_self_play_worker(
             model = ChessNet()
             model.load_state_dict(state, strict=True)
         model = model.to(dev).eval()
+        # ONE inference wrapper (BatchNorm folding, packed weights) and ONE set of search engines (tree arenas, CUDA
+        # graphs) per worker, reused by every group of games
+        from .net import InferenceNet
+
+        net = model if isinstance(model, InferenceNet) else InferenceNet(model, dev)
+        engines: Dict[Any, Any] = {}
 
         common_meta = {
             "worker_idx": int(worker_idx), "device": str(dev), "games": games_total, "games_per_chunk": group,
@@ -194,7 +200,7 @@ def run_self_play_worker(
             while left > 0:
                 n_games = min(group, left)
                 batch, stats = self_play_v1_gpu(
-                    model=model, num_games=n_games, mcts_simulations=int(mcts_simulations),
+                    model=net, num_games=n_games, mcts_simulations=int(mcts_simulations),
                     temperature_init=float(temperature_init), temperature_final=float(temperature_final),
                     temperature_threshold=int(temperature_threshold), exploration_weight=float(exploration_weight),
                     device=str(dev), add_dirichlet_noise=True, dirichlet_alpha=float(dirichlet_alpha),
@@ -204,7 +210,7 @@ def run_self_play_worker(
                     sparse_top_k=int(sparse_top_k), verbose=False,
                     search_backend="root" if backend == "cuda_root" else "tree", leaves_per_wave=int(leaves_per_wave),
                     policy_target_temperature=policy_target_temperature,
-                    policy_target_prior_pseudocount=float(policy_target_prior_pseudocount))
+                    policy_target_prior_pseudocount=float(policy_target_prior_pseudocount), engine_cache=engines)
                 stats_parts.append(stats)
                 summaries[0].append(summarize_scalar_targets(batch.value_targets))
                 summaries[1].append(summarize_scalar_targets(batch.soft_value_targets))
@@ -236,13 +242,20 @@ def run_self_play_worker(
             "mixed_value_target_summary": merge_target_summaries(summaries[2]), "metadata": manifest_meta,
         }
         os.makedirs(os.path.dirname(str(output_path)) or ".", exist_ok=True)
-        torch.save(manifest, str(output_path))
+        _atomic_save(manifest, str(output_path))      # after the writer has drained: every listed chunk file is on disk
         return {"worker_idx": int(worker_idx), "device": str(dev), "games": games_total, "output_path": str(output_path),
                 "num_samples": int(sum(sizes)), "saved_chunks": len(files)}
     except Exception as exc:
         raise RuntimeError("v1 self-play process worker failed: "
                            f"worker={int(worker_idx)}, device={str(shard_device)}, games={int(shard_games)}\n"
                            f"{traceback.format_exc()}") from exc
+
+
+def _atomic_save(obj, path: str) -> None:
+    """torch.save through a temporary file + os.replace: a trainer polling for the manifest never sees a partial file."""
+    tmp = f"{path}.tmp.{os.getpid()}"
+    torch.save(obj, tmp)
+    os.replace(tmp, path)
 
 
 def merge_worker_manifests(manifest_paths: Sequence[str], *, output_path: str, metadata_base: Dict[str, Any],
@@ -283,10 +296,10 @@ def merge_worker_manifests(manifest_paths: Sequence[str], *, output_path: str, m
                  "self_play_chunk_target_bytes": int(chunk_target_bytes), "value_target_summary": dict(v),
                  "soft_value_target_summary": dict(s), "mixed_value_target_summary": dict(m)})
     os.makedirs(os.path.dirname(str(output_path)) or ".", exist_ok=True)
-    torch.save({"payload_format": "v1_sharded_manifest", "version": 1, "num_samples": int(sum(sizes)),
-                "num_shards": len(files), "shard_files": list(files), "shard_sizes": list(sizes),
-                "chunk_target_bytes": int(chunk_target_bytes), "avg_bytes_per_sample": int(bps_num // max(1, bps_den)),
-                "stats": merged.to_dict(), "metadata": meta}, str(output_path))
+    _atomic_save({"payload_format": "v1_sharded_manifest", "version": 1, "num_samples": int(sum(sizes)),
+                  "num_shards": len(files), "shard_files": list(files), "shard_sizes": list(sizes),
+                  "chunk_target_bytes": int(chunk_target_bytes), "avg_bytes_per_sample": int(bps_num // max(1, bps_den)),
+                  "stats": merged.to_dict(), "metadata": meta}, str(output_path))
     return merged, v, s, m, len(files)
 
 
@@ -314,14 +327,25 @@ def run_self_play_iteration(model: torch.nn.Module, *, num_games: int, iteration
     model = model.to(dev)
     lzdist.broadcast_model(model, src=0, group=group)
     my_manifest = os.path.join(workspace, f"worker_manifest_{int(iteration_seed):06d}_{rank:02d}.pt")
+    failure: Optional[BaseException] = None
     if games[rank] > 0:
-        run_self_play_worker(worker_idx=rank, shard_device=str(dev), shard_games=games[rank],
-                             seed=lzdist.rank_seed(iteration_seed, rank), model_state_path=None, model=model,
-                             output_path=my_manifest, target_samples_per_shard=int(target_samples_per_shard),
-                             chunk_target_bytes=int(chunk_target_bytes), chunk_output_dir=out_dir,
-                             chunk_file_prefix=f"{stem}.w{rank:02d}", chunk_file_ext=ext, **worker_kwargs)
+        try:
+            run_self_play_worker(worker_idx=rank, shard_device=str(dev), shard_games=games[rank],
+                                 seed=lzdist.rank_seed(iteration_seed, rank), model_state_path=None, model=model,
+                                 output_path=my_manifest, target_samples_per_shard=int(target_samples_per_shard),
+                                 chunk_target_bytes=int(chunk_target_bytes), chunk_output_dir=out_dir,
+                                 chunk_file_prefix=f"{stem}.w{rank:02d}", chunk_file_ext=ext, **worker_kwargs)
+        except Exception as exc:  # noqa: BLE001  reported to every rank below instead of leaving them in the barrier
+            failure = exc
     if world > 1:
-        dist.barrier(group=group)
+        # a failed worker must not leave the other ranks waiting: the failure count is all-reduced (this IS the barrier)
+        failed = torch.tensor([1 if failure is not None else 0], dtype=torch.int32,
+                              device=dev if dist.get_backend(group) == "nccl" else "cpu")
+        dist.all_reduce(failed, op=dist.ReduceOp.SUM, group=group)
+        if int(failed.item()) > 0 and failure is None:
+            raise RuntimeError(f"self-play iteration aborted: {int(failed.item())} other rank(s) failed in their worker")
+    if failure is not None:
+        raise failure
     if rank != 0:
         return None
     manifests = [os.path.join(workspace, f"worker_manifest_{int(iteration_seed):06d}_{r:02d}.pt")

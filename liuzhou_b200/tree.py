@@ -22,11 +22,12 @@ LEAF_EVAL, LEAF_DONE, LEAF_DUPLICATE = 0, 1, 2
 class _TreeStruct(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("visit", "value_sum", "prior", "info", "first_child", "parent", "state",
                                                 "root_value", "counters")] + [("capacity", ctypes.c_int64),
-                                                                             ("num_trees", ctypes.c_int64)]
+                                                                             ("num_trees", ctypes.c_int64),
+                                                                             ("tree_rows", ctypes.c_void_p)]
 
 
 _ARENA_FIELDS = ("visit", "value_sum", "prior", "info", "first_child", "parent", "state", "root_value", "counters")
-FLAG_ARENA, FLAG_ILLEGAL_ADVANCE = 1, 2                      # sticky bits of counters[1]
+FLAG_ARENA, FLAG_ILLEGAL_ADVANCE, FLAG_BAD_NETWORK = 1, 2, 4  # sticky bits of counters[1]
 
 
 class DeviceTreeBatch:
@@ -63,7 +64,10 @@ class DeviceTreeBatch:
             self.counters = torch.zeros((8,), dtype=torch.int32, device=dev)
             self.leaf_node = torch.full((slots,), -1, dtype=torch.int32, device=dev)
             self.leaf_status = torch.full((slots,), LEAF_DONE, dtype=torch.int32, device=dev)
-            self.leaf_states = torch.zeros((slots, 4), dtype=torch.int64, device=dev)
+            # leaf states are allocated in whole 64-row tiles (the tcgen05 network path evaluates multiples of 64 rows;
+            # the rows past `slots` stay zero = an empty placement position, evaluated and ignored)
+            self.leaf_states_padded = torch.zeros((-(-slots // 64) * 64, 4), dtype=torch.int64, device=dev)
+            self.leaf_states = self.leaf_states_padded[:slots]
             # descent paths (LZB_TREE_PATH_STRIDE ints per slot): written by select, consumed by expand + backup
             self.leaf_path = torch.full((slots, 34), -1, dtype=torch.int32, device=dev)
             if self.k == 1:
@@ -72,13 +76,17 @@ class DeviceTreeBatch:
             else:
                 self.root_leaf_node = torch.full((t,), -1, dtype=torch.int32, device=dev)
                 self.root_leaf_status = torch.full((t,), LEAF_DONE, dtype=torch.int32, device=dev)
-                self.root_leaf_states = torch.zeros((t, 4), dtype=torch.int64, device=dev)
+                self.root_leaf_states_padded = torch.zeros((-(-t // 64) * 64, 4), dtype=torch.int64, device=dev)
+                self.root_leaf_states = self.root_leaf_states_padded[:t]
+            if self.k == 1:
+                self.root_leaf_states_padded = self.leaf_states_padded
         self._struct = _TreeStruct()
         for name in _ARENA_FIELDS:
             setattr(self._struct, name, getattr(self, name).data_ptr())
         self._struct.capacity = cap
         self._struct.num_trees = t
         self._pending_is_root = False
+        self._tree_rows: Optional[torch.Tensor] = None
         # second arena for advance_roots (subtree reuse); allocated on first use
         self._scratch: Optional[dict] = None
         self._scratch_struct: Optional[_TreeStruct] = None
@@ -101,9 +109,10 @@ class DeviceTreeBatch:
             if encode_out is not None:
                 # fused: the kernel also writes the bf16 [slots,6,6,64] network input of every pending leaf
                 slots = self.num_trees * k
-                if (encode_out.dtype != torch.bfloat16 or tuple(encode_out.shape) != (slots, 64, 6, 6)
+                if (encode_out.dtype != torch.bfloat16 or encode_out.dim() != 4 or encode_out.size(0) < slots
+                        or tuple(encode_out.shape[1:]) != (64, 6, 6)
                         or not encode_out.is_contiguous(memory_format=torch.channels_last)):
-                    raise RuntimeError(f"encode_out must be bfloat16 [{slots},64,6,6] in channels_last memory format")
+                    raise RuntimeError(f"encode_out must be bfloat16 [>={slots},64,6,6] in channels_last memory format")
                 check(lib().lzb_tree_select_encode(
                     ctypes.byref(self._struct), ctypes.c_int32(k), ctypes.c_double(self.exploration_weight),
                     ctypes.c_double(self.virtual_loss), ptr(node), ptr(status), ptr(states),
@@ -218,6 +227,11 @@ class DeviceTreeBatch:
     def pending_states(self) -> torch.Tensor:
         return self.root_leaf_states if self._pending_is_root else self.leaf_states
 
+    @property
+    def pending_states_padded(self) -> torch.Tensor:
+        """The same rows plus the zero rows up to the next multiple of 64 (network batches are whole 64-row tiles)."""
+        return self.root_leaf_states_padded if self._pending_is_root else self.leaf_states_padded
+
     def complete_pending(self, priors: torch.Tensor, values: torch.Tensor) -> None:
         """priors f32[slots,220] dense over the action space, values f32[slots] (slots = T for roots, T*K for a
         wave); rows of slots whose status is not LEAF_EVAL are ignored.  Roots are expanded without a backup
@@ -225,8 +239,8 @@ class DeviceTreeBatch:
         root = self._pending_is_root
         k = 1 if root else self.k
         slots = self.num_trees * k
-        if tuple(priors.shape) != (slots, ACTION_DIM) or values.numel() != slots:
-            raise RuntimeError(f"priors must be [{slots}, 220] and values [{slots}]")
+        if priors.dim() != 2 or priors.size(0) < slots or priors.size(1) != ACTION_DIM or values.numel() < slots:
+            raise RuntimeError(f"priors must be [>={slots}, 220] and values [>={slots}]")
         require_cuda(priors, "priors")
         p = priors.to(torch.float32).contiguous()
         v = values.to(torch.float32).contiguous()
@@ -245,14 +259,15 @@ class DeviceTreeBatch:
         if self._pending_is_root:
             raise RuntimeError("complete_and_select follows select_leaves, not prepare_roots")
         slots = self.num_trees * self.k
-        if tuple(priors.shape) != (slots, ACTION_DIM) or values.numel() != slots:
-            raise RuntimeError(f"priors must be [{slots}, 220] and values [{slots}]")
+        if priors.dim() != 2 or priors.size(0) < slots or priors.size(1) != ACTION_DIM or values.numel() < slots:
+            raise RuntimeError(f"priors must be [>={slots}, 220] and values [>={slots}]")
         require_cuda(priors, "priors")
         p = priors.to(torch.float32).contiguous()
         v = values.to(torch.float32).contiguous()
-        if encode_out is not None and (encode_out.dtype != torch.bfloat16 or tuple(encode_out.shape) != (slots, 64, 6, 6)
+        if encode_out is not None and (encode_out.dtype != torch.bfloat16 or encode_out.dim() != 4
+                                       or encode_out.size(0) < slots or tuple(encode_out.shape[1:]) != (64, 6, 6)
                                        or not encode_out.is_contiguous(memory_format=torch.channels_last)):
-            raise RuntimeError(f"encode_out must be bfloat16 [{slots},64,6,6] in channels_last memory format")
+            raise RuntimeError(f"encode_out must be bfloat16 [>={slots},64,6,6] in channels_last memory format")
         with torch.cuda.device(self.device):
             check(lib().lzb_tree_expand_select(ctypes.byref(self._struct), ctypes.c_int32(self.k), ptr(self.leaf_node),
                                                ptr(self.leaf_status), ptr(p), ptr(v),
@@ -292,13 +307,50 @@ class DeviceTreeBatch:
                 "expansions": int(c[2]), "terminal_hits": int(c[3]), "capacity": self.capacity,
                 "siblings_scanned": int(c[4]) & 0xFFFFFFFF, "levels_descended": int(c[5]) & 0xFFFFFFFF}
 
-    def check_capacity(self) -> None:
-        flags = int(self.counters[1].item())
+    # -- leaf-batch compaction -----------------------------------------------------------------------
+    def set_tree_rows(self, rows: Optional[torch.Tensor]) -> None:
+        """rows int32[T] (kept by reference: update it IN PLACE between waves) or None.  In the simulation waves tree t
+        uses leaf-batch rows rows[t]*K..; rows[t] < 0 = the tree sits the waves out (finished game).  With the live
+        trees' rows dense in [0, n) the network only has to run on ceil64(n) rows (TreeMCTS.search(live_rows=...))."""
+        if rows is not None:
+            require_cuda(rows, "rows")
+            if rows.dtype != torch.int32 or rows.numel() != self.num_trees or not rows.is_contiguous():
+                raise RuntimeError(f"tree rows must be a contiguous int32[{self.num_trees}] tensor")
+        self._tree_rows = rows
+        self._struct.tree_rows = 0 if rows is None else rows.data_ptr()
+
+    # -- error flags ------------------------------------------------------------------------------------
+    def _raise_flags(self, flags: int) -> None:
         if flags & FLAG_ILLEGAL_ADVANCE:
             raise RuntimeError("selected action is not a child of the current root")       # the reference's message
+        if flags & FLAG_BAD_NETWORK:
+            raise RuntimeError("model value is NaN or Inf / model prior is negative, NaN, or Inf")   # portable_mcts.cpp
         if flags & FLAG_ARENA:
             raise RuntimeError(f"tree node arena exhausted (capacity {self.capacity}); raise node_capacity")
 
+    def poll_errors(self) -> None:
+        """Non-blocking error check for hot loops: queues an async copy of the sticky flag word into pinned memory and
+        raises if an EARLIER copy (whose event has completed) carried a flag -- an error surfaces at most one call late
+        and the GPU never waits for the host.  ``check_capacity()`` is the blocking form (end of an iteration)."""
+        if getattr(self, "_flag_host", None) is None:
+            self._flag_host = torch.zeros((2,), dtype=torch.int32).pin_memory()
+            self._flag_event = [None, None]
+            self._flag_turn = 0
+        i = self._flag_turn
+        ev = self._flag_event[i]
+        if ev is not None:
+            if not ev.query():          # the oldest copy is still in flight: check it next time
+                return
+            self._raise_flags(int(self._flag_host[i]))
+        with torch.cuda.device(self.device):
+            self._flag_host[i:i + 1].copy_(self.counters[1:2], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        self._flag_event[i] = ev
+        self._flag_turn = 1 - i
+
+    def check_capacity(self) -> None:
+        self._raise_flags(int(self.counters[1].item()))
 
 
 def encode_inputs(packed: torch.Tensor, layout: str = "f32_nchw", out: Optional[torch.Tensor] = None) -> torch.Tensor:

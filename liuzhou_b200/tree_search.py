@@ -68,18 +68,48 @@ class TreeMCTS:
         self._advanced = False
         t, slots = self.num_trees, self.num_trees * k
         dev = self.device
-        self._root_in = net.new_input(t)
-        self._wave_in = self._root_in if k == 1 else net.new_input(slots)
-        self._root_pri = torch.zeros((t, ACTION_DIM), dtype=torch.float32, device=dev)
-        self._root_val = torch.zeros((t,), dtype=torch.float32, device=dev)
-        self._wave_pri = self._root_pri if k == 1 else torch.zeros((slots, ACTION_DIM), dtype=torch.float32, device=dev)
-        self._wave_val = self._root_val if k == 1 else torch.zeros((slots,), dtype=torch.float32, device=dev)
+        # network batches are whole 64-row tiles (the tcgen05 convolution works on 256-row tile pairs = 64 boards): the
+        # buffers are padded, the pad rows hold empty positions whose outputs nobody reads
+        tp, sp = -(-t // 64) * 64, -(-slots // 64) * 64
+        self._tp, self._sp = tp, sp
+        self._root_in = net.new_input(tp)
+        self._wave_in = self._root_in if k == 1 else net.new_input(sp)
+        self._root_pri = torch.zeros((tp, ACTION_DIM), dtype=torch.float32, device=dev)
+        self._root_val = torch.zeros((tp,), dtype=torch.float32, device=dev)
+        self._wave_pri = self._root_pri if k == 1 else torch.zeros((sp, ACTION_DIM), dtype=torch.float32, device=dev)
+        self._wave_val = self._root_val if k == 1 else torch.zeros((sp,), dtype=torch.float32, device=dev)
         self._wave_graph: Optional[torch.cuda.CUDAGraph] = None
         self._root_graph: Optional[torch.cuda.CUDAGraph] = None
         self.root_graph_launches = self.wave_graph_launches = self.search_extra_launches = 0
         self._first_graph: Optional[torch.cuda.CUDAGraph] = None
         self._last_graph: Optional[torch.cuda.CUDAGraph] = None
         self.evals = 0
+        # leaf-batch compaction (set_live / search(live_rows=...)): wave graphs per batch bucket, captured on first use
+        self._rows: Optional[torch.Tensor] = None
+        self._bucket_graphs: dict = {}
+        self._bucket = self.num_trees
+
+    # ---- leaf-batch compaction: the network only evaluates the live trees' leaves ----------------------------------
+    def bucket_for(self, live: int) -> int:
+        """Smallest supported wave batch (in trees) that holds `live` trees: multiples of 64 up to 256, then of 256."""
+        t = self.num_trees
+        live = max(1, min(int(live), t))
+        step = 64 if live <= 256 else 256
+        b = -(-live // step) * step
+        return t if (b >= t or t % 64 != 0) else b
+
+    def set_live(self, active: Optional[torch.Tensor]) -> None:
+        """active bool[T] (device) or None.  Live trees get the dense leaf-batch rows 0..n-1 (in tree order), the others
+        sit the simulation waves out; no host synchronisation.  Pass an upper bound of n as search(live_rows=...)."""
+        if active is None:
+            self.tree.set_tree_rows(None)
+            return
+        act = active.to(device=self.device, dtype=torch.bool).view(-1)
+        if self._rows is None:
+            self._rows = torch.empty((self.num_trees,), dtype=torch.int32, device=self.device)
+        rows = torch.cumsum(act.to(torch.int32), 0, dtype=torch.int32) - 1
+        self._rows.copy_(torch.where(act, rows, torch.full_like(rows, -1)))
+        self.tree.set_tree_rows(self._rows)
 
     # one network evaluation of the pending leaves + expansion (+ backup).  On the tcgen05 path the network input is
     # the channel-padded bf16 [n,64,6,6] tensor and the select kernel writes it itself (one launch less per wave).
@@ -94,7 +124,7 @@ class TreeMCTS:
         val = self._root_val if root else self._wave_val
         if not encoded:
             encode_inputs(tree.pending_states, "bf16_nhwc", out=x)
-        self.net.forward_priors(x, tree.pending_states, priors_out=pri, values_out=val)
+        self.net.forward_priors(x, tree.pending_states_padded, priors_out=pri, values_out=val)
         tree.complete_pending(pri, val)
 
     def _root_step(self) -> None:
@@ -111,18 +141,45 @@ class TreeMCTS:
         if not fused:
             encode_inputs(self.tree.pending_states, "bf16_nhwc", out=self._wave_in)
 
-    def _wave_mid(self) -> None:
+    def _wave_forward(self, bucket: Optional[int]) -> None:
+        """The network on the pending leaves: all slots, or only the first bucket * K rows (the live trees' leaves)."""
+        tree = self.tree
+        n = self._sp if (bucket is None or bucket >= self.num_trees) else int(bucket) * tree.k
+        self.net.forward_priors(self._wave_in[:n], tree.pending_states_padded[:n], priors_out=self._wave_pri[:n],
+                                values_out=self._wave_val[:n])
+
+    def _wave_mid(self, bucket: Optional[int] = None) -> None:
         tree = self.tree
         fused = self._fused_encode(self._wave_in)
-        self.net.forward_priors(self._wave_in, tree.pending_states, priors_out=self._wave_pri, values_out=self._wave_val)
+        self._wave_forward(bucket)
         tree.complete_and_select(self._wave_pri, self._wave_val, self._wave_in if fused else None)
         if not fused:
             encode_inputs(tree.pending_states, "bf16_nhwc", out=self._wave_in)
 
-    def _wave_last(self) -> None:
-        tree = self.tree
-        self.net.forward_priors(self._wave_in, tree.pending_states, priors_out=self._wave_pri, values_out=self._wave_val)
-        tree.complete_pending(self._wave_pri, self._wave_val)
+    def _wave_last(self, bucket: Optional[int] = None) -> None:
+        self._wave_forward(bucket)
+        self.tree.complete_pending(self._wave_pri, self._wave_val)
+
+    def _graphs_for(self, bucket: int):
+        """(wave graph, last-wave graph) for a wave batch of `bucket` trees; the full-size pair comes from _capture()."""
+        if bucket >= self.num_trees:
+            return self._wave_graph, self._last_graph
+        pair = self._bucket_graphs.get(bucket)
+        if pair is None:
+            dev = self.device
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):          # warm-up at this batch size outside the capture; leaves the tree intact:
+                self._wave_forward(bucket)         # only the network runs (its outputs are overwritten before use)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g_mid, g_last = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_mid, pool=self._root_graph.pool()):
+                self._wave_mid(bucket)
+            with torch.cuda.graph(g_last, pool=self._root_graph.pool()):
+                self._wave_last(bucket)
+            pair = self._bucket_graphs[bucket] = (g_mid, g_last)
+        return pair
 
     def _wave_step(self) -> None:
         """One stand-alone wave (select -> network -> expand + backup); used by tools and the tree-kernel timing."""
@@ -191,9 +248,16 @@ class TreeMCTS:
     @torch.no_grad()
     def search(self, root_states: torch.Tensor, *, active: Optional[torch.Tensor] = None,
                temperatures: Optional[torch.Tensor] = None, add_dirichlet_noise: Optional[bool] = None,
-               sample_moves: Optional[bool] = None) -> TreeSearchOutput:
+               sample_moves: Optional[bool] = None, live_rows: Optional[int] = None) -> TreeSearchOutput:
+        """``live_rows``: after ``set_live(active)``, a host-side UPPER BOUND of the number of live trees -- the simulation
+        waves then run the network on ``bucket_for(live_rows)`` rows instead of all trees (same results: the rows of
+        trees that sit out were never used)."""
         cfg = self.cfg
         tree = self.tree
+        if live_rows is not None and tree._tree_rows is None:
+            raise RuntimeError("search(live_rows=...) needs set_live(active) first")
+        bucket = self.num_trees if (live_rows is None or tree._tree_rows is None) else self.bucket_for(live_rows)
+        self._bucket = bucket
         keep = bool(cfg.reuse_subtree) and self._advanced      # roots already in place (advance() after the last move)
         self._advanced = False
         if keep:
@@ -214,16 +278,18 @@ class TreeMCTS:
         if cfg.add_dirichlet_noise if add_dirichlet_noise is None else add_dirichlet_noise:
             self._apply_root_noise()
         if use_graph:
+            g_mid, g_last = self._graphs_for(bucket)
             self._first_graph.replay()
             for _ in range(self.waves - 1):
-                self._wave_graph.replay()
-            self._last_graph.replay()
+                g_mid.replay()
+            g_last.replay()
         else:
             self._first_select()
             for _ in range(self.waves - 1):
-                self._wave_mid()
-            self._wave_last()
-        self.evals += self.num_trees * (1 + self.waves * tree.k)
+                self._wave_mid(bucket)
+            self._wave_last(bucket)
+        self.evals += self.num_trees + bucket * self.waves * tree.k
+        tree.poll_errors()                      # sticky arena / illegal-advance / bad-network flags, without a host sync
         beta = float(cfg.policy_target_prior_pseudocount)
         do_sample = cfg.sample_moves if sample_moves is None else sample_moves
         out = tree.root_outputs(with_priors=(beta > 0.0) or not do_sample)

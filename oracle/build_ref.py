@@ -13,6 +13,13 @@ and the reference's CMake build is not used.  Outputs (binaries only):
                                             with --cuda also the three reference .cu kernels
                                             compiled for sm_100)               -> tensor-op reference
 
+  oracle/_ref/pysrc/{src,v0/python,v1}     (--pysrc, default) a plain copy of the reference's PYTHON host code for
+                                            this path (v1/python/mcts_gpu.py, self_play_gpu_runner.py, src/ ...), so that
+                                            the GPU box -- which has no /root/reference -- can run the UNMODIFIED
+                                            reference entry over its own v0_core CUDA (the "reference on the same
+                                            B200" denominator) and over our v0_core shim (the boundary proof).
+                                            Never imported by liuzhou_b200/, never committed.
+
 oracle/_ref/ is git-ignored but NOT gpurun-ignored, so the binaries travel to the GPU box.
 The GPU box has no /root/reference: this script is a no-op there (keeps prebuilt files).
 
@@ -151,10 +158,25 @@ def build_v0_core(force: bool, cuda: bool) -> Path:
     return target
 
 
+def copy_pysrc() -> Path:
+    """The reference's python packages for this path, byte for byte, into the git-ignored oracle/_ref/pysrc."""
+    import shutil
+
+    dst = OUT / "pysrc"
+    if dst.exists():
+        shutil.rmtree(dst)
+    ignore = shutil.ignore_patterns("__pycache__", "*.pyc", "*.so", "*.md")
+    shutil.copytree(REF / "src", dst / "src", ignore=ignore)
+    shutil.copytree(REF / "v0" / "python", dst / "v0" / "python", ignore=ignore)
+    shutil.copytree(REF / "v1", dst / "v1", ignore=shutil.ignore_patterns("__pycache__", "*.pyc", "*.so", "*.md", "cpp"))
+    return dst
+
+
 def main() -> int:
     ap = argparse.ArgumentParser(description=__doc__)
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--cuda", action="store_true", help="also compile the reference .cu kernels (sm_100)")
+    ap.add_argument("--no-pysrc", action="store_true", help="skip the copy of the reference's python packages")
     ap.add_argument("--only", choices=["portable", "v0_core"], default=None)
     args = ap.parse_args()
     if not REF.is_dir():
@@ -165,6 +187,8 @@ def main() -> int:
         print("[build_ref] portable tree MCTS ->", build_portable(args.force))
     if args.only in (None, "v0_core"):
         print("[build_ref] v0_core ->", build_v0_core(args.force, args.cuda))
+    if args.only is None and not args.no_pysrc:
+        print("[build_ref] python host code ->", copy_pysrc())
     return 0
 
 

@@ -90,9 +90,13 @@ def test_trunk_and_heads_tc_path_matches_cudnn_path():
     x = (torch.rand((128, 11, 6, 6), device=DEV) > 0.6).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
     x64[:, :11] = x
     out_tc = [o.clone() for o in net._forward_eager(x64)]
-    out_tc11 = [o.clone() for o in net._forward_eager(x)]      # 11-channel input: cuDNN stem + our trunk convs
-    for a, b in zip(out_tc, out_tc11):
-        torch.testing.assert_close(a, b, rtol=5e-2, atol=5e-2)
+    with pytest.raises(RuntimeError):                          # no silent library path: unpadded inputs are refused
+        net._forward_eager(x)
+    with pytest.raises(RuntimeError):
+        net.new_input(100)
+    out_pub = net.forward(x.float())                           # the public entry pads rows and channels itself
+    for a, b in zip(out_tc, out_pub):
+        assert torch.equal(a, b)
     net.trunk.use_tc = net.heads.use_tc = False
     out_cudnn = [o.clone() for o in net._forward_eager(x)]
     ref = model.to(DEV).float().eval()

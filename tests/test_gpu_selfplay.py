@@ -59,7 +59,7 @@ def test_root_search_batch_stagewise_vs_oracle():
 
     st = _playout_states(6, 31, every=5)
     b = st["board"].shape[0]
-    net = InferenceNet(_small_net(), DEV)
+    net = InferenceNet(_small_net(), DEV, allow_library_convs=True)
     recorded = []
     orig = net.forward
 
@@ -139,7 +139,7 @@ def test_tree_mcts_search_graph_vs_eager_and_oracle_replay():
     st = _playout_states(5, 41, every=7)
     n = st["board"].shape[0]
     packed = native.pack_states(to_torch(st, DEV))
-    net = InferenceNet(_small_net(), DEV)
+    net = InferenceNet(_small_net(), DEV, allow_library_convs=True)
     res = []
     for graph in (True, False):
         cfg = TreeMCTSConfig(num_simulations=48, exploration_weight=1.25, add_dirichlet_noise=False,
@@ -188,7 +188,12 @@ def test_self_play_entry_format_and_determinism(backend):
     targets, policies over legal actions, and bit-identical reruns for a fixed torch seed."""
     from liuzhou_b200.self_play import self_play_v1_gpu
 
-    model = _small_net()
+    from liuzhou_b200.net import InferenceNet
+
+    model = InferenceNet(_small_net(), DEV, allow_library_convs=True)
+    with pytest.raises(RuntimeError):                   # other network shapes need the explicit library-conv opt-in
+        self_play_v1_gpu(_small_net(), num_games=2, mcts_simulations=2, temperature_init=1.0, temperature_final=0.1,
+                         temperature_threshold=10, exploration_weight=1.0, device=DEV, search_backend=backend)
     runs = []
     for _ in range(2):
         torch.manual_seed(99)
@@ -233,8 +238,8 @@ def test_fused_trunk_matches_pytorch_forward():
             m.running_var.uniform_(0.5, 1.5)
             m.weight.data.uniform_(0.5, 1.5)
             m.bias.data.normal_(0.0, 0.2)
-    fused = InferenceNet(model, DEV, fused=True)
-    plain = InferenceNet(model, DEV, fused=False)
+    fused = InferenceNet(model, DEV, fused=True, allow_library_convs=True)
+    plain = InferenceNet(model, DEV, fused=False, allow_library_convs=True)
     assert fused.trunk is not None and plain.trunk is None
     x = fused.new_input(257)
     x.copy_((torch.rand(257, 11, 6, 6, device=DEV) > 0.6).to(torch.bfloat16))
@@ -269,7 +274,7 @@ def test_fused_heads_kernel_vs_fp32_pytorch_heads(dims):
             m.running_var.uniform_(0.5, 1.5)
             m.weight.data.uniform_(0.5, 1.5)
             m.bias.data.normal_(0.0, 0.2)
-    net = InferenceNet(model, DEV)
+    net = InferenceNet(model, DEV, allow_library_convs=True)
     if (pc + vc) % 8 != 0:
         assert net.heads is None
         return
@@ -355,7 +360,7 @@ def test_tree_mcts_subtree_reuse_across_moves_vs_oracle_replay():
     st = _playout_states(5, 41, every=9)
     n = st["board"].shape[0]
     sims = 40
-    net = InferenceNet(_small_net(), DEV)
+    net = InferenceNet(_small_net(), DEV, allow_library_convs=True)
 
     def gpu_eval(pend_states, tree_idx):
         full = oracle.initial_states(n)
@@ -401,7 +406,7 @@ def test_stepper_with_subtree_reuse_keeps_roots_in_sync():
     from liuzhou_b200.engine import SelfPlayStepper
     from liuzhou_b200.net import InferenceNet
 
-    net = InferenceNet(_small_net(), DEV)
+    net = InferenceNet(_small_net(), DEV, allow_library_convs=True)
     torch.manual_seed(3)
     sp = SelfPlayStepper(net, 256, simulations=24, seed=11, device=DEV, reuse_subtree=True, max_game_plies=40)
     sp.diversify(seed=5, max_random_plies=30, groups=4)
@@ -440,3 +445,28 @@ def test_self_play_tree_backend_policy_target_options():
                                add_dirichlet_noise=True, max_game_plies=60, sample_moves=True, concurrent_games=16,
                                search_backend="tree")
     assert not torch.all((base.policy_targets > 0) == base.legal_masks)  # visit-only targets leave unvisited moves at 0
+
+
+def test_tree_self_play_fast_path_equals_literal_wave_loop():
+    """The public tree-backend entry (packed layout, no per-ply host sync, leaf batches compacted to the live games and
+    padded to 64-row tiles, value targets broadcast at the end) against the literal reference-style wave loop over the
+    drop-in ops (tests/_slow_selfplay.py): identical trajectory batch, bit for bit.  70 games = not a multiple of 64 (the
+    padded tile path), default 128-channel network = every convolution on the tcgen05 kernel; deterministic moves."""
+    from liuzhou_b200 import _lib
+    from liuzhou_b200.net import ChessNet, InferenceNet
+    from liuzhou_b200.self_play import self_play_v1_gpu
+    from tests._slow_selfplay import slow_tree_self_play
+
+    torch.manual_seed(11)
+    net = InferenceNet(ChessNet(), DEV)
+    assert not net.library_convs
+    ref, ref_len, ref_out = slow_tree_self_play(net, 70, 12, device=DEV)
+    batch, stats = self_play_v1_gpu(net, num_games=70, mcts_simulations=12, temperature_init=1.0, temperature_final=0.1,
+                                    temperature_threshold=10, exploration_weight=1.0, device=DEV,
+                                    add_dirichlet_noise=False, sample_moves=False, concurrent_games=70,
+                                    search_backend="tree")
+    assert batch.num_samples == ref.num_samples > 70 * 30
+    for f in ("state_tensors", "legal_masks", "policy_targets", "value_targets", "soft_value_targets"):
+        assert torch.equal(getattr(batch, f), getattr(ref, f)), f
+    assert abs(stats.avg_game_length - float(ref_len.float().mean())) < 1e-6
+    assert [stats.black_wins, stats.white_wins, stats.draws] == ref_out.tolist()
