@@ -142,6 +142,14 @@ LZB_API int lzb_root_finalize_from_visits(const int64_t *legal_index_mat, const 
                                   int64_t *chosen_action_indices, int32_t *chosen_action_codes,
                                   uint8_t *chosen_valid_mask, float *root_value, void *stream);
 
+/* (a10) root_sparse_writeback -- module.cpp:365-439: scatter an externally supplied legal policy f32[R,M] (x valid_mask)
+ * and the column picked per root (local_picks i64[R]) back to dense rows; same output convention as above. */
+LZB_API int lzb_root_sparse_writeback(const int64_t *legal_index_mat, const int32_t *action_code_mat,
+                                      const uint8_t *valid_mask, const float *legal_policy, const int64_t *local_picks,
+                                      const int64_t *valid_root_indices, int64_t R, int64_t M, int64_t batch_size,
+                                      int64_t total_action_dim, float *policy_dense, int64_t *chosen_action_indices,
+                                      int32_t *chosen_action_codes, uint8_t *chosen_valid_mask, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (a14) self_play_step_inplace -- module.cpp:632-871.  Mutates the 12 state tensors, plies, done.
  * Output buffers must hold K entries; *num_finalized (device i64) receives F.  Order of the F entries:

@@ -212,6 +212,37 @@ finalize_visits_kernel(const int64_t* __restrict__ legal_index_mat, const int32_
 }
 
 // ------------------------------------------------------------------------------------------------------
+// (a10) root_sparse_writeback -- module.cpp:365-439: an externally computed legal policy [R,M] and the picked column
+// of every root go back to dense [B,A] rows.  Warp per root; `policy_dense` rows are pre-zeroed, the scatter is an
+// atomicAdd because the reference's scatter_add_ also sums repeated indices (padding columns carry index 0 with
+// weight policy * 0).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+sparse_writeback_kernel(const int64_t* __restrict__ legal_index_mat, const int32_t* __restrict__ action_code_mat,
+                        const uint8_t* __restrict__ valid_mask, const float* __restrict__ legal_policy,
+                        const int64_t* __restrict__ picks, const int64_t* __restrict__ roots, int64_t R, int M, int64_t A,
+                        float* __restrict__ policy_dense, int64_t* __restrict__ chosen_idx,
+                        int32_t* __restrict__ chosen_codes, uint8_t* __restrict__ chosen_valid) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    for (int64_t r = warp; r < R; r += nwarps) {
+        const int64_t base = r * M, b = roots[r];
+        float* dense = policy_dense + b * A;
+        for (int c = lane; c < M; c += 32) {
+            const float w = legal_policy[base + c] * (valid_mask[base + c] ? 1.0f : 0.0f);
+            atomicAdd(dense + legal_index_mat[base + c], w);
+        }
+        if (lane == 0) {
+            const int64_t pick = picks[r];
+            chosen_idx[b] = legal_index_mat[base + pick];
+            reinterpret_cast<int4*>(chosen_codes)[b] = reinterpret_cast<const int4*>(action_code_mat)[base + pick];
+            chosen_valid[b] = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // (a14) self_play_step_inplace -- module.cpp:632-871
 // ------------------------------------------------------------------------------------------------------
 struct StepScratch { int32_t flag; float result; float soft; int32_t pad; };   // 16 B per active row
@@ -437,6 +468,33 @@ extern "C" int lzb_root_finalize_from_visits(const int64_t* legal_index_mat, con
                                                             chosen_action_indices, chosen_action_codes,
                                                             chosen_valid_mask, root_value);
     return check_launch("finalize_visits_kernel");
+}
+
+extern "C" int lzb_root_sparse_writeback(const int64_t* legal_index_mat, const int32_t* action_code_mat,
+                                         const uint8_t* valid_mask, const float* legal_policy, const int64_t* local_picks,
+                                         const int64_t* valid_root_indices, int64_t R, int64_t M, int64_t batch_size,
+                                         int64_t total_action_dim, float* policy_dense, int64_t* chosen_action_indices,
+                                         int32_t* chosen_action_codes, uint8_t* chosen_valid_mask, void* stream) {
+    LZB_REQUIRE(batch_size >= 0, "batch_size must be non-negative");
+    LZB_REQUIRE(total_action_dim > 0, "total_action_dim must be positive");
+    LZB_REQUIRE(R >= 0 && M >= 0 && M < (1 << 24), "bad shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (batch_size > 0) {
+        LZB_REQUIRE(policy_dense && chosen_action_indices && chosen_action_codes && chosen_valid_mask, "null output");
+        cudaMemsetAsync(policy_dense, 0, sizeof(float) * batch_size * total_action_dim, s);
+        cudaMemsetAsync(chosen_action_indices, 0xFF, sizeof(int64_t) * batch_size, s);
+        cudaMemsetAsync(chosen_action_codes, 0xFF, sizeof(int32_t) * 4 * batch_size, s);
+        cudaMemsetAsync(chosen_valid_mask, 0, batch_size, s);
+    }
+    if (R == 0) return LZB_OK;
+    LZB_REQUIRE(M > 0, "roots without action columns");
+    LZB_REQUIRE(legal_index_mat && action_code_mat && valid_mask && legal_policy && local_picks && valid_root_indices,
+                "null input");
+    sparse_writeback_kernel<<<warp_grid(R), kThreads, 0, s>>>(legal_index_mat, action_code_mat, valid_mask, legal_policy,
+                                                             local_picks, valid_root_indices, R, (int)M, total_action_dim,
+                                                             policy_dense, chosen_action_indices, chosen_action_codes,
+                                                             chosen_valid_mask);
+    return check_launch("sparse_writeback_kernel");
 }
 
 extern "C" int lzb_self_play_step_inplace(const lzb_states_out* states, int64_t B, int64_t* plies, uint8_t* done,

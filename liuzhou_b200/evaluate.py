@@ -76,8 +76,16 @@ class _SearchAgent:
         self._temps = torch.full((num_slots,), float(temperature), dtype=torch.float32, device=self.net.device)
 
     def select(self, states: torch.Tensor, active: torch.Tensor) -> torch.Tensor:
+        """Only the games where this agent moves are searched: their leaves are compacted into the first rows of the
+        wave batch and the network runs on ceil(live) rows (one host read of the count per ply -- cheap next to the
+        64+ network evaluations of a search)."""
+        n_live = int(active.sum().item())
+        if n_live == 0:
+            return torch.full((active.numel(),), -1, dtype=torch.int64, device=active.device)
+        self.mcts.set_live(active)
         out = self.mcts.search(states, active=active, temperatures=self._temps, add_dirichlet_noise=False,
-                               sample_moves=self.sample_moves)
+                               sample_moves=self.sample_moves, live_rows=n_live)
+        self.searched_rows = getattr(self, "searched_rows", 0) + self.mcts._bucket
         return out.chosen_action_indices
 
 

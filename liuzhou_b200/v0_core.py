@@ -264,32 +264,42 @@ def root_pack_sparse_actions(legal_mask, probs, metadata):
 
 def root_sparse_writeback(legal_index_mat, action_code_mat, valid_mask, legal_policy, local_picks,
                           valid_root_indices, batch_size, total_action_dim):
-    """module.cpp:365-439 (not on the v1 hot path; kept for surface completeness).  Scatter of an externally
-    supplied legal policy + picks back to dense [B, A] rows, expressed with device-side torch indexing."""
+    """-> (policy_dense f32[B,A], chosen_action_indices i64[B], chosen_action_codes i32[B,4], chosen_valid_mask bool[B]);
+    module.cpp:365-439: an externally supplied legal policy + per-root picks scattered back to dense rows."""
     if int(batch_size) < 0:
         raise RuntimeError("batch_size must be non-negative")
     if int(total_action_dim) <= 0:
         raise RuntimeError("total_action_dim must be positive")
+    if legal_index_mat.dim() != 2 or valid_mask.dim() != 2 or legal_policy.dim() != 2:
+        raise RuntimeError("legal_index_mat / valid_mask / legal_policy must be [R, M]")
+    if action_code_mat.dim() != 3 or action_code_mat.size(2) != 4:
+        raise RuntimeError("action_code_mat must be [R, M, 4]")
+    r, m = legal_index_mat.shape
+    if tuple(valid_mask.shape) != (r, m) or tuple(legal_policy.shape) != (r, m) or tuple(action_code_mat.shape[:2]) != (r, m):
+        raise RuntimeError("legal_index_mat / valid_mask / legal_policy / action_code_mat shape mismatch")
+    if local_picks.dim() != 1 or local_picks.numel() != r or valid_root_indices.dim() != 1 or valid_root_indices.numel() != r:
+        raise RuntimeError("local_picks / valid_root_indices size mismatch")
     require_cuda(legal_index_mat, "legal_index_mat")
     dev = legal_index_mat.device
-    legal_idx = legal_index_mat.to(torch.int64)
-    mask_f = valid_mask.to(torch.float32)
-    policy = legal_policy.to(torch.float32)
-    picks = local_picks.to(torch.int64)
-    roots = valid_root_indices.to(torch.int64)
-    policy_valid = torch.zeros((legal_idx.size(0), int(total_action_dim)), dtype=torch.float32, device=dev)
-    policy_valid.scatter_add_(1, legal_idx, policy * mask_f)
-    chosen_idx_local = legal_idx.gather(1, picks.view(-1, 1)).view(-1)
-    chosen_codes_local = action_code_mat.to(torch.int32).gather(1, picks.view(-1, 1, 1).expand(-1, 1, 4)).view(-1, 4)
-    policy_dense = torch.zeros((int(batch_size), int(total_action_dim)), dtype=torch.float32, device=dev)
-    chosen_action_indices = torch.full((int(batch_size),), -1, dtype=torch.int64, device=dev)
-    chosen_action_codes = torch.full((int(batch_size), 4), -1, dtype=torch.int32, device=dev)
-    chosen_valid_mask = torch.zeros((int(batch_size),), dtype=torch.bool, device=dev)
-    policy_dense.index_copy_(0, roots, policy_valid)
-    chosen_action_indices.index_copy_(0, roots, chosen_idx_local)
-    chosen_action_codes.index_copy_(0, roots, chosen_codes_local)
-    chosen_valid_mask.index_fill_(0, roots, True)
-    return policy_dense, chosen_action_indices, chosen_action_codes, chosen_valid_mask
+    for t in (action_code_mat, valid_mask, legal_policy, local_picks, valid_root_indices):
+        if t.device != dev:
+            raise RuntimeError("all tensors must be on the same device")
+    li = legal_index_mat.to(torch.int64).contiguous()
+    ac = action_code_mat.to(torch.int32).contiguous()
+    vm = valid_mask.to(torch.bool).contiguous()
+    lp = legal_policy.to(torch.float32).contiguous()
+    pk = local_picks.to(torch.int64).contiguous()
+    ro = valid_root_indices.to(torch.int64).contiguous()
+    bsz, adim = int(batch_size), int(total_action_dim)
+    with torch.cuda.device(dev):
+        policy_dense = torch.empty((bsz, adim), dtype=torch.float32, device=dev)
+        chosen_idx = torch.empty((bsz,), dtype=torch.int64, device=dev)
+        chosen_codes = torch.empty((bsz, 4), dtype=torch.int32, device=dev)
+        chosen_valid = torch.empty((bsz,), dtype=torch.bool, device=dev)
+        check(lib().lzb_root_sparse_writeback(ptr(li), ptr(ac), ptr(vm), ptr(lp), ptr(pk), ptr(ro), i64(r), i64(m),
+                                              i64(bsz), i64(adim), ptr(policy_dense), ptr(chosen_idx), ptr(chosen_codes),
+                                              ptr(chosen_valid), stream_ptr(dev)))
+    return policy_dense, chosen_idx, chosen_codes, chosen_valid
 
 
 def root_finalize_from_visits(legal_index_mat, action_code_mat, valid_mask, visits, value_sum, valid_root_indices,

@@ -281,6 +281,31 @@ def random_playouts_range(seed: int, g0: int, g1: int, max_plies: int = 512):
             "hash_xor": int(out[4])}
 
 
+def random_playouts_each(seed: int, g0: int, g1: int, max_plies: int = 512, threads: int = 0):
+    """Per-game (plies int32, result int8, hash uint64) of games [g0, g1), played in C on `threads` host threads (the C
+    call releases the GIL)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    n = int(g1) - int(g0)
+    plies = np.zeros((n,), np.int32)
+    result = np.zeros((n,), np.int8)
+    hashes = np.zeros((n,), np.uint64)
+    threads = int(threads) or (os.cpu_count() or 1)
+    chunk = max(1, -(-n // (threads * 4)))
+    L = lib()
+
+    def work(lo):
+        hi = min(n, lo + chunk)
+        L.or_random_playouts_each(ctypes.c_uint64(seed), ctypes.c_uint64(g0 + lo), ctypes.c_uint64(g0 + hi),
+                                  ctypes.c_int(max_plies), ctypes.c_void_p(plies[lo:].ctypes.data),
+                                  ctypes.c_void_p(result[lo:].ctypes.data), ctypes.c_void_p(hashes[lo:].ctypes.data))
+
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        list(pool.map(work, range(0, n, chunk)))
+    return plies, result, hashes
+
+
 def state_hash(st: dict, i: int = 0) -> int:
     arr = states_to_structs({k: v[i:i + 1] for k, v in st.items()})
     return int(lib().or_state_hash(ctypes.byref(arr[0])))
@@ -382,6 +407,7 @@ from .composites import (  # noqa: E402,F401
     project_policy_logits_fast,
     root_finalize_from_visits,
     root_pack_sparse_actions,
+    root_sparse_writeback,
     self_play_step_inplace,
     soft_value_from_board,
     terminal_mask_from_next_state,

@@ -87,6 +87,31 @@ def root_finalize_from_visits(legal_index_mat, action_code_mat, valid_mask, visi
     return policy_dense, chosen_idx, chosen_codes, chosen_valid, root_value
 
 
+def root_sparse_writeback(legal_index_mat, action_code_mat, valid_mask, legal_policy, local_picks,
+                          valid_root_indices, batch_size: int, total_action_dim: int):
+    """module.cpp:365-439: dense scatter of a legal policy [R,M] (x valid_mask, repeated indices add up as in
+    scatter_add_) and of the picked column per root; rows that are not valid roots stay 0 / -1 / False."""
+    li = np.asarray(legal_index_mat, dtype=np.int64)
+    ac = np.asarray(action_code_mat, dtype=np.int32)
+    vm = np.asarray(valid_mask).astype(bool)
+    lp = np.asarray(legal_policy, dtype=F32)
+    picks = np.asarray(local_picks, dtype=np.int64).reshape(-1)
+    roots = np.asarray(valid_root_indices, dtype=np.int64).reshape(-1)
+    r = li.shape[0]
+    policy_dense = np.zeros((batch_size, total_action_dim), F32)
+    chosen_idx = np.full((batch_size,), -1, np.int64)
+    chosen_codes = np.full((batch_size, 4), -1, np.int32)
+    chosen_valid = np.zeros((batch_size,), bool)
+    for i in range(r):
+        row = np.zeros((total_action_dim,), F32)
+        np.add.at(row, li[i], (lp[i] * vm[i].astype(F32)).astype(F32))
+        policy_dense[roots[i]] = row
+        chosen_idx[roots[i]] = li[i, picks[i]]
+        chosen_codes[roots[i]] = ac[i, picks[i]]
+        chosen_valid[roots[i]] = True
+    return policy_dense, chosen_idx, chosen_codes, chosen_valid
+
+
 def soft_value_from_board(boards, soft_value_k: float):
     """module.cpp:537-545 == mcts_gpu.py:677-686: tanh(k * (black - white) / 18)."""
     boards = np.asarray(boards).reshape(-1, 36)

@@ -776,3 +776,16 @@ void or_random_playouts_range(uint64_t seed, uint64_t g0, uint64_t g1, int max_p
     }
     out[0] = plies; out[1] = bw; out[2] = ww; out[3] = dr; out[4] = hx;
 }
+
+/* Parity helper (full-size config-2 test): play games [g0, g1) and return every game's (plies, result, chained state
+ * hash) -- the per-game form of or_random_playouts_range; arrays are indexed by g - g0. */
+void or_random_playouts_each(uint64_t seed, uint64_t g0, uint64_t g1, int max_plies, int32_t *plies_out,
+                             int8_t *result_out, uint64_t *hash_out) {
+    for (uint64_t g = g0; g < g1; ++g) {
+        int res = 0;
+        uint64_t h = 0;
+        plies_out[g - g0] = (int32_t)or_random_playout(seed, g, max_plies, 0, &res, 0, &h);
+        result_out[g - g0] = (int8_t)res;
+        hash_out[g - g0] = h;
+    }
+}

@@ -125,6 +125,8 @@ int or_random_playout(uint64_t seed, uint64_t game, int max_plies, or_state *fin
                       int *result_from_black, int16_t *trace, uint64_t *state_hash);
 
 void or_random_playouts_range(uint64_t seed, uint64_t g0, uint64_t g1, int max_plies, uint64_t *out);
+void or_random_playouts_each(uint64_t seed, uint64_t g0, uint64_t g1, int max_plies, int32_t *plies_out,
+                             int8_t *result_out, uint64_t *hash_out);
 
 /* FNV-style hash of a state in canonical field order (used for checksum-of-checksums properties). */
 uint64_t or_state_hash(const or_state *s);

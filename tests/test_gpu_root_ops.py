@@ -177,6 +177,39 @@ def test_finalize_trajectory_inplace_vs_oracle(v0):
     assert got[0].numel() == 0 and _np(got[2]).tolist() == [0, 0, 0]
 
 
+def test_root_sparse_writeback_vs_oracle_and_reference(v0):
+    """a10: `root_sparse_writeback` (module.cpp:365-439) -- the CUDA kernel against the oracle restatement (pinned to the
+    reference binary on the CPU) and, where oracle/_ref travelled, against the reference's own op on this GPU."""
+    st = _playout_states(8, 31)
+    mask, meta = oracle.encode_actions_fast(st)
+    rng = np.random.default_rng(9)
+    mask[::11] = False
+    probs = (rng.random(mask.shape).astype(np.float32) + 0.01) * mask
+    (_tm, roots, cnt, valid_mask, legal_idx, priors, code_mat, _f, _c, _p) = oracle.root_pack_sparse_actions(mask, probs, meta)
+    policy = rng.random(priors.shape).astype(np.float32) + 0.05
+    picks = (rng.integers(0, 1 << 30, roots.size) % cnt).astype(np.int64)
+    args = (_t(legal_idx), _t(code_mat), _t(valid_mask), _t(policy), _t(picks), _t(roots), mask.shape[0], 220)
+    got = v0.root_sparse_writeback(*args)
+    exp = oracle.root_sparse_writeback(legal_idx, code_mat, valid_mask, policy, picks, roots, mask.shape[0], 220)
+    assert got[0].dtype == torch.float32 and got[1].dtype == torch.int64 and got[2].dtype == torch.int32
+    assert got[3].dtype == torch.bool
+    for i, (g, e) in enumerate(zip(got, exp)):
+        assert np.array_equal(_np(g), e), i
+    ref = load_ref()
+    if ref is not None:
+        for i, (g, r) in enumerate(zip(got, ref[0].root_sparse_writeback(*args))):
+            assert torch.equal(g, r), i
+    # no valid roots at all
+    empty = v0.root_sparse_writeback(torch.zeros((0, 0), dtype=torch.int64, device=DEV),
+                                     torch.zeros((0, 0, 4), dtype=torch.int32, device=DEV),
+                                     torch.zeros((0, 0), dtype=torch.bool, device=DEV), torch.zeros((0, 0), device=DEV),
+                                     torch.zeros((0,), dtype=torch.int64, device=DEV),
+                                     torch.zeros((0,), dtype=torch.int64, device=DEV), 5, 220)
+    assert not empty[0].any() and bool((empty[1] == -1).all()) and not empty[3].any()
+    with pytest.raises(RuntimeError):
+        v0.root_sparse_writeback(*args[:6], -1, 220)
+
+
 @pytest.mark.skipif(load_ref() is None, reason="oracle/_ref (reference binaries) not present on this box")
 def test_composites_vs_reference_on_gpu(v0):
     """Same ops from the reference's own module executed on CUDA tensors on this box."""

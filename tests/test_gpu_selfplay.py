@@ -470,3 +470,71 @@ def test_tree_self_play_fast_path_equals_literal_wave_loop():
         assert torch.equal(getattr(batch, f), getattr(ref, f)), f
     assert abs(stats.avg_game_length - float(ref_len.float().mean())) < 1e-6
     assert [stats.black_wins, stats.white_wins, stats.draws] == ref_out.tolist()
+
+
+def test_tree_search_full_size_vs_oracle_three_plies_with_reuse():
+    """BASELINE configs[2] at FULL size against the oracle: 4,096 trees x 200 simulations per move, default network on the
+    tcgen05 path, three consecutive moves with subtree reuse (advance_roots).  The oracle's tree (restatement of
+    PortableTreeBatch, pinned against the reference binary) is fed, wave by wave, the priors / values the GPU network
+    produces for ITS pending leaves -- identical visit counts are required on every one of the 4,096 roots after every
+    move, and identical chosen moves."""
+    from liuzhou_b200 import native
+    from liuzhou_b200.net import ChessNet, InferenceNet
+    from liuzhou_b200.tree import encode_inputs
+    from liuzhou_b200.tree_search import TreeMCTS, TreeMCTSConfig
+
+    n, sims = 4096, 200
+    torch.manual_seed(20260314)
+    net = InferenceNet(ChessNet(), DEV)
+    chunks = []
+    for i, steps in enumerate((0, 9, 30, 45, 70, 100, 140, 200)):
+        pb = native.PlayoutBatch(n // 8, seed=99, device=DEV, game_offset=i * (n // 8))
+        if steps:
+            pb.run(max_steps=steps)
+        chunks.append(pb.packed)
+    roots = torch.cat(chunks).contiguous()
+    st = {k: _np(t) for k, t in zip(STATE_FIELDS, native.unpack_states(roots))}
+    mcts = TreeMCTS(net, n, TreeMCTSConfig(num_simulations=sims, add_dirichlet_noise=False, sample_moves=False,
+                                           reuse_subtree=True), DEV)
+    x = net.new_input(n)
+    full = {k: np.array(v, copy=True) for k, v in oracle.initial_states(n).items()}
+
+    def gpu_eval(pend_states, tree_idx):
+        for k in STATE_FIELDS:
+            full[k][tree_idx] = pend_states[k]
+        pk = native.pack_states(to_torch(full, DEV))
+        encode_inputs(pk, "bf16_nhwc", out=x)
+        p, v = net.forward_priors(x, pk)
+        return _np(p)[tree_idx], _np(v)[tree_idx]
+
+    def oracle_move(ref):
+        pend = ref.prepare_roots()
+        if len(pend["tree_indices"]):
+            ref.complete_pending(*gpu_eval(ref.pending_states(), pend["tree_indices"]))
+        else:
+            ref.complete_pending(np.zeros((0, 220), np.float32), np.zeros((0,), np.float32))
+        for _ in range(sims):
+            pend = ref.select_leaves()
+            if len(pend["tree_indices"]):
+                ref.complete_pending(*gpu_eval(ref.pending_states(), pend["tree_indices"]))
+            else:
+                ref.complete_pending(np.zeros((0, 220), np.float32), np.zeros((0,), np.float32))
+        return ref.root_outputs()
+
+    ref = oracle.TreeBatch(st, 1.0)
+    cur = roots
+    temps = torch.ones((n,), device=DEV)
+    for move in range(3):
+        out = mcts.search(cur, temperatures=temps)
+        ro = oracle_move(ref)
+        visits = _np(out.visit_counts)
+        assert np.array_equal(ro["visit_counts"], visits), (move, int((ro["visit_counts"] != visits).any(1).sum()))
+        live = ~_np(out.terminal_mask)
+        assert live.sum() > n // 2
+        np.testing.assert_allclose(_np(out.root_value)[live], ro["root_values"][live], rtol=1e-5, atol=1e-6)
+        chosen = out.chosen_action_indices
+        mcts.advance(chosen)
+        ref.advance_roots(_np(chosen).astype(np.int32))
+        nxt = native.apply_actions(cur, chosen.clamp_min(0).to(torch.int32))
+        cur = torch.where((chosen >= 0).view(-1, 1), nxt, cur).contiguous()
+    mcts.tree.check_capacity()

@@ -197,6 +197,25 @@ def test_root_pack_and_finalize_match_reference():
     np.testing.assert_allclose(got[4], ref[4].numpy(), rtol=1e-5, atol=1e-6)
 
 
+def test_root_sparse_writeback_matches_reference():
+    """module.cpp:365-439: the scatter of an external legal policy + picks back to dense rows (exact: products and
+    single adds only)."""
+    v0_core, _ = REF
+    torch = _torch()
+    st, mask, meta, probs, rng = _search_inputs()
+    mask[::13] = False
+    (_tm, roots, cnt, valid_mask, legal_idx, priors, code_mat, _flat, _ca, _pa) = oracle.root_pack_sparse_actions(
+        mask, probs, meta)
+    policy = (rng.random(priors.shape).astype(np.float32) + 0.05)          # NOT masked: the op applies valid_mask itself
+    picks = (rng.integers(0, 1 << 30, roots.size) % cnt).astype(np.int64)
+    ref = v0_core.root_sparse_writeback(torch.from_numpy(legal_idx), torch.from_numpy(code_mat),
+                                        torch.from_numpy(valid_mask), torch.from_numpy(policy), torch.from_numpy(picks),
+                                        torch.from_numpy(roots), mask.shape[0], 220)
+    got = oracle.root_sparse_writeback(legal_idx, code_mat, valid_mask, policy, picks, roots, mask.shape[0], 220)
+    for i, (g, r) in enumerate(zip(got, ref)):
+        assert np.array_equal(g, r.numpy()), i
+
+
 def test_project_policy_matches_reference():
     v0_core, _ = REF
     torch = _torch()
