@@ -96,7 +96,7 @@ class TreeMCTS:
         live = max(1, min(int(live), t))
         step = 64 if live <= 256 else 256
         b = -(-live // step) * step
-        return t if (b >= t or t % 64 != 0) else b
+        return t if b >= t else b
 
     def set_live(self, active: Optional[torch.Tensor]) -> None:
         """active bool[T] (device) or None.  Live trees get the dense leaf-batch rows 0..n-1 (in tree order), the others

@@ -117,3 +117,58 @@ def test_encode_inputs_channel_padded_layout():
     x64 = torch.full((256, 64, 6, 6), 7.0, dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last)
     encode_inputs(pb.packed, "bf16_nhwc", out=x64)
     assert torch.equal(x64[:, :11], x11) and not x64[:, 11:].any()
+
+
+def _kernel_names(fn):
+    """Names of every CUDA kernel launched by fn() (torch.profiler / CUPTI)."""
+    from torch.profiler import ProfilerActivity, profile
+
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    return [e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+
+
+_LIBRARY_CONV = ("cudnn", "convolve", "nvjet", "cutlass", "xmma", "gemm", "implicit_convolve", "winograd")
+
+
+def test_no_library_convolution_for_any_batch_size():
+    """One convolution path: batches that are not multiples of 64 (a `_split_games` share of 65,311 positions through
+    the drop-in `InferenceNet.forward`, a 4,000-game tree search) run on `conv_tc_kernel` with padded tiles -- not a
+    single cuDNN / cuBLAS / CUTLASS kernel is launched (kernel names from torch.profiler)."""
+    from liuzhou_b200 import native
+    from liuzhou_b200.net import ChessNet, InferenceNet
+    from liuzhou_b200.tree_search import TreeMCTS, TreeMCTSConfig
+
+    torch.manual_seed(1)
+    net = InferenceNet(ChessNet(), DEV)
+    x = (torch.rand((65_311, 11, 6, 6), device=DEV) > 0.6).float()
+    net.forward(x)                                                         # warm-up (allocations)
+    names = _kernel_names(lambda: net.forward(x))
+    assert sum("conv_tc_kernel" in n for n in names) >= 22 * 4             # 4 chunks of <= 16,384 rows
+    bad = [n for n in names if any(t in n.lower() for t in _LIBRARY_CONV)]
+    assert not bad, sorted(set(bad))[:5]
+
+    n_trees = 4000
+    pb = native.PlayoutBatch(n_trees, seed=5, device=DEV)
+    pb.run(max_steps=30)
+    mcts = TreeMCTS(net, n_trees, TreeMCTSConfig(num_simulations=6, add_dirichlet_noise=False, sample_moves=False), DEV)
+    temps = torch.ones((n_trees,), device=DEV)
+    out = mcts.search(pb.packed, temperatures=temps)                       # captures the graphs
+    assert bool((out.visit_counts.sum(1)[~out.terminal_mask] == 6).all())
+    names = _kernel_names(lambda: mcts.search(pb.packed, temperatures=temps))
+    assert sum("conv_tc_kernel" in n for n in names) >= 22 * 7
+    bad = [n for n in names if any(t in n.lower() for t in _LIBRARY_CONV)]
+    assert not bad, sorted(set(bad))[:5]
+    # the same search with only 1,000 live trees compacts its waves to a 1,024-row batch and gives the same counts
+    active = torch.zeros((n_trees,), dtype=torch.bool, device=DEV)
+    active[::4] = True
+    full = mcts.search(pb.packed, active=active, temperatures=temps)
+    mcts.set_live(active)
+    compact = mcts.search(pb.packed, active=active, temperatures=temps, live_rows=1000)
+    assert mcts._bucket == 1024
+    mcts.set_live(None)
+    assert torch.equal(full.visit_counts, compact.visit_counts)
+    assert torch.equal(full.chosen_action_indices, compact.chosen_action_indices)
+    assert bool((compact.visit_counts[~active] == 0).all())

@@ -15,7 +15,10 @@ def _tiny_net(seed):
     from liuzhou_b200.net import ChessNet
 
     torch.manual_seed(seed)
-    return ChessNet(trunk_channels=8, num_blocks=1, policy_channels=4, value_channels=4, value_mlp_channels=8)
+    from liuzhou_b200.net import InferenceNet
+
+    return InferenceNet(ChessNet(trunk_channels=8, num_blocks=1, policy_channels=4, value_channels=4,
+                                 value_mlp_channels=8), DEV, allow_library_convs=True)
 
 
 def _replay(trace, g):

@@ -59,7 +59,9 @@ def test_scalar_api_errors_and_per_phase_functions():
 
     s = v.GameState()
     assert v.generate_placement_positions(s) == [(r, c) for r in range(6) for c in range(6)]
-    assert v.generate_mark_targets(s) == [] and v.generate_movement_moves(s) == [] and not v.has_legal_movement_moves(s)
+    assert v.generate_mark_targets(s) == [] and v.generate_movement_moves(s) == []
+    with pytest.raises(RuntimeError):            # HasLegalMovementMoves throws outside MOVEMENT (rule_engine.cpp:421-424)
+        v.has_legal_movement_moves(s)
     s2 = v.apply_placement_move(s, (2, 3))
     assert s2.board[2][3] == 1 and s2.current_player == v.Player.WHITE and s2.move_count == 0     # counters untouched
     s3 = v.apply_move_struct(s, v.MoveRecord.placement((2, 3)))

@@ -110,7 +110,9 @@ def test_root_search_noise_and_sampling_invariants():
 
     st = _playout_states(6, 32, every=4)
     b = st["board"].shape[0]
-    mcts = V1RootMCTS(_small_net(), V1RootMCTSConfig(num_simulations=32), DEV)
+    from liuzhou_b200.net import InferenceNet as _IN
+
+    mcts = V1RootMCTS(_IN(_small_net(), DEV, allow_library_convs=True), V1RootMCTSConfig(num_simulations=32), DEV)
     state = GpuStateBatch(*to_torch(st, DEV))
     force = torch.zeros(b, dtype=torch.bool, device=DEV)
     force[::3] = True
@@ -281,10 +283,14 @@ def test_fused_heads_kernel_vs_fp32_pytorch_heads(dims):
     assert net.heads is not None
     st = _playout_states(3, 5, every=2)
     n = st["board"].shape[0]
+    if not net.library_convs:                  # the tcgen05 path works on whole 64-board tiles: trim to a multiple of 64
+        n = n // 64 * 64
+        st = {k: v[:n] for k, v in st.items()}
     packed = native.pack_states(to_torch(st, DEV))
     from liuzhou_b200.tree import encode_inputs
 
-    x = encode_inputs(packed, "bf16_nhwc")
+    x = encode_inputs(packed, "bf16_nhwc") if net.library_convs else encode_inputs(packed, "bf16_nhwc",
+                                                                                     out=net.new_input(n))
     a = net.trunk(x)
     raw = net.heads(a, want_raw=True)
     # fp32 reference heads on the same (bf16) trunk activations
@@ -430,7 +436,10 @@ def test_self_play_tree_backend_policy_target_options():
     from liuzhou_b200.self_play import self_play_v1_gpu
 
     torch.manual_seed(5)
-    batch, stats = self_play_v1_gpu(_small_net(), num_games=16, mcts_simulations=12, temperature_init=1.0,
+    from liuzhou_b200.net import InferenceNet as _IN
+
+    small = _IN(_small_net(), DEV, allow_library_convs=True)
+    batch, stats = self_play_v1_gpu(small, num_games=16, mcts_simulations=12, temperature_init=1.0,
                                     temperature_final=0.1, temperature_threshold=6, exploration_weight=1.0, device=DEV,
                                     add_dirichlet_noise=True, max_game_plies=60, sample_moves=True, concurrent_games=16,
                                     search_backend="tree", policy_target_temperature=1.0,
@@ -440,7 +449,7 @@ def test_self_play_tree_backend_policy_target_options():
     assert torch.all((pol > 0) == legal)                               # full legal support, nothing outside
     assert torch.allclose(pol.sum(1), torch.ones(batch.num_samples, device=pol.device), atol=1e-4)
     torch.manual_seed(5)
-    base, _ = self_play_v1_gpu(_small_net(), num_games=16, mcts_simulations=12, temperature_init=1.0,
+    base, _ = self_play_v1_gpu(small, num_games=16, mcts_simulations=12, temperature_init=1.0,
                                temperature_final=0.1, temperature_threshold=6, exploration_weight=1.0, device=DEV,
                                add_dirichlet_noise=True, max_game_plies=60, sample_moves=True, concurrent_games=16,
                                search_backend="tree")
