@@ -598,15 +598,17 @@ def time_trunk_conv(net, n, stream, reps: int = 30) -> dict:
     # between the layers (a layer's prologue / weight prefetch overlaps the previous layer's epilogue)
     nb = len(net.trunk.model.blocks)
 
-    def chain():
-        xr, act = res, a
-        for i in range(nb):
-            h, _ = conv_bf16(act, t[f"wp1_{i}"], bias=t[f"bf1_{i}"], relu1=True)
-            last = i == nb - 1
-            sn, tn = ("trunk_s", "trunk_t") if last else (f"s1_{i + 1}", f"t1_{i + 1}")
-            xr, act = conv_bf16(h, t[f"wp2_{i}"], residual=xr, scale=t[sn], shift=t[tn], want_out1=not last, want_out2=True)
-
-    ms_chain = replay_ms(chain) / max(1, 2 * nb)
+    # The 20 trunk launches as they run in the forward -- the product's own FusedTrunk.__call__ on real channel-padded
+    # inputs: stem + (conv1, conv2) x 10 with programmatic dependent launch between the layers, X updated in place, three
+    # activation buffers.  The stem launch (K = 64) is timed alone in the same way and subtracted, so the figure is the
+    # average duration of a 3x3 128 -> 128 launch inside the chain.
+    x_in = net.new_input(n)
+    x_in[:, :11] = (torch.rand((n, 11, 6, 6), device=dev) > 0.6).to(torch.bfloat16)
+    xo1, xo2 = torch.empty_like(a), torch.empty_like(a)
+    ms_stem = replay_ms(lambda: conv_bf16(x_in, t["stem_wp"], bias=t["stem_bf"], relu1=True, scale=t["s1_0"],
+                                          shift=t["t1_0"], want_out2=True, out1=xo1, out2=xo2))
+    ms_trunk = replay_ms(lambda: net.trunk(x_in))
+    ms_chain = (ms_trunk - ms_stem) / max(1, 2 * nb)
     flops_per_state = 2.0 * 36 * 128 * 128 * 9
     ms = 0.5 * (ms1 + ms2)
     # per-launch DRAM traffic: read from the committed ncu --set full summary of this kernel (4,096-state launch), scaled by n
@@ -614,7 +616,8 @@ def time_trunk_conv(net, n, stream, reps: int = 30) -> dict:
     traffic = None if t4096 is None else t4096 * n / 4096.0
     return {"ms": ms, "ms_conv1": ms1, "ms_conv2": ms2, "tflops": n * flops_per_state / (ms / 1e3) / 1e12,
             "ms_in_chain": ms_chain, "tflops_in_chain": n * flops_per_state / (ms_chain / 1e3) / 1e12,
-            "launches_in_chain": 2 * nb, "flops_per_state": flops_per_state, "traffic_bytes": traffic,
+            "launches_in_chain": 2 * nb, "ms_stem_launch": ms_stem, "ms_trunk": ms_trunk,
+            "flops_per_state": flops_per_state, "traffic_bytes": traffic,
             "traffic_source": traffic_src}
 
 
