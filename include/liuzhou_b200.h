@@ -322,6 +322,16 @@ LZB_API int lzb_conv_bf16(const void *x, const void *w, int64_t n, int32_t cin, 
                           const void *residual, const float *scale, const float *shift, int32_t relu1, void *out1,
                           void *out2, void *stream);
 
+/* The whole ChessNet trunk + the heads' 1x1 convolution as ONE persistent kernel (csrc/lz_trunk.cu): replaces the stem
+ * conv, the 2 x blocks residual-block convs with their BatchNorm / ReLU / residual adds, and PolicyHead.conv1 +
+ * ValueHead.conv1 with their BatchNorm + ReLU (src/neural_network.py:83-96,98-151,213-259).  Activations stay in shared
+ * memory / tensor memory across all layers; the residual stream is kept in fp32.
+ * planes bf16 [n,6,6,64] (lzb_encode_inputs_packed layout 2); w_stem bf16 [9][128][64]; w_trunk bf16 [2*blocks*9+1][128][128]
+ * (conv1_0, conv2_0, ..., heads 1x1; tap-major, K-major rows, BatchNorm folded where it follows a conv); params f32
+ * [2*blocks+2][3][128] = bias | scale | shift per layer; out bf16 [n,6,6,128]. */
+LZB_API int lzb_trunk_bf16(const void *planes, int64_t n, const void *w_stem, const void *w_trunk, const float *params,
+                           int32_t blocks, void *out, void *stream);
+
 /* Fused network heads: everything of PolicyHead / ValueHead after their 1x1 convolutions
  * (src/neural_network.py:98-151: global pooling, gpool_linear, bn2 + relu, the three output convs,
  * log-softmax, value MLP) + bucket expectation (:201-210) + masked softmax over the legal actions of the

@@ -399,8 +399,8 @@ class FusedHeads:
         self._set("wfc2_t", pack_mma_b(f(vh.fc2.weight)))
         self._set("bfc2", f(vh.fc2.bias))
 
-    def __call__(self, a: torch.Tensor, states: Optional[torch.Tensor] = None, *, priors_out=None, values_out=None,
-                 want_raw: bool = False):
+    def __call__(self, a: Optional[torch.Tensor], states: Optional[torch.Tensor] = None, *, priors_out=None,
+                 values_out=None, want_raw: bool = False, pv: Optional[torch.Tensor] = None):
         """a: trunk output bf16 [n,C,6,6] channels-last.  With `states` (packed int64[n,4]) returns
         (priors f32[n,220], values f32[n]); with want_raw returns (log_p1, log_p2, log_pmc, value_logits) fp32."""
         import ctypes
@@ -408,9 +408,12 @@ class FusedHeads:
         from ._lib import check, i64, lib, ptr, stream_ptr
 
         t = self._t
-        n = a.size(0)
-        dev = a.device
-        if self.use_tc:
+        src = pv if pv is not None else a
+        n = src.size(0)
+        dev = src.device
+        if pv is not None:
+            pass                    # relu(bn1(conv1(a))) of both heads already computed (the fused trunk kernel's last layer)
+        elif self.use_tc:
             if n % 64 != 0:
                 raise RuntimeError("the tcgen05 network path works on whole 64-board tiles (n % 64 == 0)")
             pv, _ = conv_bf16(a, t["conv_wp"], bias=t["conv_bias"], relu1=True)
@@ -472,6 +475,13 @@ class InferenceNet:
             self.trunk.use_tc = False            # the tcgen05 path is all or nothing (trunk and heads convolutions)
             self.trunk._probe()
         self.flops_per_state = flops_per_state(self.model)
+        # LZB_TRUNK_IMPL: 1 (default) = the whole trunk + heads conv as ONE persistent kernel (csrc/lz_trunk.cu: activations
+        # stay in shared memory / TMEM across all layers); 0 = one kernel launch per convolution (csrc/lz_conv.cu)
+        self.fused_trunk = self._tc_ready() and os.environ.get("LZB_TRUNK_IMPL", "1") != "0"
+        self._ft = {}
+        self._pv = {}
+        if self.fused_trunk:
+            self._pack_fused_trunk()
         self.library_convs = not self._tc_ready()
         if self.library_convs and not allow_library_convs:
             raise RuntimeError(
@@ -491,6 +501,52 @@ class InferenceNet:
             p.requires_grad_(False)
         return m
 
+    def _pack_fused_trunk(self) -> None:
+        """Weights / per-layer epilogue parameters in the layout of lzb_trunk_bf16: w_trunk bf16 [(2*blocks*9 + 1), 128, 128]
+        = conv1_0, conv2_0, ..., conv2_{B-1} (9 taps each, BatchNorm folded where it follows the conv), heads 1x1;
+        params f32 [2*blocks + 2, 3, 128] = (bias | scale | shift) per layer: stem (stem_bn folded: bias; bn1_0: scale /
+        shift), conv1_i (bn2_i folded: bias), conv2_i (bn1_{i+1} or trunk_bn: scale / shift), heads conv (bn1 folded: bias)."""
+        t, h = self.trunk._t, self.heads._t
+        nb = len(self.model.blocks)
+        dev = self.device
+        ws = []
+        params = torch.zeros((2 * nb + 2, 3, 128), dtype=torch.float32, device=dev)
+        params[:, 1] = 1.0
+        params[0, 0], params[0, 1], params[0, 2] = t["stem_bf"], t["s1_0"], t["t1_0"]
+        for i in range(nb):
+            ws += [t[f"wp1_{i}"], t[f"wp2_{i}"]]
+            params[2 * i + 1, 0] = t[f"bf1_{i}"]
+            sn, tn = ("trunk_s", "trunk_t") if i == nb - 1 else (f"s1_{i + 1}", f"t1_{i + 1}")
+            params[2 * i + 2, 1], params[2 * i + 2, 2] = t[sn], t[tn]
+        ws.append(h["conv_wp"])
+        params[2 * nb + 1, 0] = h["conv_bias"]
+        w_trunk = torch.cat(ws, 0).contiguous()
+        for name, val in (("w_trunk", w_trunk), ("params", params.contiguous())):
+            if name in self._ft:
+                self._ft[name].copy_(val)          # in place: captured CUDA graphs stay valid
+            else:
+                self._ft[name] = val.clone()
+
+    def _trunk_heads_conv(self, x: torch.Tensor) -> torch.Tensor:
+        """planes bf16 [n,64,6,6] channels-last -> relu(bn(conv1)) of both heads, bf16 [n,128,6,6] channels-last: stem,
+        every residual block and the heads' 1x1 conv in ONE kernel launch (lzb_trunk_bf16)."""
+        import ctypes
+
+        from ._lib import check, i64, lib, ptr, stream_ptr
+
+        n = x.size(0)
+        if not (x.size(1) == 64 and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)):
+            raise RuntimeError("the fused trunk takes bf16 [n,64,6,6] channel-padded planes in channels_last format "
+                               f"(got {tuple(x.shape)}); use InferenceNet.new_input / InferenceNet.forward, which pad")
+        pv = self._pv.get(n)
+        if pv is None:
+            pv = self._pv[n] = torch.empty((n, 128, 6, 6), dtype=torch.bfloat16, device=x.device,
+                                           memory_format=torch.channels_last)
+        check(lib().lzb_trunk_bf16(ptr(x), i64(n), ptr(self.trunk._t["stem_wp"]), ptr(self._ft["w_trunk"]),
+                                   ptr(self._ft["params"]), ctypes.c_int32(len(self.model.blocks)), ptr(pv),
+                                   stream_ptr(x.device)))
+        return pv
+
     def load_state_dict(self, state_dict) -> None:
         """In-place weight refresh (e.g. after an NCCL broadcast); captured graphs stay valid."""
         own = self.model.state_dict()
@@ -502,12 +558,16 @@ class InferenceNet:
             self.trunk.refresh()
         if self.heads is not None:
             self.heads.refresh()
+        if self.fused_trunk:
+            self._pack_fused_trunk()
 
     @torch.no_grad()
     def _forward_eager(self, x: torch.Tensor):
         """-> fp32 (log_p1 [n,36], log_p2, log_pmc, value_logits [n,bins])."""
         if self.trunk is not None:
             with torch.cuda.device(self.device):
+                if self.fused_trunk:
+                    return self.heads(None, want_raw=True, pv=self._trunk_heads_conv(x))
                 a = self.trunk(x)
                 if self.heads is not None:
                     return self.heads(a, want_raw=True)
@@ -522,6 +582,9 @@ class InferenceNet:
         """Network + head post-processing for the tree search: bf16 planes [n,11,6,6] + packed states int64[n,4] ->
         (priors f32[n,220] = softmax over each state's legal actions, values f32[n] = bucket expectation)."""
         with torch.cuda.device(self.device):
+            if self.fused_trunk:
+                return self.heads(None, states, priors_out=priors_out, values_out=values_out,
+                                  pv=self._trunk_heads_conv(x))
             if self.trunk is not None and self.heads is not None:
                 return self.heads(self.trunk(x), states, priors_out=priors_out, values_out=values_out)
             from .tree import heads_to_priors

@@ -172,3 +172,39 @@ def test_no_library_convolution_for_any_batch_size():
     assert torch.equal(full.visit_counts, compact.visit_counts)
     assert torch.equal(full.chosen_action_indices, compact.chosen_action_indices)
     assert bool((compact.visit_counts[~active] == 0).all())
+
+
+@pytest.mark.parametrize("n,blocks", [(64, 1), (192, 2), (4096, 10), (130 * 64, 3)])
+def test_fused_trunk_kernel_matches_per_layer_path_and_fp32(n, blocks):
+    """lzb_trunk_bf16 (whole trunk + heads conv in one persistent kernel, activations resident in shared memory / TMEM,
+    fp32 residual stream) against the per-layer tcgen05 path (bf16 residual stream) and the fp32 PyTorch module on the
+    same positions: the fused kernel must be at least as close to fp32 as the per-layer path."""
+    from liuzhou_b200.net import ChessNet, InferenceNet
+
+    torch.manual_seed(17)
+    model = ChessNet(num_blocks=blocks)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0.0, 0.2)
+            m.running_var.uniform_(0.6, 1.4)
+            m.weight.data.uniform_(0.7, 1.3)
+            m.bias.data.normal_(0.0, 0.1)
+    net = InferenceNet(model, DEV)
+    assert net.fused_trunk
+    x = net.new_input(n)
+    planes = (torch.rand((n, 11, 6, 6), device=DEV) > 0.6).to(torch.bfloat16)
+    x[:, :11] = planes
+    fused = [o.clone() for o in net._forward_eager(x)]
+    again = [o.clone() for o in net._forward_eager(x)]
+    for a, b in zip(fused, again):
+        assert torch.equal(a, b)                                  # deterministic
+    net.fused_trunk = False
+    layered = [o.clone() for o in net._forward_eager(x)]
+    ref = model.to(DEV).float().eval()
+    with torch.no_grad():
+        out_ref = [o.float() for o in ref(planes.float())]
+    for f, l, r in zip(fused[:3], layered[:3], out_ref[:3]):
+        ef, el = (f.exp() - r.exp()).abs().max().item(), (l.exp() - r.exp()).abs().max().item()
+        assert ef <= max(1.5e-2, 1.2 * el), (ef, el)
+        assert (f.exp() - l.exp()).abs().max().item() <= 3e-2
+    torch.testing.assert_close(fused[3], out_ref[3].reshape(fused[3].shape), rtol=8e-2, atol=8e-2)
