@@ -42,10 +42,11 @@ constexpr int kBufRows = 136;                          // rows per chunk buffer 
 constexpr uint32_t kChunkBytes = kBufRows * 128;       // 17,408: [rows][64 ch] bf16, SWIZZLE_128B
 constexpr uint32_t kBoxBytes = kBoxRows * 128;         // 16,128 per TMA box
 constexpr uint32_t kCopyBytes = 2 * kChunkBytes;       // one dx copy, 128 channels
-constexpr uint32_t kWSliceBytes = 64 * 64 * 2;         // 8 KB: 64 couts (this CTA's half) x 64 cin of one tap
-constexpr int kWStages = 12;
-constexpr uint32_t kAccH = 0, kAccX = 128;             // TMEM column offsets of the two accumulators
-constexpr uint32_t kTrunkTmemCols = 256;
+constexpr int kCopyBufs = 4;                           // ring of copy buffers shared by the two tiles in flight
+constexpr uint32_t kWStageBytes = 2 * 64 * 64 * 2;     // 16 KB: one tap, this CTA's 64 couts x 128 cin (two 64-channel slices)
+constexpr int kWStages = 4;
+constexpr uint32_t kAccH = 0, kAccX = 128;             // TMEM column offsets inside a slot's 256 columns
+constexpr uint32_t kTrunkTmemCols = 512;               // 2 slots x (acc_h + acc_x)
 
 struct TrunkParams {
     const float* params;       // [layers][3][128] : bias | scale | shift
@@ -53,29 +54,46 @@ struct TrunkParams {
     int images;
     int blocks;                // residual blocks; layers = 2 * blocks + 2
     int debug;
+    unsigned long long* trace;   // debug bit 8: clock64 stamps of cluster 0's leader CTA ([0,4096) MMA thread, [4096,8192) epilogue warp 2)
 };
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
+
+// Job order of a cluster: its pair tiles k = 0 .. ntiles-1 are taken two at a time (slots 0 / 1); a round runs
+// layer 0 of slot 0, layer 0 of slot 1, layer 1 of slot 0, ...: while the tensor core works on one slot, the epilogue
+// warps turn the other slot's accumulator into its next operand.  Operand copies are numbered in consumption order
+// (3 per job, 1 for the 1x1 heads layer) and live in ring buffer number (copy index % 4).
+struct Sched {
+    int layers;
+    __device__ __forceinline__ int ncopies(int l) const { return l == layers - 1 ? 1 : 3; }
+    // copies of a round with ns slots that precede job (l, s)
+    __device__ __forceinline__ int before(int l, int s, int ns) const {
+        return l < layers - 1 ? ns * 3 * l + 3 * s : ns * 3 * (layers - 1) + s;
+    }
+    __device__ __forceinline__ int round_total(int ns) const { return ns * (3 * (layers - 1) + 1); }
+};
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTrunkThreads, 1)
 trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW0,
              const __grid_constant__ CUtensorMap tmW1, const TrunkParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t a_smem = base;                                    // 3 copies x 2 chunks
-    const uint32_t w_smem = a_smem + 3 * kCopyBytes;                 // weight ring
-    const uint32_t bar0 = w_smem + kWStages * kWSliceBytes;
-    const uint32_t in_full = bar0;                                   // leader: stem input copies landed
-    const uint32_t in_empty = in_full + 8;                           // both  : the tile's last MMAs are done
-    const uint32_t ready_bar = in_empty + 8;                         // [2] leader: chunk kc of the copies written (16 arrivals)
-    const uint32_t wfull_bar = ready_bar + 16;                       // [kWStages] leader
+    const uint32_t a_smem = base;                                    // kCopyBufs copy buffers x 2 chunks
+    const uint32_t w_smem = a_smem + kCopyBufs * kCopyBytes;         // weight ring
+    const uint32_t bar0 = w_smem + kWStages * kWStageBytes;
+    const uint32_t full_bar = bar0;                                  // [4] leader: copy buffer written (16 arrivals, or TMA)
+    const uint32_t empty_bar = full_bar + 8 * kCopyBufs;             // [4] both  : the MMAs that read the buffer are done
+    const uint32_t wfull_bar = empty_bar + 8 * kCopyBufs;            // [kWStages] leader
     const uint32_t wempty_bar = wfull_bar + 8 * kWStages;            // [kWStages] both
-    const uint32_t accfull_bar = wempty_bar + 8 * kWStages;          // both  : the layer's accumulator is complete
-    const uint32_t epidone_bar = accfull_bar + 8;                    // leader: last layer's accumulator drained (16 arrivals)
-    const uint32_t tmem_slot = epidone_bar + 8;
+    const uint32_t accfull_bar = wempty_bar + 8 * kWStages;          // [2] both  : a slot's accumulator is complete
+    const uint32_t epidone_bar = accfull_bar + 16;                   // [2] leader: a slot's last accumulator drained (16 arrivals)
+    const uint32_t tmem_slot = epidone_bar + 16;
     const uint32_t vec_smem = (tmem_slot + 16 + 15u) & ~15u;         // [2][3][128] f32 layer parameters, double buffered
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     float* vec = reinterpret_cast<float*>(gen + (vec_smem - base));
@@ -86,22 +104,25 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
     const int64_t pair_tiles = (P.images + 2 * kBoards - 1) / (2 * kBoards);
-    const int layers = 2 * P.blocks + 2;
+    const int ntiles = (int)((pair_tiles - cluster_id + num_clusters - 1) / num_clusters);   // pair tiles of this cluster
+    const int rounds = (ntiles + 1) / 2;
+    Sched sch;
+    sch.layers = 2 * P.blocks + 2;
+    const int layers = sch.layers;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmIn); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1);
-        mbar_init(in_full, 1); mbar_init(in_empty, 1);
-        mbar_init(ready_bar, 16); mbar_init(ready_bar + 8, 16);
+        for (int i = 0; i < kCopyBufs; ++i) { mbar_init(full_bar + 8 * i, 16); mbar_init(empty_bar + 8 * i, 1); }
         for (int i = 0; i < kWStages; ++i) { mbar_init(wfull_bar + 8 * i, 1); mbar_init(wempty_bar + 8 * i, 1); }
-        mbar_init(accfull_bar, 1); mbar_init(epidone_bar, 16);
+        for (int i = 0; i < 2; ++i) { mbar_init(accfull_bar + 8 * i, 1); mbar_init(epidone_bar + 8 * i, 16); }
         fence_barrier_init();
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTrunkTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    // the copies start out all zero: pad rows / columns are never written afterwards (or are rewritten with zeros)
-    for (uint32_t i = threadIdx.x; i < 3 * kCopyBytes / 16; i += kTrunkThreads)
+    // the copy buffers start out all zero: pad rows are never written afterwards, pad columns are rewritten with zeros
+    for (uint32_t i = threadIdx.x; i < kCopyBufs * kCopyBytes / 16; i += kTrunkThreads)
         *reinterpret_cast<uint4*>(gen + (a_smem - base) + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async();
     tc_fence_before();
@@ -113,100 +134,128 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
-        // ===================== TMA producer (both CTAs): stem input copies + every weight slice, in MMA order ===========
-        const uint32_t in_full_leader = mapa_rank(in_full, 0), wfull_leader = mapa_rank(wfull_bar, 0);
-        uint32_t wst = 0, wph = 0, tile_ph = 0;
-        for (int64_t pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
-            const int board0 = (int)(2 * pt + rank) * kBoards;
-            mbar_wait(in_empty, tile_ph ^ 1);                       // the previous tile no longer reads the copies
-            if (elect_one()) {
-                if (leader) mbar_arrive_expect_tx(in_full, 2 * 3 * kBoxBytes);
-#pragma unroll
-                for (int dxi = 0; dxi < 3; ++dxi)                   // planes (64-channel padded), chunk 0 of copy dx
-                    tma_tile4d_2sm(a_smem + dxi * kCopyBytes, &tmIn, in_full_leader, 0, dxi - 1, -1, board0);
-            }
-            __syncwarp();
-            tile_ph ^= 1;
+        // ===================== TMA producer (both CTAs): stem input copies + every weight tap, in MMA order =============
+        const uint32_t full_leader = mapa_rank(full_bar, 0), wfull_leader = mapa_rank(wfull_bar, 0);
+        uint32_t wst = 0, wph = 0;
+        int g_round = 0;                                             // copies before this round
+        for (int r = 0; r < rounds; ++r) {
+            const int ns = ntiles - 2 * r >= 2 ? 2 : 1;
             for (int l = 0; l < layers; ++l) {
-                const int taps = l == layers - 1 ? 1 : 9, kch = l == 0 ? 1 : 2;
-                const int tap_base = l == 0 ? 0 : (l - 1) * 9;       // index of the layer's first tap in its weight tensor
-                for (int kc = 0; kc < kch; ++kc) {
+                const int taps = l == layers - 1 ? 1 : 9;
+                for (int s = 0; s < ns; ++s) {
+                    if (l == 0) {                                    // the stem's three copies come from global memory
+                        const int64_t pt = cluster_id + (int64_t)(2 * r + s) * num_clusters;
+                        const int board0 = (int)(2 * pt + rank) * kBoards;
+                        const int g0 = g_round + sch.before(0, s, ns);
+                        for (int c = 0; c < 3; ++c) {
+                            const int g = g0 + c, buf = g & 3;
+                            mbar_wait(empty_bar + 8 * buf, (((uint32_t)g >> 2) & 1u) ^ 1u);
+                            if (elect_one()) {
+                                if (leader) {                        // 16 arrivals expected: 1 with the byte count + 15 plain
+                                    mbar_arrive_expect_tx(full_bar + 8 * buf, 2 * kBoxBytes);
+                                    mbar_arrive_n(full_bar + 8 * buf, 15);
+                                }
+                                tma_tile4d_2sm(a_smem + buf * kCopyBytes, &tmIn, full_leader + 8 * buf, 0, c - 1, -1, board0);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    const int tap_base = l == 0 ? 0 : (l - 1) * 9;
                     for (int t = 0; t < taps; ++t) {
-                        // MMA order within a chunk: dx-major, dy-minor; tap index in the weight tensor = (dy+1)*3 + (dx+1)
+                        // MMA order: dx-major, dy-minor; tap index in the weight tensor = (dy + 1) * 3 + (dx + 1)
                         const int tap = taps == 9 ? (t % 3) * 3 + (t / 3) : 0;
                         mbar_wait(wempty_bar + 8 * wst, wph ^ 1);
                         if (elect_one()) {
-                            if (leader) mbar_arrive_expect_tx(wfull_bar + 8 * wst, 2 * kWSliceBytes);
-                            if (l == 0)
-                                tma_tile2d_2sm(w_smem + wst * kWSliceBytes, &tmW0, wfull_leader + 8 * wst, 0,
-                                               tap * 128 + (int)rank * 64);
-                            else
-                                tma_tile2d_2sm(w_smem + wst * kWSliceBytes, &tmW1, wfull_leader + 8 * wst, kc * 64,
-                                               (tap_base + tap) * 128 + (int)rank * 64);
+                            const uint32_t dstw = w_smem + wst * kWStageBytes;
+                            if (P.debug & 32) {          // timing experiment: no weight loads, the MMAs read whatever is there
+                                if (leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wfull_bar + 8 * wst) : "memory");
+                            } else if (l == 0) {
+                                if (leader) mbar_arrive_expect_tx(wfull_bar + 8 * wst, 2 * 8192);
+                                tma_tile2d_2sm(dstw, &tmW0, wfull_leader + 8 * wst, 0, tap * 128 + (int)rank * 64);
+                            } else {
+                                if (leader) mbar_arrive_expect_tx(wfull_bar + 8 * wst, 2 * kWStageBytes);
+                                tma_tile2d_2sm(dstw, &tmW1, wfull_leader + 8 * wst, 0, (tap_base + tap) * 128 + (int)rank * 64);
+                                tma_tile2d_2sm(dstw + 8192, &tmW1, wfull_leader + 8 * wst, 64, (tap_base + tap) * 128 + (int)rank * 64);
+                            }
                         }
                         __syncwarp();
                         if (++wst == kWStages) { wst = 0; wph ^= 1; }
                     }
                 }
             }
+            g_round += sch.round_total(ns);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA) =====================
         if (leader) {
-            uint32_t wst = 0, wph = 0, tile_ph = 0, ready_ph = 0;
-            for (int64_t pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
-                mbar_wait_cluster(epidone_bar, tile_ph ^ 1);         // acc_h of the previous tile has been drained
-                mbar_wait(in_full, tile_ph);                         // stem input copies are in shared memory
-                tc_fence_after();
+            uint32_t wst = 0, wph = 0;
+            uint32_t acc_tile_ph[2] = {0, 0};
+            int g = 0;                                               // next copy to consume
+            int tr_m = 0;
+            for (int r = 0; r < rounds; ++r) {
+                const int ns = ntiles - 2 * r >= 2 ? 2 : 1;
                 for (int l = 0; l < layers; ++l) {
-                    const int taps = l == layers - 1 ? 1 : 9, kch = l == 0 ? 1 : 2;
+                    const int kch = l == 0 ? 1 : 2;
                     const bool conv2 = l >= 2 && l < layers - 1 && (l & 1) == 0;     // accumulates onto the residual stream
-                    const uint32_t d_tmem = tmem_base + (conv2 ? kAccX : kAccH);
-                    for (int kc = 0; kc < kch; ++kc) {
-                        if (l > 0) {                                 // chunk kc of the copies written by layer l - 1's epilogue
-                            mbar_wait_cluster(ready_bar + 8 * kc, ready_ph);
-                            tc_fence_after();
+                    for (int s = 0; s < ns; ++s) {
+                        if (l == 0) {                                // acc_h of this slot's previous tile has been drained
+                            mbar_wait_cluster(epidone_bar + 8 * s, acc_tile_ph[s] ^ 1);
+                            acc_tile_ph[s] ^= 1;
                         }
-                        for (int t = 0; t < taps; ++t) {
-                            const int dxi = taps == 9 ? t / 3 : 1, dyi = taps == 9 ? t % 3 : 1;
-                            mbar_wait(wfull_bar + 8 * wst, wph);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)s * 256u + (conv2 ? kAccX : kAccH);
+                        const int nc = sch.ncopies(l);
+                        for (int c = 0; c < nc; ++c, ++g) {
+                            const int buf = g & 3;
+                            const int dxi = nc == 3 ? c : 1;
+                            if (P.trace && blockIdx.x == 0 && lane == 0 && tr_m < 4090) P.trace[tr_m++] = clock64();   // before the copy wait
+                            mbar_wait_cluster(full_bar + 8 * buf, ((uint32_t)g >> 2) & 1u);
                             tc_fence_after();
-                            if (elect_one()) {
-                                const uint64_t adesc = umma_desc_sw128(a_smem + dxi * kCopyBytes + kc * kChunkBytes +
-                                                                       (uint32_t)(dyi * 6) * 128u);
-                                const uint64_t bdesc = umma_desc_sw128(w_smem + wst * kWSliceBytes);
+                            if (P.trace && blockIdx.x == 0 && lane == 0 && tr_m < 4090) P.trace[tr_m++] = clock64();   // copy ready
+                            for (int dyi = (nc == 3 ? 0 : 1); dyi < (nc == 3 ? 3 : 2); ++dyi) {
+                                mbar_wait(wfull_bar + 8 * wst, wph);
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    const bool first_tap = c == 0 && dyi == (nc == 3 ? 0 : 1);
+                                    const bool last_tap = c == nc - 1 && dyi == (nc == 3 ? 2 : 1);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    if (!(P.debug & 4))
-                                        umma_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, (uint32_t)(conv2 || (kc | t | k) != 0));
-                                umma_commit_2sm(wempty_bar + 8 * wst, 3);
-                                if (kc == kch - 1 && t == taps - 1) {
-                                    umma_commit_2sm(accfull_bar, 3);                 // the layer's accumulator is complete
-                                    if (l == layers - 1) umma_commit_2sm(in_empty, 3);   // ... and the copies are free
+                                    for (int kc = 0; kc < 2; ++kc) {
+                                        if (kc < kch) {
+                                            const uint64_t adesc = umma_desc_sw128(a_smem + buf * kCopyBytes + kc * kChunkBytes +
+                                                                                   (uint32_t)(dyi * 6) * 128u);
+                                            const uint64_t bdesc = umma_desc_sw128(w_smem + wst * kWStageBytes + kc * 8192);
+#pragma unroll
+                                            for (int k = 0; k < 4; ++k)
+                                                if (!(P.debug & 4))
+                                                    umma_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k,
+                                                             (uint32_t)(conv2 || !first_tap || (kc | k) != 0));
+                                        }
+                                    }
+                                    umma_commit_2sm(wempty_bar + 8 * wst, 3);
+                                    if (dyi == (nc == 3 ? 2 : 1)) umma_commit_2sm(empty_bar + 8 * buf, 3);   // copy consumed
+                                    if (last_tap) umma_commit_2sm(accfull_bar + 8 * s, 3);
+                                    (void)dxi;
                                 }
+                                __syncwarp();
+                                if (++wst == kWStages) { wst = 0; wph ^= 1; }
                             }
-                            __syncwarp();
-                            if (++wst == kWStages) { wst = 0; wph ^= 1; }
                         }
                     }
-                    if (l > 0) ready_ph ^= 1;
                 }
-                tile_ph ^= 1;
             }
         }
     } else {
         // ===================== epilogue: warps 2..9 =====================
-        // thread <-> accumulator row i = q * 32 + lane (TMEM lane quarter q = warp % 4), 32 of the 64 columns of the
-        // current chunk (col_half = (warp - 2) / 4).  Row i = b * 42 + y * 6 + x; rows with i % 42 >= 36 or b = 3 are junk.
+        // thread <-> accumulator row i = q * 32 + lane (TMEM lane quarter q = warp % 4) and 64 of the 128 columns
+        // (col_half = (warp - 2) / 4), handled 32 at a time.  Row i = b * 42 + y * 6 + x; i % 42 >= 36 or b = 3: junk.
         const int q = warp & 3, col_half = (warp - 2) >> 2;
         const int epi_tid = threadIdx.x - 64;
         const int i_row = q * 32 + lane;
         const int b = i_row / kBoardRows, rem = i_row - b * kBoardRows;
         const bool row_ok = b < kBoards && rem < 36;
         const int y = rem / 6, x = rem - y * 6;
-        // shared-memory targets of this pixel in the three copies: copy dx holds pixel (y, x' + dx) at (y, x'); the column
-        // x' that has no source (its neighbour is off the board) is written with zeros by the thread that wraps onto it
-        uint32_t dst[3], swz[3];
+        // position of this pixel in copy dx: copy dx holds pixel (y, x' + dx) at (y, x'); the column x' that has no source
+        // (its neighbour is off the board) is written with zeros by the thread that wraps onto it
+        uint32_t rowoff[3], swz[3];
         bool zero[3];
 #pragma unroll
         for (int dxi = 0; dxi < 3; ++dxi) {
@@ -214,115 +263,144 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
             zero[dxi] = xs < 0 || xs > 5;
             const int xp = (xs + 6) % 6;
             const int rho = b * kBoardRows + (y + 1) * 6 + xp;
-            dst[dxi] = a_smem + dxi * kCopyBytes + (uint32_t)rho * 128u;
+            rowoff[dxi] = (uint32_t)rho * 128u;
             swz[dxi] = (uint32_t)(rho & 7);
         }
-        const uint32_t ready_leader = mapa_rank(ready_bar, 0), epidone_leader = mapa_rank(epidone_bar, 0);
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        uint32_t acc_ph = 0;
-        // layer parameters: bias | scale | shift, 3 x 128 f32 per layer, double buffered in shared memory
-        for (int i = epi_tid; i < 384; i += 256) vec[i] = P.params[i];
-        for (int64_t pt = cluster_id; pt < pair_tiles; pt += num_clusters) {
-            const int board0 = (int)(2 * pt + rank) * kBoards;
+        const uint32_t full_leader = mapa_rank(full_bar, 0), epidone_leader = mapa_rank(epidone_bar, 0);
+        uint32_t acc_ph[2] = {0, 0};
+        int tr_e = 0;
+        for (int i = epi_tid; i < 384; i += 256) vec[i] = P.params[i];       // layer 0
+        int g_round = 0;
+        for (int r = 0; r < rounds; ++r) {
+            const int ns = ntiles - 2 * r >= 2 ? 2 : 1;
             for (int l = 0; l < layers; ++l) {
-                epi_bar_sync();                                        // everyone is done with layer l - 1: its buffer is free
-                {
-                    const int ln = l + 1 < layers ? l + 1 : 0;         // prefetch the next layer's parameters
-                    float* vn = vec + ((l + 1) & 1) * 384;
-                    for (int i = epi_tid; i < 384; i += 256) vn[i] = P.params[ln * 384 + i];
-                }
-                const float* vp = vec + (l & 1) * 384;
                 const bool last = l == layers - 1;
                 const bool conv2 = l >= 2 && !last && (l & 1) == 0;
                 const bool stem = l == 0;
-                const uint32_t acc_col = conv2 ? kAccX : kAccH;
-                const int ncopies_lo = l + 1 == layers - 1 ? 1 : 0, ncopies_hi = l + 1 == layers - 1 ? 2 : 3;   // 1x1 next: copy 0 only
-                mbar_wait(accfull_bar, acc_ph);
-                acc_ph ^= 1;
-                tc_fence_after();
-#pragma unroll 1
-                for (int kc = 0; kc < 2; ++kc) {
-                    const int c0 = kc * 64 + col_half * 32;            // first of this thread's 32 output channels
-                    uint32_t v[32];
-                    tmem_ld32(lane_addr + acc_col + (uint32_t)c0, v);
-                    tmem_ld_wait();
-                    uint32_t pk[16];
-                    const float4* vb = reinterpret_cast<const float4*>(vp + c0);            // bias  (broadcast reads)
-                    const float4* vs = reinterpret_cast<const float4*>(vp + 128 + c0);      // scale
-                    const float4* vt = reinterpret_cast<const float4*>(vp + 256 + c0);      // shift
-                    if (stem) {
-                        // x0 = relu(conv + bias) -> residual stream (fp32, TMEM); a0 = relu(scale * x0 + shift) -> copies
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bb = vb[j];
-                            v[4 * j] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j]) + bb.x, 0.0f));
-                            v[4 * j + 1] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.0f));
-                            v[4 * j + 2] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.0f));
-                            v[4 * j + 3] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.0f));
-                        }
-                        tmem_st32(lane_addr + kAccX + (uint32_t)c0, v);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 ss = vs[j], tt = vt[j];
-                            pk[2 * j] = pack_bf16(fmaxf(fmaf(ss.x, __uint_as_float(v[4 * j]), tt.x), 0.0f),
-                                                  fmaxf(fmaf(ss.y, __uint_as_float(v[4 * j + 1]), tt.y), 0.0f));
-                            pk[2 * j + 1] = pack_bf16(fmaxf(fmaf(ss.z, __uint_as_float(v[4 * j + 2]), tt.z), 0.0f),
-                                                      fmaxf(fmaf(ss.w, __uint_as_float(v[4 * j + 3]), tt.w), 0.0f));
-                        }
-                        tmem_st_wait();
-                    } else if (conv2) {
-                        // the accumulator IS x' = x + conv2(h); a' = relu(scale * x' + shift)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 ss = vs[j], tt = vt[j];
-                            pk[2 * j] = pack_bf16(fmaxf(fmaf(ss.x, __uint_as_float(v[4 * j]), tt.x), 0.0f),
-                                                  fmaxf(fmaf(ss.y, __uint_as_float(v[4 * j + 1]), tt.y), 0.0f));
-                            pk[2 * j + 1] = pack_bf16(fmaxf(fmaf(ss.z, __uint_as_float(v[4 * j + 2]), tt.z), 0.0f),
-                                                      fmaxf(fmaf(ss.w, __uint_as_float(v[4 * j + 3]), tt.w), 0.0f));
-                        }
-                    } else {
-                        // conv1 / heads conv: relu(acc + bias)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bb = vb[j];
-                            pk[2 * j] = pack_bf16(fmaxf(__uint_as_float(v[4 * j]) + bb.x, 0.0f),
-                                                  fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.0f));
-                            pk[2 * j + 1] = pack_bf16(fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.0f),
-                                                      fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.0f));
-                        }
+                for (int s = 0; s < ns; ++s) {
+                    epi_bar_sync();                                    // everyone has finished the previous job
+                    // the next layer's parameters: loaded now, stored after this job's work (latency off the critical path)
+                    float pre[2] = {0.0f, 0.0f};
+                    const bool prefetch = s == ns - 1;
+                    if (prefetch) {
+                        const int ln = l + 1 < layers ? l + 1 : 0;
+                        pre[0] = P.params[ln * 384 + epi_tid];
+                        if (epi_tid < 128) pre[1] = P.params[ln * 384 + 256 + epi_tid];
                     }
-                    if (last) {
-                        if (row_ok && board0 + b < P.images && !(P.debug & 1)) {
-                            uint4* o = reinterpret_cast<uint4*>(P.out + ((int64_t)(board0 + b) * 36 + rem) * 128 + c0);
+                    const float* vp = vec + (l & 1) * 384;
+                    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s * 256u;
+                    const uint32_t acc_col = conv2 ? kAccX : kAccH;
+                    const int64_t pt = cluster_id + (int64_t)(2 * r + s) * num_clusters;
+                    const int board0 = (int)(2 * pt + rank) * kBoards;
+                    if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 4090) P.trace[4096 + tr_e++] = clock64();   // waiting
+                    mbar_wait(accfull_bar + 8 * s, acc_ph[s]);
+                    acc_ph[s] ^= 1;
+                    tc_fence_after();
+                    if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 4090) P.trace[4096 + tr_e++] = clock64();   // accumulator ready
+                    // 1. the whole accumulator row segment (64 channels) -> registers -> bias / BatchNorm / ReLU -> bf16, ONCE:
+                    //    after this the accumulator is dead, so the slot's next MMAs may overwrite it at any time
+                    uint32_t pk[2][16];
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) o[t] = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int c0 = col_half * 64 + hh * 32;        // first of 32 output channels (chunk kc = col_half)
+                        uint32_t v[32];
+                        tmem_ld32(lane_addr + acc_col + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        const float4* vb = reinterpret_cast<const float4*>(vp + c0);            // bias  (broadcast reads)
+                        const float4* vs = reinterpret_cast<const float4*>(vp + 128 + c0);      // scale
+                        const float4* vt = reinterpret_cast<const float4*>(vp + 256 + c0);      // shift
+                        if (stem) {
+                            // x0 = relu(conv + bias) -> residual stream (fp32, TMEM); a0 = relu(scale * x0 + shift)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 bb = vb[j];
+                                v[4 * j] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j]) + bb.x, 0.0f));
+                                v[4 * j + 1] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.0f));
+                                v[4 * j + 2] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.0f));
+                                v[4 * j + 3] = __float_as_uint(fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.0f));
+                            }
+                            tmem_st32(lane_addr + kAccX + (uint32_t)c0, v);
                         }
-                    } else {
-                        if (row_ok) {
+                        if (stem || conv2) {
+                            // conv2: the accumulator IS x' = x + conv2(h); a' = relu(scale * x' + shift)
 #pragma unroll
-                            for (int dxi = 0; dxi < 3; ++dxi) {
-                                if (dxi < ncopies_lo || dxi >= ncopies_hi) continue;
-                                const uint32_t rowaddr = dst[dxi] + (uint32_t)kc * kChunkBytes;
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 ss = vs[j], tt = vt[j];
+                                pk[hh][2 * j] = pack_bf16(fmaxf(fmaf(ss.x, __uint_as_float(v[4 * j]), tt.x), 0.0f),
+                                                          fmaxf(fmaf(ss.y, __uint_as_float(v[4 * j + 1]), tt.y), 0.0f));
+                                pk[hh][2 * j + 1] = pack_bf16(fmaxf(fmaf(ss.z, __uint_as_float(v[4 * j + 2]), tt.z), 0.0f),
+                                                              fmaxf(fmaf(ss.w, __uint_as_float(v[4 * j + 3]), tt.w), 0.0f));
+                            }
+                        } else {
+                            // conv1 / heads conv: relu(acc + bias)
 #pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    const uint32_t c16 = (uint32_t)(col_half * 4 + t) ^ swz[dxi];
-                                    if (zero[dxi]) st_shared_v4(rowaddr + c16 * 16, 0u, 0u, 0u, 0u);
-                                    else st_shared_v4(rowaddr + c16 * 16, pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-                                }
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 bb = vb[j];
+                                pk[hh][2 * j] = pack_bf16(fmaxf(__uint_as_float(v[4 * j]) + bb.x, 0.0f),
+                                                          fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.0f));
+                                pk[hh][2 * j + 1] = pack_bf16(fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.0f),
+                                                              fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.0f));
                             }
                         }
-                        fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+                    }
+                    if (stem) tmem_st_wait();
+                    if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 4090) P.trace[4096 + tr_e++] = clock64();   // phase 1 done
+                    // 2. the operand copies of this slot's NEXT layer, in ring order, as their buffers become free -- or,
+                    //    after the last layer, the rows of the output tensor
+                    if (last) {
+                        if (row_ok && board0 + b < P.images && !(P.debug & 1)) {
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                uint4* o = reinterpret_cast<uint4*>(P.out + ((int64_t)(board0 + b) * 36 + rem) * 128 + col_half * 64 + hh * 32);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t)
+                                    o[t] = make_uint4(pk[hh][4 * t], pk[hh][4 * t + 1], pk[hh][4 * t + 2], pk[hh][4 * t + 3]);
+                            }
+                        }
+                    } else {
+                        const int nc = sch.ncopies(l + 1);
+                        const int g0 = g_round + sch.before(l + 1, s, ns);
+                        for (int c = 0; c < nc; ++c) {
+                            const int dxi = nc == 3 ? c : 1;
+                            const int g = g0 + c, buf = g & 3;
+                            mbar_wait(empty_bar + 8 * buf, (((uint32_t)g >> 2) & 1u) ^ 1u);      // its previous readers are done
+                            if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 4090) P.trace[4096 + tr_e++] = clock64();   // buffer free
+                            if (row_ok && !(P.debug & 16)) {
+                                // copy dx index is a loop variable: select this thread's row offset / swizzle / zero flag
+                                const uint32_t ro = dxi == 0 ? rowoff[0] : dxi == 1 ? rowoff[1] : rowoff[2];
+                                const uint32_t sw = dxi == 0 ? swz[0] : dxi == 1 ? swz[1] : swz[2];
+                                const bool zr = dxi == 0 ? zero[0] : dxi == 1 ? zero[1] : zero[2];
+                                const uint32_t rowaddr = a_smem + buf * kCopyBytes + (uint32_t)col_half * kChunkBytes + ro;
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                                    for (int t = 0; t < 4; ++t) {
+                                        const uint32_t c16 = (uint32_t)(hh * 4 + t) ^ sw;
+                                        if (zr) st_shared_v4(rowaddr + c16 * 16, 0u, 0u, 0u, 0u);
+                                        else st_shared_v4(rowaddr + c16 * 16, pk[hh][4 * t], pk[hh][4 * t + 1], pk[hh][4 * t + 2], pk[hh][4 * t + 3]);
+                                    }
+                            }
+                            fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_release_cluster(full_leader + 8 * buf);
+                            if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 4090) P.trace[4096 + tr_e++] = clock64();   // copy published
+                        }
+                    }
+                    if (last) {                           // acc_h has been read: this slot's next tile may overwrite it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_release_cluster(ready_leader + 8 * kc);
+                        if (lane == 0) mbar_arrive_release_cluster(epidone_leader + 8 * s);
+                    }
+                    if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 4090) P.trace[4096 + tr_e++] = clock64();   // job done
+                    if (prefetch) {
+                        float* vn = vec + ((l + 1) & 1) * 384;
+                        vn[epi_tid] = pre[0];
+                        if (epi_tid < 128) vn[256 + epi_tid] = pre[1];
                     }
                 }
-                if (last) {                           // acc_h has been read: the next tile's stem may overwrite it
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_release_cluster(epidone_leader);
-                }
             }
+            g_round += sch.round_total(ns);
         }
     }
 
@@ -340,6 +418,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 }  // namespace
 }  // namespace lzb
+
+static unsigned long long* g_trunk_trace = nullptr;
+// debug: copy the clock64 trace of the last launch (LZB_TRUNK_DEBUG & 8) to host memory (8192 u64)
+extern "C" __attribute__((visibility("default"))) int lzb_trunk_debug_trace(unsigned long long* host_out) {
+    if (!g_trunk_trace) return LZB_ERR_INVALID_ARGUMENT;
+    return cudaMemcpy(host_out, g_trunk_trace, 8192 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? LZB_OK : LZB_ERR_CUDA;
+}
 
 // planes bf16 [n,6,6,64] (channel-padded input), w_stem bf16 [9][128][64], w_trunk bf16 [2*blocks*9 + 1][128][128]
 // (conv1_0, conv2_0, ..., conv2_{blocks-1}, heads 1x1; BatchNorm folded where it follows a conv), params f32
@@ -387,8 +472,8 @@ extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem,
                                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (rc != CUDA_SUCCESS) { set_error("lzb_trunk: tensor map (weights %d) failed (%d)", which, (int)rc); return LZB_ERR_CUDA; }
     }
-    constexpr size_t smem = 1024 + 3 * (size_t)kCopyBytes + (size_t)kWStages * kWSliceBytes + 8 * (6 + 2 * kWStages) + 32 +
-                            2 * 384 * sizeof(float) + 256;
+    constexpr size_t smem = 1024 + (size_t)kCopyBufs * kCopyBytes + (size_t)kWStages * kWStageBytes +
+                            8 * (2 * kCopyBufs + 2 * kWStages + 4) + 32 + 2 * 384 * sizeof(float) + 256;
     static int sm_count[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("lzb_trunk: bad current device"); return LZB_ERR_CUDA; }
@@ -405,6 +490,8 @@ extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem,
     P.params = params; P.out = reinterpret_cast<__nv_bfloat16*>(out); P.images = (int)n; P.blocks = blocks;
     static const int debug = getenv("LZB_TRUNK_DEBUG") ? atoi(getenv("LZB_TRUNK_DEBUG")) : 0;
     P.debug = debug;
+    if ((debug & 8) && !g_trunk_trace) { cudaMalloc(&g_trunk_trace, 8192 * 8); cudaMemset(g_trunk_trace, 0, 8192 * 8); }
+    P.trace = g_trunk_trace;
     const int64_t pair_tiles = (n + 2 * kBoards - 1) / (2 * kBoards);
     const int clusters = (int)(pair_tiles < sm_count[dev] / 2 ? pair_tiles : sm_count[dev] / 2);
     cudaLaunchConfig_t cfg = {};

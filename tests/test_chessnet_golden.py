@@ -83,7 +83,7 @@ def test_bf16_tcgen05_forward_vs_reference_golden(tag):
     x = torch.from_numpy(oracle.states_to_model_input(st)).cuda()
     c0 = _lib.launch_count()
     outs = [o.float().cpu() for o in net.forward(x)]           # public path: pads 256 -> 256 rows, 11 -> 64 channels
-    assert _lib.launch_count() - c0 >= 23                       # 22 convolutions + the heads tail, all ours
+    assert _lib.launch_count() - c0 >= 2                        # the fused trunk kernel + the heads tail, both ours
     worst = {}
     for name, o in zip(("log_p1", "log_p2", "log_pmc"), outs[:3]):
         ref = torch.from_numpy(z[f"{tag}_{name}"])
