@@ -44,12 +44,11 @@ constexpr uint32_t kBoxBytes = kBoxRows * 128;         // 16,128 per TMA box
 constexpr uint32_t kCopyBytes = 2 * kChunkBytes;       // one dx copy, 128 channels
 constexpr int kCopyBufs = 4;                           // ring of copy buffers shared by the two tiles in flight
 constexpr uint32_t kWStageBytes = 2 * 64 * 64 * 2;     // 16 KB: one tap, this CTA's 64 couts x 128 cin (two 64-channel slices)
-constexpr int kWStages = 4;
+constexpr int kWStages = 5;
 constexpr uint32_t kAccH = 0, kAccX = 128;             // TMEM column offsets inside a slot's 256 columns
 constexpr uint32_t kTrunkTmemCols = 512;               // 2 slots x (acc_h + acc_x)
 
 struct TrunkParams {
-    const float* params;       // [layers][3][128] : bias | scale | shift
     __nv_bfloat16* out;        // [images * 36][128] : relu(heads conv + bias), the input of heads_tail_kernel
     int images;
     int blocks;                // residual blocks; layers = 2 * blocks + 2
@@ -57,10 +56,22 @@ struct TrunkParams {
     unsigned long long* trace;   // debug bit 8: clock64 stamps of cluster 0's leader CTA ([0,4096) MMA thread, [4096,8192) epilogue warp 2)
 };
 
+// Per-layer epilogue parameters in CONSTANT memory (warp-uniform reads through the constant cache: no shared-memory
+// traffic -- thread-side shared-memory accesses are starved while the tensor core streams its operands).  Compact layout:
+// stem: bias | scale | shift (384); conv1 of block i: bias (128); conv2 of block i: scale | shift (256); heads: bias (128).
+constexpr int kMaxBlocks = 10;
+constexpr int kTableFloats = 384 + kMaxBlocks * (128 + 256) + 128;      // 4,352 floats = 17 KB
+__constant__ float c_trunk_table[kTableFloats];      // refreshed from device memory in stream order before every launch
+__host__ __device__ __forceinline__ int table_offset(int l, int layers) {   // first float of layer l
+    if (l == 0) return 0;
+    if (l == layers - 1) return 384 + (layers - 2) / 2 * 384;
+    const int i = (l - 1) >> 1;
+    return 384 + i * 384 + ((l & 1) ? 0 : 128);
+}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 __device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
 }
@@ -94,9 +105,7 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     const uint32_t accfull_bar = wempty_bar + 8 * kWStages;          // [2] both  : a slot's accumulator is complete
     const uint32_t epidone_bar = accfull_bar + 16;                   // [2] leader: a slot's last accumulator drained (16 arrivals)
     const uint32_t tmem_slot = epidone_bar + 16;
-    const uint32_t vec_smem = (tmem_slot + 16 + 15u) & ~15u;         // [2][3][128] f32 layer parameters, double buffered
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-    float* vec = reinterpret_cast<float*>(gen + (vec_smem - base));
     volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,6 +118,10 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     Sched sch;
     sch.layers = 2 * P.blocks + 2;
     const int layers = sch.layers;
+    // Every cluster walks the 9 taps of a layer in its own rotation (copy order and dy order; the sum is order-free):
+    // the 74 clusters run nearly in lockstep, and without this they would all ask the L2 for the same 32 KB weight tap
+    // at the same moment (a handful of hot L2 slices); rotated, nine different taps are in demand at any time.
+    const int rot_c = cluster_id % 3, rot_d = (cluster_id / 3) % 3;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmIn); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1);
@@ -155,15 +168,16 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                                     mbar_arrive_expect_tx(full_bar + 8 * buf, 2 * kBoxBytes);
                                     mbar_arrive_n(full_bar + 8 * buf, 15);
                                 }
-                                tma_tile4d_2sm(a_smem + buf * kCopyBytes, &tmIn, full_leader + 8 * buf, 0, c - 1, -1, board0);
+                                tma_tile4d_2sm(a_smem + buf * kCopyBytes, &tmIn, full_leader + 8 * buf, 0, (c + rot_c) % 3 - 1, -1, board0);
                             }
                             __syncwarp();
                         }
                     }
                     const int tap_base = l == 0 ? 0 : (l - 1) * 9;
                     for (int t = 0; t < taps; ++t) {
-                        // MMA order: dx-major, dy-minor; tap index in the weight tensor = (dy + 1) * 3 + (dx + 1)
-                        const int tap = taps == 9 ? (t % 3) * 3 + (t / 3) : 0;
+                        // MMA order: copy-major, dy-minor (both rotated per cluster); tap index in the weight tensor =
+                        // (dy + 1) * 3 + (dx + 1)
+                        const int tap = taps == 9 ? ((t % 3 + rot_d) % 3) * 3 + (t / 3 + rot_c) % 3 : 0;
                         mbar_wait(wempty_bar + 8 * wst, wph ^ 1);
                         if (elect_one()) {
                             const uint32_t dstw = w_smem + wst * kWStageBytes;
@@ -211,12 +225,13 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                             mbar_wait_cluster(full_bar + 8 * buf, ((uint32_t)g >> 2) & 1u);
                             tc_fence_after();
                             if (P.trace && blockIdx.x == 0 && lane == 0 && tr_m < 4090) P.trace[tr_m++] = clock64();   // copy ready
-                            for (int dyi = (nc == 3 ? 0 : 1); dyi < (nc == 3 ? 3 : 2); ++dyi) {
+                            for (int d = 0; d < nc; ++d) {            // nc = 3: three dy taps per copy; heads conv: one tap (dy = 0)
+                                const int dyi = nc == 3 ? (d + rot_d) % 3 : 1;
                                 mbar_wait(wfull_bar + 8 * wst, wph);
                                 tc_fence_after();
                                 if (elect_one()) {
-                                    const bool first_tap = c == 0 && dyi == (nc == 3 ? 0 : 1);
-                                    const bool last_tap = c == nc - 1 && dyi == (nc == 3 ? 2 : 1);
+                                    const bool first_tap = c == 0 && d == 0;
+                                    const bool last_tap = c == nc - 1 && d == nc - 1;
 #pragma unroll
                                     for (int kc = 0; kc < 2; ++kc) {
                                         if (kc < kch) {
@@ -231,7 +246,7 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                                         }
                                     }
                                     umma_commit_2sm(wempty_bar + 8 * wst, 3);
-                                    if (dyi == (nc == 3 ? 2 : 1)) umma_commit_2sm(empty_bar + 8 * buf, 3);   // copy consumed
+                                    if (d == nc - 1) umma_commit_2sm(empty_bar + 8 * buf, 3);   // copy consumed
                                     if (last_tap) umma_commit_2sm(accfull_bar + 8 * s, 3);
                                     (void)dxi;
                                 }
@@ -248,7 +263,6 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
         // thread <-> accumulator row i = q * 32 + lane (TMEM lane quarter q = warp % 4) and 64 of the 128 columns
         // (col_half = (warp - 2) / 4), handled 32 at a time.  Row i = b * 42 + y * 6 + x; i % 42 >= 36 or b = 3: junk.
         const int q = warp & 3, col_half = (warp - 2) >> 2;
-        const int epi_tid = threadIdx.x - 64;
         const int i_row = q * 32 + lane;
         const int b = i_row / kBoardRows, rem = i_row - b * kBoardRows;
         const bool row_ok = b < kBoards && rem < 36;
@@ -269,7 +283,6 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
         const uint32_t full_leader = mapa_rank(full_bar, 0), epidone_leader = mapa_rank(epidone_bar, 0);
         uint32_t acc_ph[2] = {0, 0};
         int tr_e = 0;
-        for (int i = epi_tid; i < 384; i += 256) vec[i] = P.params[i];       // layer 0
         int g_round = 0;
         for (int r = 0; r < rounds; ++r) {
             const int ns = ntiles - 2 * r >= 2 ? 2 : 1;
@@ -278,16 +291,7 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                 const bool conv2 = l >= 2 && !last && (l & 1) == 0;
                 const bool stem = l == 0;
                 for (int s = 0; s < ns; ++s) {
-                    epi_bar_sync();                                    // everyone has finished the previous job
-                    // the next layer's parameters: loaded now, stored after this job's work (latency off the critical path)
-                    float pre[2] = {0.0f, 0.0f};
-                    const bool prefetch = s == ns - 1;
-                    if (prefetch) {
-                        const int ln = l + 1 < layers ? l + 1 : 0;
-                        pre[0] = P.params[ln * 384 + epi_tid];
-                        if (epi_tid < 128) pre[1] = P.params[ln * 384 + 256 + epi_tid];
-                    }
-                    const float* vp = vec + (l & 1) * 384;
+                    const float* tp = c_trunk_table + table_offset(l, layers);   // constant bank, warp-uniform addresses
                     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s * 256u;
                     const uint32_t acc_col = conv2 ? kAccX : kAccH;
                     const int64_t pt = cluster_id + (int64_t)(2 * r + s) * num_clusters;
@@ -306,9 +310,10 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                         uint32_t v[32];
                         tmem_ld32(lane_addr + acc_col + (uint32_t)c0, v);
                         tmem_ld_wait();
-                        const float4* vb = reinterpret_cast<const float4*>(vp + c0);            // bias  (broadcast reads)
-                        const float4* vs = reinterpret_cast<const float4*>(vp + 128 + c0);      // scale
-                        const float4* vt = reinterpret_cast<const float4*>(vp + 256 + c0);      // shift
+                        // stem: bias | scale | shift; conv1 / heads: bias; conv2: scale | shift
+                        const float4* vb = reinterpret_cast<const float4*>(tp + c0);
+                        const float4* vs = reinterpret_cast<const float4*>(tp + (stem ? 128 : 0) + c0);
+                        const float4* vt = reinterpret_cast<const float4*>(tp + (stem ? 256 : 128) + c0);
                         if (stem) {
                             // x0 = relu(conv + bias) -> residual stream (fp32, TMEM); a0 = relu(scale * x0 + shift)
 #pragma unroll
@@ -361,7 +366,7 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                         const int nc = sch.ncopies(l + 1);
                         const int g0 = g_round + sch.before(l + 1, s, ns);
                         for (int c = 0; c < nc; ++c) {
-                            const int dxi = nc == 3 ? c : 1;
+                            const int dxi = nc == 3 ? (c + rot_c) % 3 : 1;
                             const int g = g0 + c, buf = g & 3;
                             mbar_wait(empty_bar + 8 * buf, (((uint32_t)g >> 2) & 1u) ^ 1u);      // its previous readers are done
                             if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 4090) P.trace[4096 + tr_e++] = clock64();   // buffer free
@@ -393,11 +398,6 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                         if (lane == 0) mbar_arrive_release_cluster(epidone_leader + 8 * s);
                     }
                     if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 4090) P.trace[4096 + tr_e++] = clock64();   // job done
-                    if (prefetch) {
-                        float* vn = vec + ((l + 1) & 1) * 384;
-                        vn[epi_tid] = pre[0];
-                        if (epi_tid < 128) vn[256 + epi_tid] = pre[1];
-                    }
                 }
             }
             g_round += sch.round_total(ns);
@@ -427,13 +427,14 @@ extern "C" __attribute__((visibility("default"))) int lzb_trunk_debug_trace(unsi
 }
 
 // planes bf16 [n,6,6,64] (channel-padded input), w_stem bf16 [9][128][64], w_trunk bf16 [2*blocks*9 + 1][128][128]
-// (conv1_0, conv2_0, ..., conv2_{blocks-1}, heads 1x1; BatchNorm folded where it follows a conv), params f32
-// [2*blocks+2][3][128] (bias | scale | shift per layer), out bf16 [n,6,6,128] = relu(heads conv + bias).
+// (conv1_0, conv2_0, ..., conv2_{blocks-1}, heads 1x1; BatchNorm folded where it follows a conv), params f32 (DEVICE
+// memory, compact: stem bias | scale | shift (384), then per block conv1 bias (128) + conv2 scale | shift (256), then the
+// heads conv bias (128)), out bf16 [n,6,6,128] = relu(heads conv + bias).  blocks <= 10.
 extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem, const void* w_trunk, const float* params,
                               int32_t blocks, void* out, void* stream) {
     using namespace lzb;
     LZB_REQUIRE(n > 0 && n < (1ll << 30), "bad batch size");
-    LZB_REQUIRE(blocks >= 1 && blocks <= 64, "blocks must be in [1, 64]");
+    LZB_REQUIRE(blocks >= 1 && blocks <= kMaxBlocks, "blocks must be in [1, 10]");
     LZB_REQUIRE(planes && w_stem && w_trunk && params && out, "null pointer");
     LZB_REQUIRE(((reinterpret_cast<uintptr_t>(planes) | reinterpret_cast<uintptr_t>(w_stem) | reinterpret_cast<uintptr_t>(w_trunk) |
                   reinterpret_cast<uintptr_t>(out)) & 15) == 0, "pointers must be 16-byte aligned");
@@ -473,7 +474,7 @@ extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem,
         if (rc != CUDA_SUCCESS) { set_error("lzb_trunk: tensor map (weights %d) failed (%d)", which, (int)rc); return LZB_ERR_CUDA; }
     }
     constexpr size_t smem = 1024 + (size_t)kCopyBufs * kCopyBytes + (size_t)kWStages * kWStageBytes +
-                            8 * (2 * kCopyBufs + 2 * kWStages + 4) + 32 + 2 * 384 * sizeof(float) + 256;
+                            8 * (2 * kCopyBufs + 2 * kWStages + 4) + 32 + 256;
     static int sm_count[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("lzb_trunk: bad current device"); return LZB_ERR_CUDA; }
@@ -486,8 +487,16 @@ extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem,
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 2) sms = kNumSMs;
         sm_count[dev] = sms;
     }
+    // the parameter table goes to constant memory in stream order (device -> constant copy; a memcpy node under capture),
+    // so every launch -- also a graph replay after an in-place weight refresh, or another network on this stream -- sees
+    // its own current parameters
+    if (cudaMemcpyToSymbolAsync(c_trunk_table, params, sizeof(float) * (size_t)(384 + blocks * 384 + 128), 0,
+                                cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) {
+        set_error("lzb_trunk: parameter table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return LZB_ERR_CUDA;
+    }
     TrunkParams P;
-    P.params = params; P.out = reinterpret_cast<__nv_bfloat16*>(out); P.images = (int)n; P.blocks = blocks;
+    P.out = reinterpret_cast<__nv_bfloat16*>(out); P.images = (int)n; P.blocks = blocks;
     static const int debug = getenv("LZB_TRUNK_DEBUG") ? atoi(getenv("LZB_TRUNK_DEBUG")) : 0;
     P.debug = debug;
     if ((debug & 8) && !g_trunk_trace) { cudaMalloc(&g_trunk_trace, 8192 * 8); cudaMemset(g_trunk_trace, 0, 8192 * 8); }

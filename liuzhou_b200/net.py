@@ -477,7 +477,8 @@ class InferenceNet:
         self.flops_per_state = flops_per_state(self.model)
         # LZB_TRUNK_IMPL: 1 (default) = the whole trunk + heads conv as ONE persistent kernel (csrc/lz_trunk.cu: activations
         # stay in shared memory / TMEM across all layers); 0 = one kernel launch per convolution (csrc/lz_conv.cu)
-        self.fused_trunk = self._tc_ready() and os.environ.get("LZB_TRUNK_IMPL", "1") != "0"
+        self.fused_trunk = (self._tc_ready() and len(self.model.blocks) <= 10
+                            and os.environ.get("LZB_TRUNK_IMPL", "1") != "0")
         self._ft = {}
         self._pv = {}
         if self.fused_trunk:
@@ -504,24 +505,22 @@ class InferenceNet:
     def _pack_fused_trunk(self) -> None:
         """Weights / per-layer epilogue parameters in the layout of lzb_trunk_bf16: w_trunk bf16 [(2*blocks*9 + 1), 128, 128]
         = conv1_0, conv2_0, ..., conv2_{B-1} (9 taps each, BatchNorm folded where it follows the conv), heads 1x1;
-        params f32 [2*blocks + 2, 3, 128] = (bias | scale | shift) per layer: stem (stem_bn folded: bias; bn1_0: scale /
-        shift), conv1_i (bn2_i folded: bias), conv2_i (bn1_{i+1} or trunk_bn: scale / shift), heads conv (bn1 folded: bias)."""
+        params f32, compact: stem (stem_bn folded: bias; bn1_0: scale | shift), then per block conv1_i (bn2_i folded: bias)
+        and conv2_i (bn1_{i+1} or trunk_bn: scale | shift), then the heads conv (bn1 folded: bias)."""
         t, h = self.trunk._t, self.heads._t
         nb = len(self.model.blocks)
         dev = self.device
         ws = []
-        params = torch.zeros((2 * nb + 2, 3, 128), dtype=torch.float32, device=dev)
-        params[:, 1] = 1.0
-        params[0, 0], params[0, 1], params[0, 2] = t["stem_bf"], t["s1_0"], t["t1_0"]
+        parts = [t["stem_bf"], t["s1_0"], t["t1_0"]]               # stem: bias | scale | shift
         for i in range(nb):
             ws += [t[f"wp1_{i}"], t[f"wp2_{i}"]]
-            params[2 * i + 1, 0] = t[f"bf1_{i}"]
             sn, tn = ("trunk_s", "trunk_t") if i == nb - 1 else (f"s1_{i + 1}", f"t1_{i + 1}")
-            params[2 * i + 2, 1], params[2 * i + 2, 2] = t[sn], t[tn]
+            parts += [t[f"bf1_{i}"], t[sn], t[tn]]                   # conv1: bias; conv2: scale | shift
         ws.append(h["conv_wp"])
-        params[2 * nb + 1, 0] = h["conv_bias"]
+        parts.append(h["conv_bias"])                                 # heads conv: bias
         w_trunk = torch.cat(ws, 0).contiguous()
-        for name, val in (("w_trunk", w_trunk), ("params", params.contiguous())):
+        params = torch.cat([p_.float().reshape(-1) for p_ in parts]).to(dev).contiguous()
+        for name, val in (("w_trunk", w_trunk), ("params", params)):
             if name in self._ft:
                 self._ft[name].copy_(val)          # in place: captured CUDA graphs stay valid
             else:
