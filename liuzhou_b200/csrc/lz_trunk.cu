@@ -118,10 +118,11 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     Sched sch;
     sch.layers = 2 * P.blocks + 2;
     const int layers = sch.layers;
-    // Every cluster walks the 9 taps of a layer in its own rotation (copy order and dy order; the sum is order-free):
-    // the 74 clusters run nearly in lockstep, and without this they would all ask the L2 for the same 32 KB weight tap
-    // at the same moment (a handful of hot L2 slices); rotated, nine different taps are in demand at any time.
-    const int rot_c = cluster_id % 3, rot_d = (cluster_id / 3) % 3;
+    // Tap order (copy order and dy order inside a copy).  A per-cluster rotation was tried (so that the 74 clusters, which
+    // run nearly in lockstep, do not all ask the L2 for the same 32 KB weight tap at the same moment): no gain (877 us
+    // either way), and it made a board's fp32 summation order -- hence its low-order bits -- depend on WHERE in the batch
+    // it sits, which breaks the equality of compacted and full-batch searches.  Fixed order: results are position-free.
+    const int rot_c = 0, rot_d = 0;
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmIn); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1);

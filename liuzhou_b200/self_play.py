@@ -84,7 +84,8 @@ class _TreeWaveResult:
 
 def _play_wave_tree(tree_mcts: TreeMCTS, wave_games: int, *, temperature_init: float, temperature_final: float,
                     temperature_threshold: int, add_dirichlet_noise: bool, sample_moves: bool, opening_random_n: int,
-                    max_plies: int, soft_value_k: float, live_check_period: int = 4) -> _TreeWaveResult:
+                    max_plies: int, soft_value_k: float, live_check_period: int = 4,
+                    progress: Optional[list] = None) -> _TreeWaveResult:
     """One wave of ``wave_games`` games from the initial position to the end of every game, on the packed layout, with the
     reference's wave semantics (self_play_gpu_runner.py:159-256: every live game appends one row per ply, no refill,
     step / finalise rules of module.cpp:632-871) but WITHOUT a host round trip per ply:
@@ -120,6 +121,8 @@ def _play_wave_tree(tree_mcts: TreeMCTS, wave_games: int, *, temperature_init: f
     while ply < int(max_plies) + 1:
         if ply > 0 and ply % int(live_check_period) == 0:
             live_upper = int((~done).sum().item())   # the only host synchronisation of the loop
+            if progress is not None:
+                progress.append((ply, live_upper, time.perf_counter()))
             if live_upper == 0:
                 break
         if ply >= cap:                               # rare: a game longer than the preallocated block
@@ -135,6 +138,8 @@ def _play_wave_tree(tree_mcts: TreeMCTS, wave_games: int, *, temperature_init: f
                             float(temperature_final)).to(torch.float32)
         out = tree_mcts.search(states, active=active, temperatures=temps, add_dirichlet_noise=add_dirichlet_noise,
                                sample_moves=sample_moves, live_rows=live_upper)
+        if ply == 0:
+            tree_mcts.warm_buckets()                 # first use of this engine: capture the smaller wave batches once
         chosen = out.chosen_action_indices
         # legal-mask rows as the reference stores them: v0_core.encode_actions_fast semantics (no game-over check)
         legal_now = native.mask_words_to_bool(native.legal_masks(states, scalar_semantics=False)[0])

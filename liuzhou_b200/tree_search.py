@@ -84,32 +84,55 @@ class TreeMCTS:
         self._first_graph: Optional[torch.cuda.CUDAGraph] = None
         self._last_graph: Optional[torch.cuda.CUDAGraph] = None
         self.evals = 0
-        # leaf-batch compaction (set_live / search(live_rows=...)): wave graphs per batch bucket, captured on first use
-        self._rows: Optional[torch.Tensor] = None
+        # leaf-batch compaction (set_live / search(live_rows=...)): wave graphs per batch bucket, captured on first use.
+        # The row map lives in ONE tensor for the lifetime of the engine and is always attached to the tree (identity =
+        # no compaction): the kernels' arguments -- this pointer included -- are frozen into the captured CUDA graphs.
+        self._rows = torch.arange(self.num_trees, dtype=torch.int32, device=self.device)
+        self._live_set = False
+        self.tree.set_tree_rows(self._rows)
         self._bucket_graphs: dict = {}
         self._bucket = self.num_trees
+        self._buckets_warm = False
 
     # ---- leaf-batch compaction: the network only evaluates the live trees' leaves ----------------------------------
     def bucket_for(self, live: int) -> int:
-        """Smallest supported wave batch (in trees) that holds `live` trees: multiples of 64 up to 256, then of 256."""
+        """Smallest supported wave batch (in trees) that holds `live` trees: 64 / 128 / 256, then multiples of 256 (every
+        bucket is a pair of captured CUDA graphs; ``warm_buckets()`` captures the whole ladder once per engine)."""
         t = self.num_trees
         live = max(1, min(int(live), t))
-        step = 64 if live <= 256 else 256
-        b = -(-live // step) * step
+        if live <= 256:
+            b = 64
+            while b < live:
+                b *= 2
+        else:
+            b = -(-live // 256) * 256
         return t if b >= t else b
+
+    def bucket_ladder(self):
+        t = self.num_trees
+        return sorted({self.bucket_for(n) for n in [64, 128, 256] + list(range(512, t + 1, 256))} - {t})
+
+    def warm_buckets(self) -> None:
+        """Capture the wave graphs of every bucket of the ladder now (between two searches), so that a shrinking batch
+        never stops to capture in the middle of an iteration.  One-off cost per engine (~1 s at 4,096 trees); engines are
+        kept across iterations (self_play_v1_gpu(engine_cache=...), run_self_play_worker)."""
+        if not self.cfg.use_cuda_graph or self._wave_graph is None or self._buckets_warm:
+            return
+        for b in self.bucket_ladder():
+            self._graphs_for(b)
+        self._buckets_warm = True
 
     def set_live(self, active: Optional[torch.Tensor]) -> None:
         """active bool[T] (device) or None.  Live trees get the dense leaf-batch rows 0..n-1 (in tree order), the others
         sit the simulation waves out; no host synchronisation.  Pass an upper bound of n as search(live_rows=...)."""
         if active is None:
-            self.tree.set_tree_rows(None)
+            self._rows.copy_(torch.arange(self.num_trees, dtype=torch.int32, device=self.device))
+            self._live_set = False
             return
         act = active.to(device=self.device, dtype=torch.bool).view(-1)
-        if self._rows is None:
-            self._rows = torch.empty((self.num_trees,), dtype=torch.int32, device=self.device)
         rows = torch.cumsum(act.to(torch.int32), 0, dtype=torch.int32) - 1
         self._rows.copy_(torch.where(act, rows, torch.full_like(rows, -1)))
-        self.tree.set_tree_rows(self._rows)
+        self._live_set = True
 
     # one network evaluation of the pending leaves + expansion (+ backup).  On the tcgen05 path the network input is
     # the channel-padded bf16 [n,64,6,6] tensor and the select kernel writes it itself (one launch less per wave).
@@ -254,9 +277,11 @@ class TreeMCTS:
         trees that sit out were never used)."""
         cfg = self.cfg
         tree = self.tree
-        if live_rows is not None and tree._tree_rows is None:
+        if live_rows is not None and not self._live_set:
             raise RuntimeError("search(live_rows=...) needs set_live(active) first")
-        bucket = self.num_trees if (live_rows is None or tree._tree_rows is None) else self.bucket_for(live_rows)
+        if live_rows is None and self._live_set:
+            self.set_live(None)                 # a full-batch search: identity rows
+        bucket = self.num_trees if live_rows is None else self.bucket_for(live_rows)
         self._bucket = bucket
         keep = bool(cfg.reuse_subtree) and self._advanced      # roots already in place (advance() after the last move)
         self._advanced = False

@@ -13,9 +13,11 @@ import torch
 import oracle
 from tests._util import GOLDEN
 
-# tolerances of the bf16 product path against the fp32 reference (22 convolutions deep, bf16 activations):
-POLICY_PROB_ATOL = 1.5e-2      # max |softmax prob - reference prob| per head entry
-VALUE_ATOL = 3e-2              # |bucket expectation - reference| (values live in [-1, 1])
+# tolerances of the bf16 product path against the fp32 reference (22 convolutions deep, bf16 operands, fp32 accumulation
+# and fp32 residual stream in the fused trunk kernel).  Measured on B200: <= 4.6e-5 on the policy probabilities and
+# <= 2.3e-5 on the value for both weight sets; the bounds below are ~20x that.
+POLICY_PROB_ATOL = 1e-3        # max |softmax prob - reference prob| per head entry
+VALUE_ATOL = 1e-3              # |bucket expectation - reference| (values live in [-1, 1])
 
 
 def _golden():

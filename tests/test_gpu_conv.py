@@ -97,7 +97,7 @@ def test_trunk_and_heads_tc_path_matches_cudnn_path():
     out_pub = net.forward(x.float())                           # the public entry pads rows and channels itself
     for a, b in zip(out_tc, out_pub):
         assert torch.equal(a, b)
-    net.trunk.use_tc = net.heads.use_tc = False
+    net.trunk.use_tc = net.heads.use_tc = net.fused_trunk = False
     out_cudnn = [o.clone() for o in net._forward_eager(x)]
     ref = model.to(DEV).float().eval()
     with torch.no_grad():
@@ -146,7 +146,7 @@ def test_no_library_convolution_for_any_batch_size():
     x = (torch.rand((65_311, 11, 6, 6), device=DEV) > 0.6).float()
     net.forward(x)                                                         # warm-up (allocations)
     names = _kernel_names(lambda: net.forward(x))
-    assert sum(("conv_pad_kernel" in n or "conv_tc_kernel" in n) for n in names) >= 22 * 4             # 4 chunks of <= 16,384 rows
+    assert sum("trunk_kernel" in n for n in names) >= 4                    # 4 chunks of <= 16,384 rows, one launch each
     bad = [n for n in names if any(t in n.lower() for t in _LIBRARY_CONV)]
     assert not bad, sorted(set(bad))[:5]
 
@@ -158,7 +158,7 @@ def test_no_library_convolution_for_any_batch_size():
     out = mcts.search(pb.packed, temperatures=temps)                       # captures the graphs
     assert bool((out.visit_counts.sum(1)[~out.terminal_mask] == 6).all())
     names = _kernel_names(lambda: mcts.search(pb.packed, temperatures=temps))
-    assert sum(("conv_pad_kernel" in n or "conv_tc_kernel" in n) for n in names) >= 22 * 7
+    assert sum("trunk_kernel" in n for n in names) >= 7                    # root step + 6 waves
     bad = [n for n in names if any(t in n.lower() for t in _LIBRARY_CONV)]
     assert not bad, sorted(set(bad))[:5]
     # the same search with only 1,000 live trees compacts its waves to a 1,024-row batch and gives the same counts
@@ -167,7 +167,7 @@ def test_no_library_convolution_for_any_batch_size():
     full = mcts.search(pb.packed, active=active, temperatures=temps)
     mcts.set_live(active)
     compact = mcts.search(pb.packed, active=active, temperatures=temps, live_rows=1000)
-    assert mcts._bucket == 1024
+    assert mcts._bucket == 1024 and 1024 in mcts.bucket_ladder() and mcts.bucket_for(65) == 128
     mcts.set_live(None)
     assert torch.equal(full.visit_counts, compact.visit_counts)
     assert torch.equal(full.chosen_action_indices, compact.chosen_action_indices)
