@@ -327,11 +327,12 @@ LZB_API int lzb_conv_bf16(const void *x, const void *w, int64_t n, int32_t cin, 
  * ValueHead.conv1 with their BatchNorm + ReLU (src/neural_network.py:83-96,98-151,213-259).  Activations stay in shared
  * memory / tensor memory across all layers; the residual stream is kept in fp32.
  * planes bf16 [n,6,6,64] (lzb_encode_inputs_packed layout 2); w_stem bf16 [9][128][64]; w_trunk bf16 [2*blocks*9+1][128][128]
- * (conv1_0, conv2_0, ..., heads 1x1; tap-major, K-major rows, BatchNorm folded where it follows a conv); params f32 in
+ * (conv1_0, conv2_0, ..., heads 1x1; tap-major, K-major rows, BatchNorm folded where it follows a conv), stored w_copies
+ * times back to back (cluster c streams copy c % w_copies: spreads the L2 traffic of the hot weight lines); params f32 in
  * DEVICE memory, compact: stem bias | scale | shift (384), per block conv1 bias (128) + conv2 scale | shift (256), heads
  * conv bias (128) -- copied to constant memory in stream order at every launch; blocks <= 10; out bf16 [n,6,6,128]. */
-LZB_API int lzb_trunk_bf16(const void *planes, int64_t n, const void *w_stem, const void *w_trunk, const float *params,
-                           int32_t blocks, void *out, void *stream);
+LZB_API int lzb_trunk_bf16(const void *planes, int64_t n, const void *w_stem, const void *w_trunk, int32_t w_copies,
+                           const float *params, int32_t blocks, void *out, void *stream);
 
 /* Fused network heads: everything of PolicyHead / ValueHead after their 1x1 convolutions
  * (src/neural_network.py:98-151: global pooling, gpool_linear, bn2 + relu, the three output convs,

@@ -53,6 +53,7 @@ struct TrunkParams {
     int images;
     int blocks;                // residual blocks; layers = 2 * blocks + 2
     int debug;
+    int w_copies;              // the trunk weight tensor is stored w_copies times back to back; cluster c reads copy c % w_copies
     unsigned long long* trace;   // debug bit 8: clock64 stamps of cluster 0's leader CTA ([0,4096) MMA thread, [4096,8192) epilogue warp 2)
 };
 
@@ -152,6 +153,8 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
         const uint32_t full_leader = mapa_rank(full_bar, 0), wfull_leader = mapa_rank(wfull_bar, 0);
         uint32_t wst = 0, wph = 0;
         int g_round = 0;                                             // copies before this round
+        // replicated weights: clusters are spread over the copies so that fewer SMs pull the same L2 lines at once
+        const int w_row0 = (cluster_id % P.w_copies) * (P.blocks * 18 + 1) * 128;
         for (int r = 0; r < rounds; ++r) {
             const int ns = ntiles - 2 * r >= 2 ? 2 : 1;
             for (int l = 0; l < layers; ++l) {
@@ -189,8 +192,8 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                                 tma_tile2d_2sm(dstw, &tmW0, wfull_leader + 8 * wst, 0, tap * 128 + (int)rank * 64);
                             } else {
                                 if (leader) mbar_arrive_expect_tx(wfull_bar + 8 * wst, 2 * kWStageBytes);
-                                tma_tile2d_2sm(dstw, &tmW1, wfull_leader + 8 * wst, 0, (tap_base + tap) * 128 + (int)rank * 64);
-                                tma_tile2d_2sm(dstw + 8192, &tmW1, wfull_leader + 8 * wst, 64, (tap_base + tap) * 128 + (int)rank * 64);
+                                tma_tile2d_2sm(dstw, &tmW1, wfull_leader + 8 * wst, 0, w_row0 + (tap_base + tap) * 128 + (int)rank * 64);
+                                tma_tile2d_2sm(dstw + 8192, &tmW1, wfull_leader + 8 * wst, 64, w_row0 + (tap_base + tap) * 128 + (int)rank * 64);
                             }
                         }
                         __syncwarp();
@@ -431,11 +434,12 @@ extern "C" __attribute__((visibility("default"))) int lzb_trunk_debug_trace(unsi
 // (conv1_0, conv2_0, ..., conv2_{blocks-1}, heads 1x1; BatchNorm folded where it follows a conv), params f32 (DEVICE
 // memory, compact: stem bias | scale | shift (384), then per block conv1 bias (128) + conv2 scale | shift (256), then the
 // heads conv bias (128)), out bf16 [n,6,6,128] = relu(heads conv + bias).  blocks <= 10.
-extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem, const void* w_trunk, const float* params,
-                              int32_t blocks, void* out, void* stream) {
+extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem, const void* w_trunk, int32_t w_copies,
+                              const float* params, int32_t blocks, void* out, void* stream) {
     using namespace lzb;
     LZB_REQUIRE(n > 0 && n < (1ll << 30), "bad batch size");
     LZB_REQUIRE(blocks >= 1 && blocks <= kMaxBlocks, "blocks must be in [1, 10]");
+    LZB_REQUIRE(w_copies >= 1 && w_copies <= 64, "w_copies must be in [1, 64]");
     LZB_REQUIRE(planes && w_stem && w_trunk && params && out, "null pointer");
     LZB_REQUIRE(((reinterpret_cast<uintptr_t>(planes) | reinterpret_cast<uintptr_t>(w_stem) | reinterpret_cast<uintptr_t>(w_trunk) |
                   reinterpret_cast<uintptr_t>(out)) & 15) == 0, "pointers must be 16-byte aligned");
@@ -463,7 +467,7 @@ extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem,
     }
     for (int which = 0; which < 2; ++which) {
         const cuuint64_t cin = which == 0 ? 64 : 128;
-        const cuuint64_t rows = which == 0 ? 9 * 128 : ((cuuint64_t)blocks * 18 + 1) * 128;
+        const cuuint64_t rows = which == 0 ? 9 * 128 : ((cuuint64_t)blocks * 18 + 1) * 128 * (cuuint64_t)w_copies;
         const cuuint64_t dim[2] = {cin, rows};
         const cuuint64_t stride[1] = {cin * 2};
         const cuuint32_t box[2] = {64, 64};
@@ -497,7 +501,7 @@ extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem,
         return LZB_ERR_CUDA;
     }
     TrunkParams P;
-    P.out = reinterpret_cast<__nv_bfloat16*>(out); P.images = (int)n; P.blocks = blocks;
+    P.out = reinterpret_cast<__nv_bfloat16*>(out); P.images = (int)n; P.blocks = blocks; P.w_copies = w_copies;
     static const int debug = getenv("LZB_TRUNK_DEBUG") ? atoi(getenv("LZB_TRUNK_DEBUG")) : 0;
     P.debug = debug;
     if ((debug & 8) && !g_trunk_trace) { cudaMalloc(&g_trunk_trace, 8192 * 8); cudaMemset(g_trunk_trace, 0, 8192 * 8); }

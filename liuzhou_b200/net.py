@@ -518,7 +518,8 @@ class InferenceNet:
             parts += [t[f"bf1_{i}"], t[sn], t[tn]]                   # conv1: bias; conv2: scale | shift
         ws.append(h["conv_wp"])
         parts.append(h["conv_bias"])                                 # heads conv: bias
-        w_trunk = torch.cat(ws, 0).contiguous()
+        self.w_copies = max(1, int(os.environ.get("LZB_TRUNK_W_COPIES", "1")))
+        w_trunk = torch.cat(ws * self.w_copies, 0).contiguous()
         params = torch.cat([p_.float().reshape(-1) for p_ in parts]).to(dev).contiguous()
         for name, val in (("w_trunk", w_trunk), ("params", params)):
             if name in self._ft:
@@ -542,8 +543,8 @@ class InferenceNet:
             pv = self._pv[n] = torch.empty((n, 128, 6, 6), dtype=torch.bfloat16, device=x.device,
                                            memory_format=torch.channels_last)
         check(lib().lzb_trunk_bf16(ptr(x), i64(n), ptr(self.trunk._t["stem_wp"]), ptr(self._ft["w_trunk"]),
-                                   ptr(self._ft["params"]), ctypes.c_int32(len(self.model.blocks)), ptr(pv),
-                                   stream_ptr(x.device)))
+                                   ctypes.c_int32(self.w_copies), ptr(self._ft["params"]),
+                                   ctypes.c_int32(len(self.model.blocks)), ptr(pv), stream_ptr(x.device)))
         return pv
 
     def load_state_dict(self, state_dict) -> None:
