@@ -800,6 +800,12 @@ def run_selfplay(args, world, rank, local_rank):
     value = positions / (elapsed_ms / 1e3)
     evals = stepper.mcts.evals - evals0
 
+    if args.profile_only:
+        if rank == 0:
+            print(json.dumps({"metric": "selfplay_positions_per_sec", "value": value, "unit": "positions/s",
+                              "ms_per_step": elapsed_ms / args.steps, "gpu_launches": int(launches),
+                              "note": "--profile-only: device-timed steps only"}), flush=True)
+        raise SystemExit(0)
     # dominant kernel group: the network forward (PyTorch / cuDNN, bf16 tensor cores) at the wave batch size,
     # timed alone with CUDA events on its stream; the tree kernels are the remainder of the wave.
     slots = games * k
@@ -1300,6 +1306,8 @@ def main() -> int:
     ap.add_argument("--no-root-line", action="store_true", help="skip the extra root-PUCT iteration in the default line")
     ap.add_argument("--search", choices=["tree", "root"], default="tree",
                     help="tree: device-resident full tree (north_star, default); root: the reference's root-PUCT backend")
+    ap.add_argument("--profile-only", action="store_true",
+                    help="for ncu launch lists: only the device-timed steps (no e2e iteration, no reference / CPU legs)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-trees", type=int, default=256, help="--impl reference: concurrent games of the CPU session")
     ap.add_argument("--ref-budget", type=float, default=240.0, help="--impl reference: target wall time of the whole run (s)")

@@ -81,6 +81,16 @@ __device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
 // layer 0 of slot 0, layer 0 of slot 1, layer 1 of slot 0, ...: while the tensor core works on one slot, the epilogue
 // warps turn the other slot's accumulator into its next operand.  Operand copies are numbered in consumption order
 // (3 per job, 1 for the 1x1 heads layer) and live in ring buffer number (copy index % 4).
+// 2-D tiled load multicast to the CTAs of `mask` (same shared-memory offset in each); with cta_group::2 the bytes are
+// signalled on the barrier at this offset in the LEADER of each destination CTA's pair
+__device__ __forceinline__ void tma_tile2d_2sm_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%4, %5}], [%2], %3, %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "h"(mask), "r"(c0), "r"(c1), "l"(kL2Default)
+        : "memory");
+}
+
 struct Sched {
     int layers;
     __device__ __forceinline__ int ncopies(int l) const { return l == layers - 1 ? 1 : 3; }
@@ -91,9 +101,14 @@ struct Sched {
     __device__ __forceinline__ int round_total(int ns) const { return ns * (3 * (layers - 1) + 1); }
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTrunkThreads, 1)
+// CS = CTAs per cluster: 2 (one MMA pair) or 4 (two MMA pairs that walk the same weight stream in lockstep: every weight
+// box is fetched from L2 ONCE per cluster and multicast to the CTA of each pair that needs it -- the weight stream, not the
+// tensor core, bounds the 2-CTA variant: profiles/r02_trunk_decompose_*.txt).  The cluster size is set at launch.
+template <int CS>
+__global__ void __launch_bounds__(kTrunkThreads, 1)
 trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW0,
              const __grid_constant__ CUtensorMap tmW1, const TrunkParams P) {
+    constexpr int kPairs = CS / 2;                                   // MMA pairs per cluster
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_smem = base;                                    // kCopyBufs copy buffers x 2 chunks
@@ -110,12 +125,21 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t crank = cluster_ctarank();                        // rank in the cluster
+    const uint32_t rank = crank & 1u;                                // rank in the MMA pair
+    const uint32_t lead_rank = crank & ~1u;                          // the pair's leader CTA
+    const uint32_t pair_in_cluster = crank >> 1;
     const bool leader = rank == 0;
-    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    // "cluster_id" below is the index of this MMA PAIR, "num_clusters" the number of pairs: tiles are dealt to pairs
+    const int cluster_id = (int)(blockIdx.x / CS) * kPairs + (int)pair_in_cluster, num_clusters = (int)(gridDim.x / CS) * kPairs;
     const int64_t pair_tiles = (P.images + 2 * kBoards - 1) / (2 * kBoards);
-    const int ntiles = (int)((pair_tiles - cluster_id + num_clusters - 1) / num_clusters);   // pair tiles of this cluster
+    // pair tiles of this pair; in a 4-CTA cluster both pairs run the SAME number of jobs (lockstep on the weight stream):
+    // the surplus ones are dummy tiles (boards beyond the batch: zero input, no output)
+    const int ntiles = CS == 2 ? (int)((pair_tiles - cluster_id + num_clusters - 1) / num_clusters)
+                               : (int)((pair_tiles + num_clusters - 1) / num_clusters);
     const int rounds = (ntiles + 1) / 2;
+    const uint16_t pair_mask = (uint16_t)(3u << (2 * pair_in_cluster));      // commit multicast: the two CTAs of this pair
+    const uint16_t all_mask = (uint16_t)((1u << CS) - 1u);
     Sched sch;
     sch.layers = 2 * P.blocks + 2;
     const int layers = sch.layers;
@@ -128,7 +152,7 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmIn); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1);
         for (int i = 0; i < kCopyBufs; ++i) { mbar_init(full_bar + 8 * i, 16); mbar_init(empty_bar + 8 * i, 1); }
-        for (int i = 0; i < kWStages; ++i) { mbar_init(wfull_bar + 8 * i, 1); mbar_init(wempty_bar + 8 * i, 1); }
+        for (int i = 0; i < kWStages; ++i) { mbar_init(wfull_bar + 8 * i, 1); mbar_init(wempty_bar + 8 * i, kPairs); }
         for (int i = 0; i < 2; ++i) { mbar_init(accfull_bar + 8 * i, 1); mbar_init(epidone_bar + 8 * i, 16); }
         fence_barrier_init();
     }
@@ -150,7 +174,7 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs): stem input copies + every weight tap, in MMA order =============
-        const uint32_t full_leader = mapa_rank(full_bar, 0), wfull_leader = mapa_rank(wfull_bar, 0);
+        const uint32_t full_leader = mapa_rank(full_bar, lead_rank), wfull_leader = mapa_rank(wfull_bar, lead_rank);
         uint32_t wst = 0, wph = 0;
         int g_round = 0;                                             // copies before this round
         // replicated weights: clusters are spread over the copies so that fewer SMs pull the same L2 lines at once
@@ -187,13 +211,30 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                             const uint32_t dstw = w_smem + wst * kWStageBytes;
                             if (P.debug & 32) {          // timing experiment: no weight loads, the MMAs read whatever is there
                                 if (leader) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wfull_bar + 8 * wst) : "memory");
-                            } else if (l == 0) {
-                                if (leader) mbar_arrive_expect_tx(wfull_bar + 8 * wst, 2 * 8192);
-                                tma_tile2d_2sm(dstw, &tmW0, wfull_leader + 8 * wst, 0, tap * 128 + (int)rank * 64);
+                            } else if (CS == 2) {
+                                if (l == 0) {
+                                    if (leader) mbar_arrive_expect_tx(wfull_bar + 8 * wst, 2 * 8192);
+                                    tma_tile2d_2sm(dstw, &tmW0, wfull_leader + 8 * wst, 0, tap * 128 + (int)rank * 64);
+                                } else {
+                                    if (leader) mbar_arrive_expect_tx(wfull_bar + 8 * wst, 2 * kWStageBytes);
+                                    tma_tile2d_2sm(dstw, &tmW1, wfull_leader + 8 * wst, 0, w_row0 + (tap_base + tap) * 128 + (int)rank * 64);
+                                    tma_tile2d_2sm(dstw + 8192, &tmW1, wfull_leader + 8 * wst, 64, w_row0 + (tap_base + tap) * 128 + (int)rank * 64);
+                                }
                             } else {
-                                if (leader) mbar_arrive_expect_tx(wfull_bar + 8 * wst, 2 * kWStageBytes);
-                                tma_tile2d_2sm(dstw, &tmW1, wfull_leader + 8 * wst, 0, w_row0 + (tap_base + tap) * 128 + (int)rank * 64);
-                                tma_tile2d_2sm(dstw + 8192, &tmW1, wfull_leader + 8 * wst, 64, w_row0 + (tap_base + tap) * 128 + (int)rank * 64);
+                                // 4-CTA cluster: the 64-cout half this CTA needs is also needed by the CTA of the same parity in
+                                // the other pair.  Each of the two loads HALF of it (32 couts = box rows [32 q, 32 q + 32), q =
+                                // pair index) and multicasts to both; the bytes are counted on each destination pair's leader.
+                                const uint16_t mc = (uint16_t)(5u << rank);          // CTAs {rank, rank + 2}
+                                const int row_half = (int)rank * 64 + (int)pair_in_cluster * 32;
+                                const uint32_t dsth = dstw + pair_in_cluster * 4096;
+                                if (l == 0) {
+                                    if (leader) mbar_arrive_expect_tx(wfull_bar + 8 * wst, 2 * 8192);
+                                    tma_tile2d_2sm_mc(dsth, &tmW0, wfull_leader + 8 * wst, 0, tap * 128 + row_half, mc);
+                                } else {
+                                    if (leader) mbar_arrive_expect_tx(wfull_bar + 8 * wst, 2 * kWStageBytes);
+                                    tma_tile2d_2sm_mc(dsth, &tmW1, wfull_leader + 8 * wst, 0, w_row0 + (tap_base + tap) * 128 + row_half, mc);
+                                    tma_tile2d_2sm_mc(dsth + 8192, &tmW1, wfull_leader + 8 * wst, 64, w_row0 + (tap_base + tap) * 128 + row_half, mc);
+                                }
                             }
                         }
                         __syncwarp();
@@ -249,9 +290,9 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                                                              (uint32_t)(conv2 || !first_tap || (kc | k) != 0));
                                         }
                                     }
-                                    umma_commit_2sm(wempty_bar + 8 * wst, 3);
-                                    if (d == nc - 1) umma_commit_2sm(empty_bar + 8 * buf, 3);   // copy consumed
-                                    if (last_tap) umma_commit_2sm(accfull_bar + 8 * s, 3);
+                                    umma_commit_2sm(wempty_bar + 8 * wst, all_mask);             // every CTA that holds this stage
+                                    if (d == nc - 1) umma_commit_2sm(empty_bar + 8 * buf, pair_mask);   // copy consumed
+                                    if (last_tap) umma_commit_2sm(accfull_bar + 8 * s, pair_mask);
                                     (void)dxi;
                                 }
                                 __syncwarp();
@@ -284,7 +325,7 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
             rowoff[dxi] = (uint32_t)rho * 128u;
             swz[dxi] = (uint32_t)(rho & 7);
         }
-        const uint32_t full_leader = mapa_rank(full_bar, 0), epidone_leader = mapa_rank(epidone_bar, 0);
+        const uint32_t full_leader = mapa_rank(full_bar, lead_rank), epidone_leader = mapa_rank(epidone_bar, lead_rank);
         uint32_t acc_ph[2] = {0, 0};
         int tr_e = 0;
         int g_round = 0;
@@ -454,6 +495,9 @@ extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem,
         }
         encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
     }
+    // LZB_TRUNK_CLUSTER = 2 (default): clusters are single MMA pairs; 4: two pairs per cluster share one multicast
+    // weight stream (33 such clusters fit a B200: 132 of 148 SMs)
+    static const int cs = (getenv("LZB_TRUNK_CLUSTER") && atoi(getenv("LZB_TRUNK_CLUSTER")) == 4) ? 4 : 2;
     alignas(64) CUtensorMap tmIn, tmW0, tmW1;
     {
         const cuuint64_t dim[4] = {64, 6, 6, (cuuint64_t)n};
@@ -470,7 +514,7 @@ extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem,
         const cuuint64_t rows = which == 0 ? 9 * 128 : ((cuuint64_t)blocks * 18 + 1) * 128 * (cuuint64_t)w_copies;
         const cuuint64_t dim[2] = {cin, rows};
         const cuuint64_t stride[1] = {cin * 2};
-        const cuuint32_t box[2] = {64, 64};
+        const cuuint32_t box[2] = {64, (cuuint32_t)(cs == 4 ? 32 : 64)};      // 4-CTA clusters: each CTA loads half a box and multicasts
         const cuuint32_t estr[2] = {1, 1};
         const CUresult rc = encode_tiled(which == 0 ? &tmW0 : &tmW1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                                          const_cast<void*>(which == 0 ? w_stem : w_trunk), dim, stride, box, estr,
@@ -480,18 +524,42 @@ extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem,
     }
     constexpr size_t smem = 1024 + (size_t)kCopyBufs * kCopyBytes + (size_t)kWStages * kWStageBytes +
                             8 * (2 * kCopyBufs + 2 * kWStages + 4) + 32 + 256;
-    static int sm_count[64] = {0};
+    static int max_clusters[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("lzb_trunk: bad current device"); return LZB_ERR_CUDA; }
-    if (sm_count[dev] == 0) {
-        if (cudaFuncSetAttribute(trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    const void* kfn = cs == 4 ? (const void*)trunk_kernel<4> : (const void*)trunk_kernel<2>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kTrunkThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    if (max_clusters[dev] == 0) {
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             set_error("lzb_trunk: cannot raise dynamic shared memory to %zu", smem);
             return LZB_ERR_CUDA;
         }
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 2) sms = kNumSMs;
-        sm_count[dev] = sms;
+        int nc = sms / cs;
+        if (cs == 4) {      // how many 4-CTA clusters of this size are co-resident (GPC boundaries strand some SMs)
+            cfg.gridDim = dim3(sms / cs * cs);
+            cfg.numAttrs = 1;
+            int q = 0;
+            if (cudaOccupancyMaxActiveClusters(&q, kfn, &cfg) == cudaSuccess && q > 0) nc = q;
+        }
+        max_clusters[dev] = nc;
     }
+    TrunkParams P;
+    P.out = reinterpret_cast<__nv_bfloat16*>(out); P.images = (int)n; P.blocks = blocks; P.w_copies = w_copies;
+    static const int debug = getenv("LZB_TRUNK_DEBUG") ? atoi(getenv("LZB_TRUNK_DEBUG")) : 0;
+    P.debug = debug;
+    if ((debug & 8) && !g_trunk_trace) { cudaMalloc(&g_trunk_trace, 8192 * 8); cudaMemset(g_trunk_trace, 0, 8192 * 8); }
+    P.trace = g_trunk_trace;
     // the parameter table goes to constant memory in stream order (device -> constant copy; a memcpy node under capture),
     // so every launch -- also a graph replay after an in-place weight refresh, or another network on this stream -- sees
     // its own current parameters
@@ -500,24 +568,14 @@ extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem,
         set_error("lzb_trunk: parameter table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return LZB_ERR_CUDA;
     }
-    TrunkParams P;
-    P.out = reinterpret_cast<__nv_bfloat16*>(out); P.images = (int)n; P.blocks = blocks; P.w_copies = w_copies;
-    static const int debug = getenv("LZB_TRUNK_DEBUG") ? atoi(getenv("LZB_TRUNK_DEBUG")) : 0;
-    P.debug = debug;
-    if ((debug & 8) && !g_trunk_trace) { cudaMalloc(&g_trunk_trace, 8192 * 8); cudaMemset(g_trunk_trace, 0, 8192 * 8); }
-    P.trace = g_trunk_trace;
     const int64_t pair_tiles = (n + 2 * kBoards - 1) / (2 * kBoards);
-    const int clusters = (int)(pair_tiles < sm_count[dev] / 2 ? pair_tiles : sm_count[dev] / 2);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kTrunkThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, trunk_kernel, tmIn, tmW0, tmW1, P) != cudaSuccess) return check_launch("trunk_kernel");
+    const int64_t clusters_needed = (pair_tiles + cs / 2 - 1) / (cs / 2);
+    const int clusters = (int)(clusters_needed < max_clusters[dev] ? clusters_needed : max_clusters[dev]);
+    cfg.gridDim = dim3(cs * clusters);
+    cfg.numAttrs = 2;
+    cudaError_t le;
+    if (cs == 4) le = cudaLaunchKernelEx(&cfg, trunk_kernel<4>, tmIn, tmW0, tmW1, P);
+    else le = cudaLaunchKernelEx(&cfg, trunk_kernel<2>, tmIn, tmW0, tmW1, P);
+    (void)le;
     return check_launch("trunk_kernel");
 }
