@@ -147,6 +147,13 @@ __device__ __forceinline__ void tma_tile4d_2sm(uint32_t dst, const CUtensorMap* 
 __device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// The same signal with the default semantics (release at CTA scope: MEMBAR.ALL.CTA, i.e. this warp's shared-memory
+// stores have been performed, then the arrive leaves the SM).  `release.cluster` above compiles to MEMBAR.ALL.GPU +
+// ERRBAR + CGAERRBAR (~1,000 cycles per use, measured with the trunk kernel's clock64 trace).  This is the form
+// CUTLASS's ClusterBarrier::arrive(cta_id) uses for every cross-CTA pipeline hand-off.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"

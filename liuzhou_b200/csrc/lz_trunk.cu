@@ -54,6 +54,7 @@ struct TrunkParams {
     int blocks;                // residual blocks; layers = 2 * blocks + 2
     int debug;
     int w_copies;              // the trunk weight tensor is stored w_copies times back to back; cluster c reads copy c % w_copies
+    int w_stages;              // weight ring depth actually used (<= kWStages; fewer = latency experiment)
     unsigned long long* trace;   // debug bit 8: clock64 stamps of cluster 0's leader CTA ([0,4096) MMA thread, [4096,8192) epilogue warp 2)
 };
 
@@ -121,10 +122,17 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     const uint32_t accfull_bar = wempty_bar + 8 * kWStages;          // [2] both  : a slot's accumulator is complete
     const uint32_t epidone_bar = accfull_bar + 16;                   // [2] leader: a slot's last accumulator drained (16 arrivals)
     const uint32_t tmem_slot = epidone_bar + 16;
+    const uint32_t dummy_bar = tmem_slot + 8;                        // timing experiments only (debug bit 64)
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_p = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Copy hand-off epilogue -> MMA thread.  The operand copies are written with st.shared by the CTA whose OWN tensor
+    // core reads them (cta_group::2: every CTA's A rows come from its own shared memory), so what has to hold is that the
+    // stores were performed and fenced into the async proxy before the arrive leaves the SM: fence.proxy.async +
+    // an arrive with the default (release, CTA-scope) semantics = MEMBAR.ALL.CTA.  debug bit 256 switches back to
+    // release.cluster / acquire.cluster (MEMBAR.ALL.GPU + CCTL.IVALL: ~1,000 cycles per copy, 3 copies per job).
+    const bool strict_sync = (P.debug & 256) != 0;
     const uint32_t crank = cluster_ctarank();                        // rank in the cluster
     const uint32_t rank = crank & 1u;                                // rank in the MMA pair
     const uint32_t lead_rank = crank & ~1u;                          // the pair's leader CTA
@@ -153,6 +161,7 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
         prefetch_tmap(&tmIn); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1);
         for (int i = 0; i < kCopyBufs; ++i) { mbar_init(full_bar + 8 * i, 16); mbar_init(empty_bar + 8 * i, 1); }
         for (int i = 0; i < kWStages; ++i) { mbar_init(wfull_bar + 8 * i, 1); mbar_init(wempty_bar + 8 * i, kPairs); }
+        mbar_init(dummy_bar, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(accfull_bar + 8 * i, 1); mbar_init(epidone_bar + 8 * i, 16); }
         fence_barrier_init();
     }
@@ -216,9 +225,14 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                                     if (leader) mbar_arrive_expect_tx(wfull_bar + 8 * wst, 2 * 8192);
                                     tma_tile2d_2sm(dstw, &tmW0, wfull_leader + 8 * wst, 0, tap * 128 + (int)rank * 64);
                                 } else {
+                                    if (P.debug & 128) {   // timing experiment: half the weight bytes (results are garbage)
+                                        if (leader) mbar_arrive_expect_tx(wfull_bar + 8 * wst, 2 * 8192);
+                                        tma_tile2d_2sm(dstw, &tmW1, wfull_leader + 8 * wst, 0, w_row0 + (tap_base + tap) * 128 + (int)rank * 64);
+                                    } else {
                                     if (leader) mbar_arrive_expect_tx(wfull_bar + 8 * wst, 2 * kWStageBytes);
                                     tma_tile2d_2sm(dstw, &tmW1, wfull_leader + 8 * wst, 0, w_row0 + (tap_base + tap) * 128 + (int)rank * 64);
                                     tma_tile2d_2sm(dstw + 8192, &tmW1, wfull_leader + 8 * wst, 64, w_row0 + (tap_base + tap) * 128 + (int)rank * 64);
+                                    }
                                 }
                             } else {
                                 // 4-CTA cluster: the 64-cout half this CTA needs is also needed by the CTA of the same parity in
@@ -238,7 +252,7 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                             }
                         }
                         __syncwarp();
-                        if (++wst == kWStages) { wst = 0; wph ^= 1; }
+                        if (++wst == (uint32_t)P.w_stages) { wst = 0; wph ^= 1; }
                     }
                 }
             }
@@ -258,7 +272,8 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                     const bool conv2 = l >= 2 && l < layers - 1 && (l & 1) == 0;     // accumulates onto the residual stream
                     for (int s = 0; s < ns; ++s) {
                         if (l == 0) {                                // acc_h of this slot's previous tile has been drained
-                            mbar_wait_cluster(epidone_bar + 8 * s, acc_tile_ph[s] ^ 1);
+                            if (strict_sync) mbar_wait_cluster(epidone_bar + 8 * s, acc_tile_ph[s] ^ 1);
+                            else mbar_wait(epidone_bar + 8 * s, acc_tile_ph[s] ^ 1);
                             acc_tile_ph[s] ^= 1;
                         }
                         const uint32_t d_tmem = tmem_base + (uint32_t)s * 256u + (conv2 ? kAccX : kAccH);
@@ -267,7 +282,8 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                             const int buf = g & 3;
                             const int dxi = nc == 3 ? c : 1;
                             if (P.trace && blockIdx.x == 0 && lane == 0 && tr_m < 4090) P.trace[tr_m++] = clock64();   // before the copy wait
-                            mbar_wait_cluster(full_bar + 8 * buf, ((uint32_t)g >> 2) & 1u);
+                            if (strict_sync) mbar_wait_cluster(full_bar + 8 * buf, ((uint32_t)g >> 2) & 1u);
+                            else mbar_wait(full_bar + 8 * buf, ((uint32_t)g >> 2) & 1u);
                             tc_fence_after();
                             if (P.trace && blockIdx.x == 0 && lane == 0 && tr_m < 4090) P.trace[tr_m++] = clock64();   // copy ready
                             for (int d = 0; d < nc; ++d) {            // nc = 3: three dy taps per copy; heads conv: one tap (dy = 0)
@@ -291,13 +307,18 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                                         }
                                     }
                                     umma_commit_2sm(wempty_bar + 8 * wst, all_mask);             // every CTA that holds this stage
+                                    if (P.debug & 64) {   // timing experiment: what does a commit cost the issue stream?
+                                        umma_commit_2sm(dummy_bar, all_mask);
+                                        umma_commit_2sm(dummy_bar, all_mask);
+                                    }
                                     if (d == nc - 1) umma_commit_2sm(empty_bar + 8 * buf, pair_mask);   // copy consumed
                                     if (last_tap) umma_commit_2sm(accfull_bar + 8 * s, pair_mask);
                                     (void)dxi;
                                 }
                                 __syncwarp();
-                                if (++wst == kWStages) { wst = 0; wph ^= 1; }
+                                if (++wst == (uint32_t)P.w_stages) { wst = 0; wph ^= 1; }
                             }
+                            if (P.trace && blockIdx.x == 0 && lane == 0 && tr_m < 4090) P.trace[tr_m++] = clock64();   // taps of this copy issued
                         }
                     }
                 }
@@ -433,14 +454,20 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                             fence_proxy_async();          // generic-proxy stores -> visible to the tensor core (async proxy)
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive_release_cluster(full_leader + 8 * buf);
+                            if (lane == 0) {
+                                if (strict_sync) mbar_arrive_release_cluster(full_leader + 8 * buf);
+                                else mbar_arrive_remote(full_leader + 8 * buf);
+                            }
                             if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 4090) P.trace[4096 + tr_e++] = clock64();   // copy published
                         }
                     }
                     if (last) {                           // acc_h has been read: this slot's next tile may overwrite it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_release_cluster(epidone_leader + 8 * s);
+                        if (lane == 0) {
+                            if (strict_sync) mbar_arrive_release_cluster(epidone_leader + 8 * s);
+                            else mbar_arrive_remote(epidone_leader + 8 * s);
+                        }
                     }
                     if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 4090) P.trace[4096 + tr_e++] = clock64();   // job done
                 }
@@ -558,6 +585,8 @@ extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem,
     P.out = reinterpret_cast<__nv_bfloat16*>(out); P.images = (int)n; P.blocks = blocks; P.w_copies = w_copies;
     static const int debug = getenv("LZB_TRUNK_DEBUG") ? atoi(getenv("LZB_TRUNK_DEBUG")) : 0;
     P.debug = debug;
+    static const int w_stages = getenv("LZB_TRUNK_W_STAGES") ? atoi(getenv("LZB_TRUNK_W_STAGES")) : kWStages;
+    P.w_stages = w_stages >= 1 && w_stages <= kWStages ? w_stages : kWStages;
     if ((debug & 8) && !g_trunk_trace) { cudaMalloc(&g_trunk_trace, 8192 * 8); cudaMemset(g_trunk_trace, 0, 8192 * 8); }
     P.trace = g_trunk_trace;
     // the parameter table goes to constant memory in stream order (device -> constant copy; a memcpy node under capture),

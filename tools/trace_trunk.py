@@ -1,5 +1,6 @@
-"""Debug: clock64 timeline of the fused trunk kernel (cluster 0, leader CTA): MMA thread (before / after every operand-copy
-wait) and epilogue warp 2 (waiting / accumulator ready / job done).  Run with LZB_TRUNK_DEBUG=8."""
+"""Debug: clock64 timeline of the fused trunk kernel (cluster 0, leader CTA): MMA thread (before the operand-copy wait /
+copy ready / its taps issued) and epilogue warp 2 (waiting / accumulator ready / phase 1 done / (buffer free, copy
+published) x copies / job done).  Run with LZB_TRUNK_DEBUG=8 (+4 no MMAs, +16 no copy stores, +32 no weight loads)."""
 import ctypes
 import sys
 from pathlib import Path
@@ -27,14 +28,22 @@ t0 = m[0]
 m -= t0
 e -= t0
 print("MMA stamps", len(m), "epilogue stamps", len(e), "span cycles", int(max(m[-1], e[-1])))
-# MMA: pairs (before wait, after wait) per copy; 3 copies per 3x3 job
-waits = m[1::2] - m[0::2]
-print("MMA thread: total wait for operand copies", int(waits.sum()), "cycles of", int(m[-1]), "; mean per copy", float(waits.mean()))
-starts = m[1::2]
-print("copy-ready stamps, first 40:", starts[:40].tolist())
-print("copy waits, first 40:", waits[:40].tolist())
-# epilogue stamps per 3x3 job: waiting, ready, phase1 done, (buffer free, published) x 3, job done = 10 stamps
-# (jobs whose next layer is the heads conv have 1 copy = 6 stamps, the heads job itself has 4) -> print raw deltas of the first jobs
-d = np.diff(e)
-print("epilogue stamp deltas (first 64):", d[:64].tolist())
-print("epilogue stamps (first 12):", e[:12].tolist())
+k = len(m) // 3 * 3
+mm = m[:k].reshape(-1, 3)
+wait_copy = mm[:, 1] - mm[:, 0]
+issue = mm[:, 2] - mm[:, 1]
+print(f"MMA thread per copy (3 taps): wait for the copy mean {wait_copy.mean():.0f}, wait-for-weights + issue mean {issue.mean():.0f} cycles;"
+      f" totals {wait_copy.sum()} + {issue.sum()} of {m[-1]}")
+# steady state: copies 60..78 = jobs 20..25 (layers 10..12 of both slots in round 0)
+print("copy  t_before_wait  wait_copy  taps_issue")
+for i in range(60, 78):
+    print(f"{i:4d} {mm[i,0]:12d} {wait_copy[i]:9d} {issue[i]:9d}")
+# epilogue: a 3x3 -> 3x3 job has 10 stamps; the stem job and the jobs around the heads conv differ, so walk by pattern:
+# find jobs by matching against the MMA timeline is overkill -- print stamps 10 jobs from stamp 200 (deep inside round 0)
+print("epilogue stamps from job ~20 (10 per job: waiting, acc ready, phase1 done, free0, pub0, free1, pub1, free2, pub2, done):")
+for j in range(20, 26):
+    st = e[j * 10:(j + 1) * 10]
+    if len(st) < 10:
+        break
+    d = np.diff(st)
+    print(f"job {j}: start {st[0]:9d}  wait_acc {d[0]:6d} phase1 {d[1]:6d} | free0 {d[2]:6d} write0 {d[3]:6d} | free1 {d[4]:6d} write1 {d[5]:6d} | free2 {d[6]:6d} write2 {d[7]:6d} | end {d[8]:4d}")

@@ -26,7 +26,7 @@ print(f"{ms * 1e3:8.1f} us")
 '''
 names = {0: "full kernel", 16: "no copy stores (STS)", 32: "no weight loads", 48: "no STS, no weight loads", 4: "no MMAs",
          20: "no MMAs, no STS", 52: "no MMAs, no STS, no W loads (skeleton + TMEM loads)"}
-for bits, name in names.items():
+for bits, name in (names.items() if __name__ == "__main__" else ()):
     env = dict(os.environ, LZB_TRUNK_DEBUG=str(bits))
     r = subprocess.run([sys.executable, "-c", CHILD % str(ROOT)], env=env, capture_output=True, text=True)
     print(f"debug={bits:2d} ({name:52s}): {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)
