@@ -62,6 +62,46 @@ __device__ __forceinline__ uint64_t ballot36(bool lo_pred, bool hi_pred) {
     return (uint64_t)lo | ((uint64_t)hi << 32);
 }
 
+// The same load split in two, so that a kernel can have the NEXT state's loads in flight while it works on (and stores
+// the wide outputs of) the current one: under saturating write traffic a dependent load costs several thousand cycles.
+template <typename I>
+struct RawState {
+    int8_t blo, bhi;
+    uint8_t mblo, mbhi, mwlo, mwhi;
+    I phase, player, pm_req, pm_rem, pc_req, pc_rem, forced, move_count, msc;
+};
+template <typename I>
+__device__ __forceinline__ void warp_fetch_state(const lzb_states_in& st, int64_t b, int lane, RawState<I>& r) {
+    const int8_t* bp = st.board + b * 36;
+    const uint8_t* mbp = st.marks_black + b * 36;
+    const uint8_t* mwp = st.marks_white + b * 36;
+    const bool hi = lane < 4;
+    r.blo = bp[lane];
+    r.bhi = hi ? bp[32 + lane] : (int8_t)0;
+    r.mblo = mbp[lane]; r.mwlo = mwp[lane];
+    r.mbhi = hi ? mbp[32 + lane] : (uint8_t)0; r.mwhi = hi ? mwp[32 + lane] : (uint8_t)0;
+    r.phase = (I)st.phase[b];
+    r.player = (I)st.current_player[b];
+    r.pm_req = (I)st.pending_marks_required[b];
+    r.pm_rem = (I)st.pending_marks_remaining[b];
+    r.pc_req = (I)st.pending_captures_required[b];
+    r.pc_rem = (I)st.pending_captures_remaining[b];
+    r.forced = (I)st.forced_removals_done[b];
+    r.move_count = st.move_count ? (I)st.move_count[b] : (I)0;
+    r.msc = st.moves_since_capture ? (I)st.moves_since_capture[b] : (I)0;
+}
+template <typename I>
+__device__ __forceinline__ void warp_build_state(const RawState<I>& r, int lane, lz::State<I>& s) {
+    const bool hi = lane < 4;
+    s.black = ballot36(r.blo == 1, hi && r.bhi == 1);
+    s.white = ballot36(r.blo == -1, hi && r.bhi == -1);
+    s.other = ballot36(r.blo != 0 && r.blo != 1 && r.blo != -1, hi && r.bhi != 0 && r.bhi != 1 && r.bhi != -1);
+    s.mb = ballot36(r.mblo != 0, hi && r.mbhi != 0);
+    s.mw = ballot36(r.mwlo != 0, hi && r.mwhi != 0);
+    s.phase = r.phase; s.player = r.player; s.pm_req = r.pm_req; s.pm_rem = r.pm_rem; s.pc_req = r.pc_req;
+    s.pc_rem = r.pc_rem; s.forced = r.forced; s.move_count = r.move_count; s.msc = r.msc;
+}
+
 // Load one state in the reference byte layout into bitboards, one warp per state.
 template <typename I>
 __device__ __forceinline__ void warp_load_state(const lzb_states_in& st, int64_t b, int lane, lz::State<I>& s,

@@ -23,14 +23,46 @@ encode_actions_kernel(lzb_states_in st, int64_t B, int pd, int md, int sd, int a
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
     const int total = pd + md + sd + ad;
+    const bool standard = pd == 36 && md == 144 && sd == 36 && ad == 4;
+    RawState<int> nxt;
+    if (warp < B) warp_fetch_state<int>(st, warp, lane, nxt);
     for (int64_t b = warp; b < B; b += nwarps) {
+        const RawState<int> cur = nxt;
+        if (b + nwarps < B) warp_fetch_state<int>(st, b + nwarps, lane, nxt);   // in flight during this state's 3.7 KB of stores
         State<int> s;
-        int8_t blo, bhi;
-        warp_load_state<int>(st, b, lane, s, blo, bhi);
+        warp_build_state<int>(cur, lane, s);
         Legal L;
         legal_actions<int, false>(s, L, ad > 0);
         uint8_t* m = mask + b * total;
         int4* meta = reinterpret_cast<int4*>(metadata) + b * total;
+        if (standard) {
+            // the reference's own dims (36 / 144 / 36 / 4): regions cannot overlap, 220 = 6 x 32 + 28 actions
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const int a = lane + 32 * j;
+                if (j == 6 && a >= 220) break;
+                int4 code = make_int4(-1, -1, -1, -1);
+                bool legal;
+                if (a < 36) {
+                    legal = (L.place >> a) & 1;
+                    if (legal) code = make_int4(kActPlace, a, -1, -1);
+                } else if (a < 180) {
+                    const int mo = a - 36, from = mo >> 2, d = mo & 3;
+                    const uint64_t mvd = d == 0 ? L.mv[0] : d == 1 ? L.mv[1] : d == 2 ? L.mv[2] : L.mv[3];
+                    legal = (mvd >> from) & 1;
+                    if (legal) code = make_int4(kActMove, from, d, from + (d == 0 ? -6 : d == 1 ? 6 : d == 2 ? -1 : 1));
+                } else if (a < 216) {
+                    legal = (L.sel >> (a - 180)) & 1;
+                    if (legal) code = make_int4(L.sel_kind, a - 180, -1, -1);
+                } else {
+                    legal = a == 216 && L.process;
+                    if (legal) code = make_int4(kActProcess, -1, -1, -1);
+                }
+                m[a] = legal ? 1 : 0;
+                meta[a] = code;
+            }
+            continue;
+        }
         const int sel_off = pd + md, rem_idx = pd + md + sd;
         for (int a = lane; a < total; a += 32) {
             // Region resolution in the reference's write order (placement, movement, selection, removal;
@@ -113,46 +145,57 @@ apply_moves_kernel(lzb_states_in in, int64_t B, const int32_t* __restrict__ code
     }
 }
 
-// Thread-per-action variant for large batches.  A warp per action keeps only 64 actions in flight per SM and one
-// action's dependent loads cost ~9 us, i.e. ~1 action/ns for the whole chip (6 % of the HBM roof at 384 B/action);
-// with one THREAD per action 2,048 actions per SM are in flight.  Each thread gathers its parent's 3 x 36 bytes as
-// 27 aligned 32-bit words, builds the bitboards with byte tests, applies the action with the same apply_action()
-// and writes the child's bytes back as words (children of consecutive threads are contiguous in memory).
+// Byte <-> bit conversions, four cells at a time.  gather4: the low bit of each byte of x (x & 0x01010101 == x) -> a nibble;
+// scatter4: a nibble -> 0x00/0x01 bytes.  Both are one multiplication by 2^0 + 2^7 + 2^14 + 2^21: the sixteen partial
+// products land on distinct bit positions (no carries), the wanted ones on 21..24 resp. 0, 8, 16, 24.
+__device__ __forceinline__ uint32_t gather4(uint32_t x01) { return ((x01 * 0x00204081u) >> 21) & 0xFu; }
+__device__ __forceinline__ uint32_t scatter4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 __device__ __forceinline__ void words_to_boards(const uint32_t (&bw)[9], uint64_t& black, uint64_t& white, uint64_t& other) {
     black = white = other = 0;
 #pragma unroll
-    for (int w = 0; w < 9; ++w)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t byte = (bw[w] >> (8 * k)) & 0xFFu;
-            const uint64_t bit = 1ULL << (4 * w + k);
-            if (byte == 1u) black |= bit;
-            else if (byte == 0xFFu) white |= bit;
-            else if (byte != 0u) other |= bit;
-        }
+    for (int w = 0; w < 9; ++w) {
+        const uint32_t is_b = __vcmpeq4(bw[w], 0x01010101u), is_w = __vcmpeq4(bw[w], 0xFFFFFFFFu);   // 0xFF per equal byte
+        const uint32_t is_o = __vcmpne4(bw[w], 0u) & ~(is_b | is_w);
+        black |= (uint64_t)gather4(is_b & 0x01010101u) << (4 * w);
+        white |= (uint64_t)gather4(is_w & 0x01010101u) << (4 * w);
+        other |= (uint64_t)gather4(is_o & 0x01010101u) << (4 * w);
+    }
 }
 __device__ __forceinline__ uint64_t words_to_marks(const uint32_t (&mw)[9]) {
     uint64_t m = 0;
 #pragma unroll
-    for (int w = 0; w < 9; ++w)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if ((mw[w] >> (8 * k)) & 0xFFu) m |= 1ULL << (4 * w + k);
+    for (int w = 0; w < 9; ++w) m |= (uint64_t)gather4(__vcmpne4(mw[w], 0u) & 0x01010101u) << (4 * w);
     return m;
 }
+// the child's bytes of cells 4w..4w+3: +1 / -1 from the bitboards, any other original byte carried over where `other` is set
+__device__ __forceinline__ uint32_t board_word(const State<long long>& s, uint32_t orig, int w) {
+    const uint32_t b = scatter4((uint32_t)(s.black >> (4 * w)) & 0xFu), wh = scatter4((uint32_t)(s.white >> (4 * w)) & 0xFu),
+                   o = scatter4((uint32_t)(s.other >> (4 * w)) & 0xFu);
+    return b | (wh * 0xFFu) | (orig & (o * 0xFFu) & ~((b | wh) * 0xFFu));
+}
 
+// Thread-per-action variant for large batches.  A warp per action keeps only 64 actions in flight per SM and one
+// action's dependent loads cost ~9 us, i.e. ~1 action/ns for the whole chip (6 % of the HBM roof at 384 B/action);
+// with one THREAD per action 2,048 actions per SM are in flight.  Each thread gathers its parent's 3 x 36 bytes as
+// 27 aligned 32-bit words, builds the bitboards four cells per multiplication, applies the action with the same
+// apply_action() and hands the child's 27 words to its warp through shared memory, so that the 32 children of a warp
+// (3 x 1,152 contiguous bytes when the output rows are the action indices) leave as fully coalesced 16-byte stores --
+// written directly by the threads, a warp's store instruction touches 36 sectors for 128 bytes.
+constexpr int kStageWords = 32 * 9;                     // one byte tensor's words of a warp's 32 children
 template <bool kInplace>
 __global__ void __launch_bounds__(kThreads, 3)
 apply_moves_thread_kernel(lzb_states_in in, int64_t B, const int32_t* __restrict__ codes, const int64_t* __restrict__ parents,
-                          int64_t N, lzb_states_out out) {
+                          int64_t N, lzb_states_out out, int vec_ok) {
+    __shared__ __align__(16) uint32_t stage[kInplace ? 1 : kWarpsPerBlock][kInplace ? 1 : 3][kInplace ? 4 : kStageWords];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-        const int64_t p = parents[i];
-        if (p < 0 || p >= B) continue;                         // :584-587 / :770-773
-        uint32_t bw[9];                                        // kept: bytes outside -1 / 0 / +1 are carried over
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < N; i0 += stride) {
+        const int64_t i = i0 + lane;
+        const int64_t p = i < N ? parents[i] : -1;
+        const bool live = p >= 0 && p < B;                     // :584-587 / :770-773: other rows are left untouched
+        uint32_t bw[9], mbw[9], mww[9];
         State<long long> s;
-        {
-            uint32_t mbw[9], mww[9];
+        if (live) {
             const uint32_t* bp = reinterpret_cast<const uint32_t*>(in.board + p * 36);
             const uint32_t* mbp = reinterpret_cast<const uint32_t*>(in.marks_black + p * 36);
             const uint32_t* mwp = reinterpret_cast<const uint32_t*>(in.marks_white + p * 36);
@@ -160,39 +203,59 @@ apply_moves_thread_kernel(lzb_states_in in, int64_t B, const int32_t* __restrict
             for (int w = 0; w < 9; ++w) { bw[w] = bp[w]; mbw[w] = mbp[w]; mww[w] = mwp[w]; }
             s.mb = words_to_marks(mbw);
             s.mw = words_to_marks(mww);
-        }
-        s.phase = in.phase[p]; s.player = in.current_player[p];
-        s.pm_req = in.pending_marks_required[p]; s.pm_rem = in.pending_marks_remaining[p];
-        s.pc_req = in.pending_captures_required[p]; s.pc_rem = in.pending_captures_remaining[p];
-        s.forced = in.forced_removals_done[p];
-        s.move_count = in.move_count ? in.move_count[p] : 0;
-        s.msc = in.moves_since_capture ? in.moves_since_capture[p] : 0;
-        const int4 code = reinterpret_cast<const int4*>(codes)[i];
-        words_to_boards(bw, s.black, s.white, s.other);
-        apply_action(s, code.x, code.y, code.z);
-        const int64_t o = kInplace ? p : i;
-        uint32_t* ob = reinterpret_cast<uint32_t*>(out.board + o * 36);
-        uint32_t* omb = reinterpret_cast<uint32_t*>(out.marks_black + o * 36);
-        uint32_t* omw = reinterpret_cast<uint32_t*>(out.marks_white + o * 36);
+            s.phase = in.phase[p]; s.player = in.current_player[p];
+            s.pm_req = in.pending_marks_required[p]; s.pm_rem = in.pending_marks_remaining[p];
+            s.pc_req = in.pending_captures_required[p]; s.pc_rem = in.pending_captures_remaining[p];
+            s.forced = in.forced_removals_done[p];
+            s.move_count = in.move_count ? in.move_count[p] : 0;
+            s.msc = in.moves_since_capture ? in.moves_since_capture[p] : 0;
+            const int4 code = reinterpret_cast<const int4*>(codes)[i];
+            words_to_boards(bw, s.black, s.white, s.other);
+            apply_action(s, code.x, code.y, code.z);
 #pragma unroll
-        for (int w = 0; w < 9; ++w) {
-            uint32_t vb = 0, vmb = 0, vmw = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int cell = 4 * w + k;
-                const uint64_t bit = 1ULL << cell;
-                const uint32_t orig = (bw[w] >> (8 * k)) & 0xFFu;      // bytes that are not -1 / 0 / +1 are carried over
-                const uint32_t byte = (s.black & bit) ? 1u : (s.white & bit) ? 0xFFu : (s.other & bit) ? orig : 0u;
-                vb |= byte << (8 * k);
-                vmb |= (uint32_t)((s.mb >> cell) & 1) << (8 * k);
-                vmw |= (uint32_t)((s.mw >> cell) & 1) << (8 * k);
+            for (int w = 0; w < 9; ++w) {
+                bw[w] = board_word(s, bw[w], w);
+                mbw[w] = scatter4((uint32_t)(s.mb >> (4 * w)) & 0xFu);
+                mww[w] = scatter4((uint32_t)(s.mw >> (4 * w)) & 0xFu);
             }
-            ob[w] = vb; omb[w] = vmb; omw[w] = vmw;
+            const int64_t o = kInplace ? p : i;
+            out.phase[o] = s.phase; out.current_player[o] = s.player;
+            out.pending_marks_required[o] = s.pm_req; out.pending_marks_remaining[o] = s.pm_rem;
+            out.pending_captures_required[o] = s.pc_req; out.pending_captures_remaining[o] = s.pc_rem;
+            out.forced_removals_done[o] = s.forced; out.move_count[o] = s.move_count; out.moves_since_capture[o] = s.msc;
         }
-        out.phase[o] = s.phase; out.current_player[o] = s.player;
-        out.pending_marks_required[o] = s.pm_req; out.pending_marks_remaining[o] = s.pm_rem;
-        out.pending_captures_required[o] = s.pc_req; out.pending_captures_remaining[o] = s.pc_rem;
-        out.forced_removals_done[o] = s.forced; out.move_count[o] = s.move_count; out.moves_since_capture[o] = s.msc;
+        // the three byte tensors: whole warp live and rows contiguous -> through shared memory, coalesced; otherwise directly
+        const bool staged = !kInplace && __all_sync(0xFFFFFFFFu, live);
+        if (staged) {
+            if constexpr (!kInplace) {
+#pragma unroll
+                for (int w = 0; w < 9; ++w) {               // lane stride 9 words: conflict-free
+                    stage[wib][0][lane * 9 + w] = bw[w];
+                    stage[wib][1][lane * 9 + w] = mbw[w];
+                    stage[wib][2][lane * 9 + w] = mww[w];
+                }
+                __syncwarp();
+                uint8_t* const dst[3] = {reinterpret_cast<uint8_t*>(out.board), out.marks_black, out.marks_white};
+#pragma unroll
+                for (int arr = 0; arr < 3; ++arr) {
+                    uint8_t* g = dst[arr] + i0 * 36;             // 1,152 contiguous bytes
+                    if (vec_ok) {
+                        const uint4* src = reinterpret_cast<const uint4*>(stage[wib][arr]);
+                        for (int k = lane; k < kStageWords / 4; k += 32) reinterpret_cast<uint4*>(g)[k] = src[k];
+                    } else {
+                        for (int k = lane; k < kStageWords; k += 32) reinterpret_cast<uint32_t*>(g)[k] = stage[wib][arr][k];
+                    }
+                }
+                __syncwarp();
+            }
+        } else if (live) {
+            const int64_t o = kInplace ? p : i;
+            uint32_t* ob = reinterpret_cast<uint32_t*>(out.board + o * 36);
+            uint32_t* omb = reinterpret_cast<uint32_t*>(out.marks_black + o * 36);
+            uint32_t* omw = reinterpret_cast<uint32_t*>(out.marks_white + o * 36);
+#pragma unroll
+            for (int w = 0; w < 9; ++w) { ob[w] = bw[w]; omb[w] = mbw[w]; omw[w] = mww[w]; }
+        }
     }
 }
 
@@ -206,36 +269,53 @@ constexpr int64_t kThreadApplyMin = 8192;      // below this the warp-per-action
 // ------------------------------------------------------------------------------------------------------
 // (a6) states_to_model_input -- encoding.cpp:26-79 : f32[B,11,6,6]
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 6)
 model_input_kernel(lzb_states_in st, int64_t B, float* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-    for (int64_t b = warp; b < B; b += nwarps) {
+    // A state's 396 floats are 99 float4; float4 k holds cells 4 (k % 9) .. + 3 of plane k / 9 (36 = 9 x 4, so a float4
+    // never straddles planes).  Lane l writes k = l, l + 32, l + 64, l + 96: its planes and cell offsets are fixed.
+    int pl[4], c0[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int k = lane + 32 * j; pl[j] = k / 9; c0[j] = 4 * (k - pl[j] * 9); }
+    const bool hi = lane < 4;
+    int8_t n_blo = 0, n_bhi = 0;
+    uint8_t n_mblo = 0, n_mwlo = 0, n_mbhi = 0, n_mwhi = 0;
+    int64_t n_cur = 0, n_phase = 0;
+    auto fetch = [&](int64_t b) {
         const int8_t* bp = st.board + b * 36;
-        const bool hi = lane < 4;
-        const int8_t blo = bp[lane], bhi = hi ? bp[32 + lane] : (int8_t)0;
+        const uint8_t* mbp = st.marks_black + b * 36;
+        const uint8_t* mwp = st.marks_white + b * 36;
+        n_blo = bp[lane]; n_bhi = hi ? bp[32 + lane] : (int8_t)0;
+        n_mblo = mbp[lane]; n_mwlo = mwp[lane];
+        n_mbhi = hi ? mbp[32 + lane] : (uint8_t)0; n_mwhi = hi ? mwp[32 + lane] : (uint8_t)0;
+        n_cur = st.current_player[b]; n_phase = st.phase[b];
+    };
+    if (warp < B) fetch(warp);
+    for (int64_t b = warp; b < B; b += nwarps) {
+        const int8_t blo = n_blo, bhi = n_bhi;
+        const uint8_t mblo = n_mblo, mwlo = n_mwlo, mbhi = n_mbhi, mwhi = n_mwhi;
         // `current` is cast to the board dtype before the compare (encoding.cpp:51)
-        const int64_t cur64 = st.current_player[b];
+        const int64_t cur64 = n_cur, phase = n_phase;
+        if (b + nwarps < B) fetch(b + nwarps);                  // next state's loads fly during this state's stores
         const int8_t cur = (int8_t)cur64, neg = (int8_t)(-cur);
         const uint64_t self_p = ballot36(blo == cur, hi && bhi == cur);
         const uint64_t opp_p = ballot36(blo == neg, hi && bhi == neg);
-        const uint8_t* mbp = st.marks_black + b * 36;
-        const uint8_t* mwp = st.marks_white + b * 36;
-        const uint64_t mb = ballot36(mbp[lane] != 0, hi && mbp[32 + lane] != 0);
-        const uint64_t mw = ballot36(mwp[lane] != 0, hi && mwp[32 + lane] != 0);
+        const uint64_t mb = ballot36(mblo != 0, mbhi != 0);
+        const uint64_t mw = ballot36(mwlo != 0, mwhi != 0);
         const bool is_black = cur64 == 1;
-        const uint64_t planes[4] = {self_p, opp_p, is_black ? mb : mw, is_black ? mw : mb};
-        const int64_t phase = st.phase[b];
+        const uint64_t own_marks = is_black ? mb : mw, opp_marks = is_black ? mw : mb;
         float4* o = reinterpret_cast<float4*>(out + b * 396);
-        for (int k = lane; k < 99; k += 32) {                  // 99 float4 = 396 floats
-            float v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int e = 4 * k + j, plane = e / 36, cell = e - plane * 36;
-                v[j] = plane < 4 ? (float)((planes[plane] >> cell) & 1) : ((phase == plane - 3) ? 1.0f : 0.0f);
+        for (int j = 0; j < 4; ++j) {
+            const int k = lane + 32 * j;
+            if (k < 99) {
+                const uint64_t pb = pl[j] == 0 ? self_p : pl[j] == 1 ? opp_p : pl[j] == 2 ? own_marks : opp_marks;
+                const uint32_t nib = pl[j] < 4 ? (uint32_t)(pb >> c0[j]) & 0xFu : (phase == pl[j] - 3 ? 0xFu : 0u);
+                o[k] = make_float4((nib & 1u) ? 1.0f : 0.0f, (nib & 2u) ? 1.0f : 0.0f, (nib & 4u) ? 1.0f : 0.0f,
+                                   (nib & 8u) ? 1.0f : 0.0f);
             }
-            o[k] = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
 }
@@ -422,8 +502,11 @@ extern "C" int lzb_batch_apply_moves(const lzb_states_in* parents, int64_t B, co
     LZB_REQUIRE((reinterpret_cast<uintptr_t>(codes) & 15) == 0, "action_codes must be 16-byte aligned");
     if (N >= kThreadApplyMin && words_ok(parents->board, parents->marks_black, parents->marks_white, children->board,
                                          children->marks_black, children->marks_white)) {
+        // 16-byte stores of a warp's 1,152-byte row group need 16-byte aligned tensors (whole torch tensors are)
+        const int vec_ok = ((reinterpret_cast<uintptr_t>(children->board) | reinterpret_cast<uintptr_t>(children->marks_black) |
+                             reinterpret_cast<uintptr_t>(children->marks_white)) & 15) == 0;
         apply_moves_thread_kernel<false><<<thread_grid(N), kThreads, 0, (cudaStream_t)stream>>>(*parents, B, codes,
-                                                                                                 parent_indices, N, *children);
+                                                                                                 parent_indices, N, *children, vec_ok);
         return check_launch("apply_moves_thread_kernel");
     }
     apply_moves_kernel<false><<<warp_grid(N), kThreads, 0, (cudaStream_t)stream>>>(*parents, B, codes, parent_indices,
@@ -440,7 +523,7 @@ extern "C" int lzb_batch_apply_moves_inplace(const lzb_states_out* states, int64
     if (N >= kThreadApplyMin && words_ok(states->board, states->marks_black, states->marks_white, states->board,
                                          states->marks_black, states->marks_white)) {
         apply_moves_thread_kernel<true><<<thread_grid(N), kThreads, 0, (cudaStream_t)stream>>>(as_in(states), B, codes,
-                                                                                                slot_indices, N, *states);
+                                                                                                slot_indices, N, *states, 0);
         return check_launch("apply_moves_inplace_thread_kernel");
     }
     apply_moves_kernel<true><<<warp_grid(N), kThreads, 0, (cudaStream_t)stream>>>(as_in(states), B, codes,

@@ -63,15 +63,35 @@ LZ_HD uint64_t in_square(uint64_t e) {
 // Cells x of `own` for which CheckLines(x) holds (rule_engine.cpp:91-136): the other five cells of x's row
 // (or column) are all in e.  x itself is NOT tested against the marked set -- reference quirk.
 LZ_HD uint64_t in_line(uint64_t own, uint64_t e) {
-    uint64_t res = 0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        uint64_t rm = row_mask(i), miss = rm & ~e;
-        res |= (miss == 0) ? rm : (((miss & (miss - 1)) == 0) ? (miss & own) : 0ULL);
-        uint64_t cm = col_mask(i);
-        miss = cm & ~e;
-        res |= (miss == 0) ? cm : (((miss & (miss - 1)) == 0) ? (miss & own) : 0ULL);
-    }
+    // All six rows and all six columns at once (SWAR on the 36-bit board; equal to the per-line loop
+    //   miss = line & ~e;  res |= miss == 0 ? line : (popcount(miss) == 1 ? miss & own : 0)
+    // on 30 M random boards).  m = missing cells; a line contributes its cells if m is empty on it, or its single
+    // missing cell if that cell is own (an own piece that is marked: the reference quirk above).
+    e &= kFull;
+    const uint64_t m = kFull & ~e;
+    constexpr uint64_t kC01 = kCol0 | (kCol0 << 1), kC0123 = kC01 | (kC01 << 2);
+    // rows: neighbouring columns are adjacent bits; the masks keep every shift inside its row
+    uint64_t t = e & (e >> 1);
+    const uint64_t rf = t & (t >> 2) & (t >> 4) & kCol0;        // row complete, flagged at its column-0 bit
+    uint64_t p = m | ((m << 1) & ~kCol0);
+    p |= (p << 2) & ~kC01;
+    p |= (p << 4) & ~kC0123;                                     // inclusive prefix OR of m along the row
+    uint64_t d = m & ((p << 1) & ~kCol0);                        // missing cells with another one to their left
+    uint64_t a = d | ((d >> 1) & ~kCol5);
+    a |= (a >> 2) & kC0123;
+    a |= (a >> 4) & kC01;                                        // column-0 bit: the row misses two or more cells
+    uint64_t res = rf * 63u | (m & own & ~((a & kCol0) * 63u));
+    // columns: neighbouring rows are 6 bits apart; shifts by multiples of 6 never leave the column
+    t = e & (e >> 6);
+    const uint64_t cf = t & (t >> 12) & (t >> 24) & kRow0;
+    p = m | (m << 6);
+    p |= p << 12;
+    p |= p << 24;
+    d = m & (p << 6) & kFull;
+    a = d | (d >> 6);
+    a |= a >> 12;
+    a |= a >> 24;
+    res |= cf * kCol0 | (m & own & ~((a & kRow0) * kCol0));
     return res;
 }
 // IsPieceInShape over a whole colour at once (rule_engine.cpp:194-208).
@@ -225,6 +245,12 @@ LZ_HD void legal_actions(const State<I>& s, Legal& L, bool aux_enabled) {
     if (phase == kPlacement) { L.place = emp; return; }
     if (phase == kRemoval) { L.process = aux_enabled; return; }
     const uint64_t opp_marked = (cur == 1) ? s.mw : s.mb;   // fast_legal_mask.cpp:381,391
+    const uint64_t opp = pieces(s, -cur);
+    // Every selection phase ends in the same "prefer pieces outside a shape" filter; the phases only choose its
+    // operands.  One in_shape() evaluation after the phase switch instead of one per branch: a warp whose threads hold
+    // states in different phases (thread-per-state kernels, playouts) runs the expensive part once, not once per phase.
+    bool need = false, strict = false;                          // strict: scalar-engine forced removal has no fallback
+    uint64_t cands = 0, sh_own = 0, sh_marked = 0;
     if (phase == kMovement) {
         const uint64_t own = pieces(s, cur);
         L.mv[0] = own & (emp << 6);                 // up:    cell-6 empty
@@ -232,42 +258,29 @@ LZ_HD void legal_actions(const State<I>& s, Legal& L, bool aux_enabled) {
         L.mv[2] = own & ((emp << 1) & ~kCol0);      // left:  cell-1 empty, c > 0
         L.mv[3] = own & ((emp >> 1) & ~kCol5);      // right: cell+1 empty, c < 5
         if ((L.mv[0] | L.mv[1] | L.mv[2] | L.mv[3]) == 0) {   // no-moves removal :164-177,:405-408
-            const uint64_t opp = pieces(s, -cur);
-            L.sel = prefer_normal(opp, opp, 0);
             L.sel_kind = kActNoMoves;
+            need = true; cands = opp; sh_own = opp; sh_marked = 0;
         }
-        return;
-    }
-    if (phase == kMark) {                                       // :204-226
+    } else if (phase == kMark) {                                // :204-226
         L.sel_kind = kActMark;
-        if (s.pm_rem > 0) {
-            const uint64_t opp = pieces(s, -cur);
-            L.sel = prefer_normal(opp & ~opp_marked, opp, opp_marked);
-        }
-        return;
-    }
-    if (phase == kCapture) {                                    // :228-249
+        if (s.pm_rem > 0) { need = true; cands = opp & ~opp_marked; sh_own = opp; sh_marked = opp_marked; }
+    } else if (phase == kCapture) {                             // :228-249
         L.sel_kind = kActCapture;
-        if (s.pc_rem > 0) {
-            const uint64_t opp = pieces(s, -cur);
-            L.sel = prefer_normal(opp, opp, opp_marked);
-        }
-        return;
-    }
-    if (phase == kForced) {                                     // :131-147
+        if (s.pc_rem > 0) { need = true; cands = opp; sh_own = opp; sh_marked = opp_marked; }
+    } else if (phase == kForced) {                              // :131-147
         L.sel_kind = kActForced;
         if (s.forced == 0 || s.forced == 1 || (!kScalar && s.forced < 2)) {
             const uint64_t tgt = (s.forced == 0) ? s.black : s.white;
-            if (kScalar) L.sel = tgt & ~in_shape(tgt, 0);       // move_generator.cpp:159-167: no fallback
-            else L.sel = prefer_normal(tgt, tgt, 0);
+            need = true; cands = tgt; sh_own = tgt; sh_marked = 0;
+            strict = kScalar;                                   // move_generator.cpp:159-167: no fallback
         }
-        return;
-    }
-    if (phase == kCounter) {                                    // :149-162
-        const uint64_t opp = pieces(s, -cur);
+    } else if (phase == kCounter) {                             // :149-162
         L.sel_kind = kActCounter;
-        L.sel = prefer_normal(opp, opp, 0);
-        return;
+        need = true; cands = opp; sh_own = opp; sh_marked = 0;
+    }
+    if (need) {
+        const uint64_t normal = cands & ~in_shape(sh_own, sh_marked);
+        L.sel = (normal || strict) ? normal : cands;
     }
 }
 

@@ -34,10 +34,39 @@ def timed(fn, reps=30, warm=20):
     return float(np.median(ts))
 
 
-def row(name, units, bytes_per_unit, ours_ms, ref_ms, note=""):
+def graph_ms(fn, reps=50):
+    """Kernel-only time: the call captured into a CUDA graph (its output allocations come from the graph's pool) and
+    replayed back to back -- no Python / ctypes / allocator time between launches."""
+    try:
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            keep = fn()                                     # noqa: F841  (outputs stay alive in the graph pool)
+        for _ in range(5):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+    except RuntimeError:
+        torch.cuda.synchronize()
+        return None
+
+
+def row(name, units, bytes_per_unit, ours_ms, ref_ms, note="", kernel_ms=None):
     gbs = units * bytes_per_unit / (ours_ms / 1e3) / 1e9
+    kgbs = None if not kernel_ms else units * bytes_per_unit / (kernel_ms / 1e3) / 1e9
     return {"op": name, "units": units, "algorithmic_bytes_per_unit": bytes_per_unit, "ours_ms": round(ours_ms, 4),
             "ours_gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / HBM, 3),
+            "kernel_ms (graph replay)": None if not kernel_ms else round(kernel_ms, 4),
+            "kernel_gbs": None if kgbs is None else round(kgbs, 1),
+            "kernel_frac_of_hbm_peak": None if kgbs is None else round(kgbs / HBM, 3),
             "reference_cuda_ms": None if ref_ms is None else round(ref_ms, 4),
             "speedup_vs_reference_cuda": None if ref_ms is None else round(ref_ms / ours_ms, 1), "note": note}
 
@@ -60,23 +89,27 @@ def main():
 
     out.append(row("encode_actions_fast", b, 3888, timed(lambda: v0_core.encode_actions_fast(*t[:10], 36, 144, 36, 4)),
                    ref_or_none(lambda: ref_core.encode_actions_fast(*t[:10], 36, 144, 36, 4)),
-                   "148 B in + 3,740 B out per state (mask + metadata), outputs allocated per call as in the reference"))
+                   "148 B in + 3,740 B out per state (mask + metadata), outputs allocated per call as in the reference",
+                   kernel_ms=graph_ms(lambda: v0_core.encode_actions_fast(*t[:10], 36, 144, 36, 4))))
     n, n_base = 1 << 20, 1 << 14                       # 16,384 distinct (state, action) pairs, each applied 64 times
     st2, codes, parents = random_apply_batch(n_base, 0xA11CEB0B)
     t2 = to_torch(st2, DEV)
     c = torch.from_numpy(codes).to(DEV).repeat(n // n_base, 1).contiguous()
     p = torch.from_numpy(parents).to(DEV).repeat(n // n_base).contiguous()
     out.append(row("batch_apply_moves", n, 384, timed(lambda: v0_core.batch_apply_moves(*t2, c, p)),
-                   ref_or_none(lambda: ref_core.batch_apply_moves(*t2, c, p)), "204 B in + 180 B out per action, 12 output tensors"))
+                   ref_or_none(lambda: ref_core.batch_apply_moves(*t2, c, p)), "204 B in + 180 B out per action, 12 output tensors",
+                   kernel_ms=graph_ms(lambda: v0_core.batch_apply_moves(*t2, c, p))))
     out.append(row("states_to_model_input", b, 1692, timed(lambda: v0_core.states_to_model_input(*t[:5])),
-                   ref_or_none(lambda: ref_core.states_to_model_input(*t[:5])), "108 B in + 1,584 B out per state"))
+                   ref_or_none(lambda: ref_core.states_to_model_input(*t[:5])), "108 B in + 1,584 B out per state",
+                   kernel_ms=graph_ms(lambda: v0_core.states_to_model_input(*t[:5]))))
     bp = 1 << 22                                            # 4 M packed states (128 MB): larger than L2
     packed = native.pack_states(t).repeat(bp // b, 1).contiguous()
     out.append(row("legal_masks (packed)", bp, 68, timed(lambda: native.legal_masks(packed)), None,
-                   "native layout: 32 B in + 32 B mask words + 4 B count out per state"))
+                   "native layout: 32 B in + 32 B mask words + 4 B count out per state; ALU-bound bit logic",
+                   kernel_ms=graph_ms(lambda: native.legal_masks(packed))))
     acts = torch.zeros((bp,), dtype=torch.int32, device=DEV)
     out.append(row("apply_actions (packed)", bp, 68, timed(lambda: native.apply_actions(packed, acts)), None,
-                   "native layout: 32 + 4 B in, 32 B out per action"))
+                   "native layout: 32 + 4 B in, 32 B out per action", kernel_ms=graph_ms(lambda: native.apply_actions(packed, acts))))
     for r, m, s in ((4096, 64, 200), (4096, 64, 800), (4096, 64, 65536)):
         g = torch.Generator(device=DEV).manual_seed(1)
         valid = torch.rand((r, m), device=DEV, generator=g) < 0.4
