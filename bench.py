@@ -277,6 +277,39 @@ def cpu_playout_baseline(budget_s: float = 12.0, threads: int | None = None) -> 
                       f"oracle/lz_oracle.c scalar-engine loop, {cores} threads"}
 
 
+def ref_engine_playout_baseline(budget_s: float = 6.0) -> dict:
+    """The reference's OWN compiled scalar engine (oracle/_ref/v0_core: rule_engine.cpp / move_generator.cpp built from
+    its unmodified sources) playing uniform-random games through its Python API -- generate_all_legal_moves_struct +
+    apply_move_struct per ply, the way the reference's tests drive it.  One thread (the calls hold the GIL)."""
+    ref_dir = ROOT / "oracle" / "_ref"
+    if not list(ref_dir.glob("v0_core*.so")):
+        return {"unavailable": "oracle/_ref/v0_core not present on this box"}
+    import random
+    if str(ref_dir) not in sys.path:
+        sys.path.insert(0, str(ref_dir))
+    try:
+        import torch  # noqa: F401  (the extension links libtorch)
+        import v0_core as ref_core
+    except Exception as exc:  # pragma: no cover
+        return {"unavailable": f"reference v0_core failed to import: {exc!r}"[:200]}
+    rng = random.Random(SEED)
+    t0 = time.perf_counter()
+    plies = games = 0
+    while time.perf_counter() - t0 < budget_s:
+        st = ref_core.GameState()
+        for _ in range(512):
+            moves = ref_core.generate_all_legal_moves_struct(st)
+            if not moves:
+                break
+            st = ref_core.apply_move_struct(st, moves[rng.randrange(len(moves))], True)
+            plies += 1
+        games += 1
+    dt = time.perf_counter() - t0
+    return {"value": plies / dt, "unit": "positions/s", "cores": 1, "kind": "reference",
+            "sample": f"{games} uniform-random games ({plies} plies) in {dt:.1f}s through the reference's compiled v0_core "
+                      f"scalar engine and its Python API, 1 thread"}
+
+
 def run_playout(args, world, rank, local_rank):
     import torch
 
@@ -372,6 +405,7 @@ def run_playout(args, world, rank, local_rank):
                      "kernel": "playout_kernel", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_unit": PLAYOUT_BYTES_PER_PLY, "units_per_launch": plies_per_launch},
         "cpu_baseline": cpu,
+        "cpu_reference_engine": ref_engine_playout_baseline(),
     }
 
 

@@ -415,14 +415,17 @@ tree_expand_kernel(lzb_tree A, int K, const int32_t* __restrict__ leaf_node, con
 // latency chains of a warp run back to back without a grid-wide barrier between them, and a simulation wave needs one
 // tree kernel instead of two (select -> network -> expand becomes network -> expand+select).  The warp's own writes
 // (children, statistics along the path) are ordered before its reads by __syncwarp().
-__global__ void __launch_bounds__(kThreads, LZB_EXPAND_MIN_BLOCKS)
+// WPB warps per block, at least MINB blocks per SM: 4,096 trees are 4,096 warps = 27.7 per SM; <8, 3> (80 registers) keeps
+// only 24 resident, so 13 % of the blocks wait for a second round and the kernel lasts two latency chains.
+template <int WPB, int MINB>
+__global__ void __launch_bounds__(WPB * 32, MINB)
 tree_expand_select_kernel(lzb_tree A, int K, int32_t* __restrict__ leaf_node, int32_t* __restrict__ leaf_status,
                           const float* __restrict__ priors, const float* __restrict__ values, double c_puct, double vl,
                           uint64_t* __restrict__ leaf_states, int32_t* __restrict__ leaf_path, uint4* __restrict__ enc_out) {
-    __shared__ float s_pri[kWarpsPerBlock][kActionDim];
+    __shared__ float s_pri[WPB][kActionDim];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + w;
-    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    const int64_t warp = (int64_t)blockIdx.x * WPB + w;
+    const int64_t nwarps = (int64_t)gridDim.x * WPB;
     for (int64_t t = warp; t < A.num_trees; t += nwarps) {
         expand_tree(A, t, K, leaf_node, leaf_status, priors, values, 1, vl, leaf_path, s_pri[w], lane);
         __syncwarp();
@@ -893,9 +896,19 @@ extern "C" int lzb_tree_expand_select(const lzb_tree* tree, int32_t K, int32_t* 
     LZB_REQUIRE(c_puct >= 0.0 && c_puct == c_puct, "exploration_weight must be finite and non-negative");
     LZB_REQUIRE(leaf_node && leaf_status && priors && values && leaf_states && leaf_path, "null pointer");
     LZB_REQUIRE((reinterpret_cast<uintptr_t>(inputs_c64) & 15) == 0, "inputs must be 16-byte aligned");
-    tree_expand_select_kernel<<<warp_grid(tree->num_trees), kThreads, 0, (cudaStream_t)stream>>>(
-        *tree, K, leaf_node, leaf_status, priors, values, c_puct, virtual_loss, leaf_states, leaf_path,
-        reinterpret_cast<uint4*>(inputs_c64));
+    static const int variant = getenv("LZB_TREE_VARIANT") ? atoi(getenv("LZB_TREE_VARIANT")) : 0;
+    uint4* enc = reinterpret_cast<uint4*>(inputs_c64);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t T = tree->num_trees;
+    if (variant == 1)
+        tree_expand_select_kernel<8, 4><<<warp_grid(T), 256, 0, s>>>(*tree, K, leaf_node, leaf_status, priors, values, c_puct,
+                                                                     virtual_loss, leaf_states, leaf_path, enc);
+    else if (variant == 2)
+        tree_expand_select_kernel<4, 7><<<(unsigned)((T + 3) / 4), 128, 0, s>>>(*tree, K, leaf_node, leaf_status, priors, values,
+                                                                                c_puct, virtual_loss, leaf_states, leaf_path, enc);
+    else
+        tree_expand_select_kernel<8, 3><<<warp_grid(T), 256, 0, s>>>(*tree, K, leaf_node, leaf_status, priors, values, c_puct,
+                                                                     virtual_loss, leaf_states, leaf_path, enc);
     return check_launch("tree_expand_select_kernel");
 }
 
