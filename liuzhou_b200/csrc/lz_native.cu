@@ -70,30 +70,6 @@ init_kernel(uint64_t* __restrict__ packed, int64_t B) {
         store_packed(packed, i, p);
 }
 
-// 16 cells (bits 0..15) -> bits 0, 4, 8, ..., 60
-__device__ __forceinline__ uint64_t spread16x4(uint64_t x) {
-    x = (x | (x << 24)) & 0x000000FF000000FFULL;
-    x = (x | (x << 12)) & 0x000F000F000F000FULL;
-    x = (x | (x << 6)) & 0x0303030303030303ULL;
-    x = (x | (x << 3)) & 0x1111111111111111ULL;
-    return x;
-}
-__device__ __forceinline__ void legal_to_words(const Legal& L, uint64_t w[4]) {
-    // bit a of word a/64, a in [0,220): place 0..35 | movement 36..179 (from*4+dir) | select 180..215 | 216
-    // movement bits m = from * 4 + dir as a 144-bit vector (m0: cells 0..15, m1: 16..31, m2: 32..35), branch-free
-    uint64_t m0 = 0, m1 = 0, m2 = 0;
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-        m0 |= spread16x4(L.mv[d] & 0xFFFFULL) << d;
-        m1 |= spread16x4((L.mv[d] >> 16) & 0xFFFFULL) << d;
-        m2 |= spread16x4((L.mv[d] >> 32) & 0xFULL) << d;
-    }
-    w[0] = L.place | (m0 << 36);
-    w[1] = (m0 >> 28) | (m1 << 36);
-    w[2] = (m1 >> 28) | (m2 << 36) | ((L.sel & 0xFFFULL) << 52);   // m2: 16 bits -> 164..179; select cells 0..11 -> 180..191
-    w[3] = (L.sel >> 12) | (L.process ? (1ULL << (216 - 192)) : 0ULL);   // cells 12..35 -> 192..215; process 216
-}
-
 template <bool kScalar>
 __global__ void __launch_bounds__(kThreads)
 legal_masks_kernel(const uint64_t* __restrict__ packed, int64_t B, uint64_t* __restrict__ mask_words,

@@ -25,6 +25,15 @@ using namespace lz;
 namespace lzb {
 namespace {
 
+// Debug timeline (LZB_TREE_TRACE=1): clock64 stamps of lane 0 of the first warp of blocks 0, 64, 128, ... (8 warps x 32
+// stamps) inside tree_expand_select_kernel; read back with lzb_tree_debug_trace.  nullptr in normal runs.
+__device__ unsigned long long* d_tree_trace = nullptr;
+#define LZB_TSTAMP(i)                                                                                   \
+    do {                                                                                                \
+        if (d_tree_trace && lane == 0 && (threadIdx.x >> 5) == 0 && (blockIdx.x & 63) == 0 && blockIdx.x < 512) \
+            d_tree_trace[(blockIdx.x >> 6) * 32 + (i)] = clock64();                                     \
+    } while (0)
+
 constexpr int32_t kFlagArena = 1, kFlagIllegalAdvance = 2, kFlagBadNetwork = 4;   // sticky bits of counters[1]
 constexpr uint32_t kInfoActionMask = 0xFFu;
 constexpr uint32_t kInfoTerminal = 1u << 16;
@@ -118,6 +127,9 @@ __device__ __forceinline__ void virtual_loss_path(const lzb_tree& A, int node, d
 }
 
 // One state -> bf16 channels-last planes padded to 64 channels ([36 cells][64 ch] = 288 x 16 B), written by a warp.
+// kPadToo = false writes only channels 0..15 (two of the eight 16-byte groups of a cell): channels 16..63 are zero padding
+// that nothing ever changes in a buffer that starts out zero (InferenceNet.new_input), and 3/4 of the 4.6 KB per leaf.
+template <bool kPadToo>
 __device__ __forceinline__ void encode_c64_row(const Packed& p, uint4* __restrict__ out, int lane) {
     State<int> s;
     unpack(p, s);
@@ -125,19 +137,22 @@ __device__ __forceinline__ void encode_c64_row(const Packed& p, uint4* __restric
     const uint64_t p0 = black ? s.black : s.white, p1 = black ? s.white : s.black;
     const uint64_t p2 = black ? s.mb : s.mw, p3 = black ? s.mw : s.mb;
     const int phase_plane = 3 + s.phase;
-    for (int e = lane; e < 288; e += 32) {
-        const int cell = e >> 3, oct = e & 7;
+    constexpr int kGroups = kPadToo ? 8 : 2;
+    for (int e = lane; e < 36 * kGroups; e += 32) {
+        const int cell = e / kGroups, oct = e - cell * kGroups;
         uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (oct < 2) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int plane = oct * 8 + c;
-                const uint64_t bits = plane == 0 ? p0 : plane == 1 ? p1 : plane == 2 ? p2 : p3;
-                const bool on = plane < 4 ? ((bits >> cell) & 1) : (plane < 11 && plane == phase_plane);
-                if (on) w[c >> 1] |= (c & 1) ? 0x3F800000u : 0x00003F80u;        // bf16 1.0
-            }
+        if (oct == 0) {                                          // planes 0..7: the four bitboards + phases 1..4
+            const uint32_t b0 = (uint32_t)(p0 >> cell) & 1u, b1 = (uint32_t)(p1 >> cell) & 1u;
+            const uint32_t b2 = (uint32_t)(p2 >> cell) & 1u, b3 = (uint32_t)(p3 >> cell) & 1u;
+            w[0] = b0 * 0x00003F80u | b1 * 0x3F800000u;          // bf16 1.0 in the low / high half
+            w[1] = b2 * 0x00003F80u | b3 * 0x3F800000u;
+            w[2] = (phase_plane == 4 ? 0x00003F80u : 0u) | (phase_plane == 5 ? 0x3F800000u : 0u);
+            w[3] = (phase_plane == 6 ? 0x00003F80u : 0u) | (phase_plane == 7 ? 0x3F800000u : 0u);
+        } else if (oct == 1) {                                   // planes 8..10: phases 5..7; 11..15: zero
+            w[0] = (phase_plane == 8 ? 0x00003F80u : 0u) | (phase_plane == 9 ? 0x3F800000u : 0u);
+            w[1] = phase_plane == 10 ? 0x00003F80u : 0u;
         }
-        out[e] = make_uint4(w[0], w[1], w[2], w[3]);
+        out[cell * 8 + oct] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -173,36 +188,47 @@ __device__ __forceinline__ void select_tree(const lzb_tree& A, int64_t t, int K,
             // SelectPath :862-874.  One dependent HBM round trip per level: the sibling scan also fetches each
             // child's first_child / info / visit, so the next level needs nothing else from the chosen child.
             int fc = A.first_child[node], nv = A.visit[node];
+            LZB_TSTAMP(8);
             int depth = 0, path_node = lane == 0 ? node : -1, scanned = 0;
             bool path_white = lane == 0 && (inf & kInfoWhite);
             while ((inf & kInfoExpanded) && info_nchild(inf) > 0 && !(inf & kInfoTerminal)) {
                 const int n = info_nchild(inf);
                 scanned += n;
-                const double sqrt_total = sqrt((double)(nv > 1 ? nv : 1));
                 const uint32_t node_white = inf & kInfoWhite;
                 double best = -INFINITY;
                 int best_i = 0x7fffffff, b_vc = 0, b_fc = -1;
                 uint32_t b_inf = 0;
+                const double sqrt_total = sqrt((double)(nv > 1 ? nv : 1));
                 for (int i = lane; i < n; i += 32) {                 // SelectChild :832-860
                     const int c = fc + i;
                     const int vc = A.visit[c];
                     const uint32_t ci = A.info[c];
                     const int cfc = A.first_child[c];
                     const double pr = A.prior[c];
+                    const double ws = A.value_sum[c];               // loaded whether or not vc > 0: ONE round trip per level
                     double q = 0.0;
                     if (vc > 0) {
-                        q = __ddiv_rn(A.value_sum[c], (double)vc);
+                        q = __ddiv_rn(ws, (double)vc);
                         if ((ci & kInfoWhite) != node_white) q = -q;
                     }
                     const double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, pr), sqrt_total), (double)(1 + vc));
                     const double score = __dadd_rn(q, u);
                     if (score > best || (score == best && i < best_i)) { best = score; best_i = i; b_vc = vc; b_fc = cfc; b_inf = ci; }
                 }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-                    const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
-                    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+                {
+                    // warp argmax (ties -> lowest child index) with three redux.sync instead of five shuffle rounds: the
+                    // score as an order-preserving 64-bit key, maximised high word first, then the lowest index among
+                    // the lanes that hold the maximum.  -0.0 == +0.0 in the reference's comparison: canonicalised.
+                    const double sc = best == 0.0 ? 0.0 : best;
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(sc);
+                    const unsigned long long key = bits ^ ((bits >> 63) ? ~0ull : 0x8000000000000000ull);
+                    const uint32_t khi = (uint32_t)(key >> 32), klo = (uint32_t)key;
+                    const bool has = best_i != 0x7fffffff;
+                    const uint32_t mhi = __reduce_max_sync(0xffffffffu, has ? khi : 0u);
+                    const bool c1 = has && khi == mhi;
+                    const uint32_t mlo = __reduce_max_sync(0xffffffffu, c1 ? klo : 0u);
+                    const bool c2 = c1 && klo == mlo;
+                    best_i = (int)__reduce_min_sync(0xffffffffu, c2 ? (uint32_t)best_i : 0x7fffffffu);
                 }
                 if (best_i == 0x7fffffff) break;                     // child == nullptr
                 const int owner = best_i & 31;                       // that lane's local best IS the global best
@@ -212,7 +238,9 @@ __device__ __forceinline__ void select_tree(const lzb_tree& A, int64_t t, int K,
                 fc = __shfl_sync(0xffffffffu, b_fc, owner);
                 ++depth;
                 if (depth < kPathLanes && lane == depth) { path_node = node; path_white = (inf & kInfoWhite) != 0; }
+                if (depth <= 8) LZB_TSTAMP(8 + depth);
             }
+            LZB_TSTAMP(20);
             const bool recorded = depth < kPathLanes;
             if (lane == 0 && depth > 0) { atomicAdd(&A.counters[4], scanned); atomicAdd(&A.counters[5], depth); }
             const uint32_t white_mask = __ballot_sync(0xffffffffu, path_white);
@@ -249,7 +277,7 @@ __device__ __forceinline__ void select_tree(const lzb_tree& A, int64_t t, int K,
                 if (enc_out) {      // the network input of this leaf, written here instead of by a separate launch
 #pragma unroll
                     for (int k = 0; k < 4; ++k) leaf.w[k] = __shfl_sync(0xffffffffu, leaf.w[k], 0);
-                    encode_c64_row(leaf, enc_out + slot * 288, lane);
+                    encode_c64_row<false>(leaf, enc_out + slot * 288, lane);
                 }
                 if (leaf_path) {                                     // the path travels to the expand / backup kernel
                     leaf_path[slot * kPathStride + lane] = path_node;
@@ -261,6 +289,9 @@ __device__ __forceinline__ void select_tree(const lzb_tree& A, int64_t t, int K,
             }
             if (lane == 0) { leaf_node[slot] = status == kLeafEval ? node : -1; leaf_status[slot] = status; }
             __syncwarp();
+            LZB_TSTAMP(21);
+            if (d_tree_trace && lane == 0 && (threadIdx.x >> 5) == 0 && (blockIdx.x & 63) == 0 && blockIdx.x < 512)
+                d_tree_trace[(blockIdx.x >> 6) * 32 + 22] = (unsigned long long)depth;
         }
     }
 }
@@ -295,9 +326,19 @@ __device__ __forceinline__ void expand_tree(const lzb_tree& A, int64_t t, int K,
         }
         for (int k = 0; k < K; ++k) {
             const int64_t slot = base * K + k;
-            if (leaf_status[slot] != kLeafEval) continue;
-            const int node = leaf_node[slot];
-            // the descent's path (for the one-round-trip backup): fetched up front, used at the end
+            LZB_TSTAMP(0);
+            // Everything whose address depends only on the slot is requested in ONE round trip, before the status is
+            // looked at (all of it is valid memory for any slot): status, node, value, this lane's 7 prior entries, the
+            // descent's path.  The second round trip fetches what hangs off the node / the path.
+            const int st = leaf_status[slot];
+            const int node_raw = leaf_node[slot];
+            const float value_f = values[slot];
+            float pv_reg[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const int a = lane + 32 * j;
+                pv_reg[j] = a < kActionDim ? priors[slot * kActionDim + a] : 0.0f;
+            }
             int path_node = -1, path_depth = -1;
             uint32_t path_white = 0;
             if (do_backup && leaf_path) {
@@ -305,13 +346,23 @@ __device__ __forceinline__ void expand_tree(const lzb_tree& A, int64_t t, int K,
                 path_depth = leaf_path[slot * kPathStride + kPathLanes];
                 path_white = (uint32_t)leaf_path[slot * kPathStride + kPathLanes + 1];
             }
+            if (st != kLeafEval) continue;
+            const int node = node_raw;
+            LZB_TSTAMP(1);
+            // statistics of the path nodes for the backup at the end: only this warp touches this tree, so they cannot
+            // change in between -- except through this warp's own virtual-loss bookkeeping (K > 1), which re-reads
+            const bool pre_backup = do_backup && path_depth >= 0 && !(K > 1 && vl > 0.0);
+            int pre_visit = 0;
+            double pre_sum = 0.0;
+            if (pre_backup && lane <= path_depth) { pre_visit = A.visit[path_node]; pre_sum = A.value_sum[path_node]; }
             State<int> s;
             unpack(load_packed(A.state, node), s);
             Legal L;
             legal_actions<int, true>(s, L, true);
             const int n = legal_count(L);
-            double value = (double)values[slot];
+            double value = (double)value_f;
             const uint32_t inf = A.info[node] & ~kInfoPending;
+            LZB_TSTAMP(2);
             if (lane == 0 && K > 1 && vl > 0.0) virtual_loss_path(A, node, vl, -1);
             __syncwarp();
             // CompletePending / Expand throw on a non-finite value or a negative / non-finite prior
@@ -319,14 +370,19 @@ __device__ __forceinline__ void expand_tree(const lzb_tree& A, int64_t t, int K,
             // flag, the leaf stays unexpanded and nothing is backed up, so the tree statistics stay clean
             bool bad = !isfinite(value);
             if (n > 0) {                          // the prior row is staged in shared memory once, checked, then used
-                for (int a = lane; a < kActionDim; a += 32) {
-                    const float pv = priors[slot * kActionDim + a];
-                    spri[a] = pv;
-                    if (legal_test(L, a) && (!(pv >= 0.0f) || isinf(pv))) bad = true;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    const int a = lane + 32 * j;
+                    if (a < kActionDim) {
+                        const float pv = pv_reg[j];
+                        spri[a] = pv;
+                        if (legal_test(L, a) && (!(pv >= 0.0f) || isinf(pv))) bad = true;
+                    }
                 }
             }
             __syncwarp();                         // staging writes visible to lane 0's sequential sum below
             bad = __any_sync(0xffffffffu, bad);
+            LZB_TSTAMP(3);
             if (bad) {
                 if (lane == 0) { A.info[node] = inf; atomicOr(&A.counters[1], kFlagBadNetwork); }
                 __syncwarp();
@@ -340,33 +396,45 @@ __device__ __forceinline__ void expand_tree(const lzb_tree& A, int64_t t, int K,
                     if (node < A.num_trees) A.root_value[node] = value;
                 }
             } else {
-                // prior_sum accumulated sequentially in ascending action order, in fp64 (:909-918)
-                double prior_sum = 0.0;
+                // prior_sum accumulated sequentially in ascending action order, in fp64 (:909-918).  Lane i holds the
+                // i-th legal action and its prior (needed for its child anyway); the values reach the adder by shuffle,
+                // so the dependent chain is one fp64 add per action instead of bit scan + shared-memory load + add.
+                // Every lane runs the same additions: no broadcast of the result.
                 int fc = 0;
-                if (lane == 0) {
-                    // one ascending pass over the legal set: placement cells, then (from, dir) moves, then selections
-                    for (uint64_t m = L.place; m; m &= m - 1) prior_sum = __dadd_rn(prior_sum, (double)spri[ctz64(m)]);
-                    for (uint64_t u = L.mv[0] | L.mv[1] | L.mv[2] | L.mv[3]; u; u &= u - 1) {
-                        const int from = ctz64(u);
+                if (lane == 0) fc = atomicAdd(&A.counters[0], n);   // requested first: its round trip runs under the sum
+                uint64_t lw[4];
+                legal_to_words(L, lw);
+                double prior_sum = 0.0;
+                int act0 = -1, act1 = -1, act2 = -1;               // this lane's actions of rounds 0..2 (n <= 72 < 96)
+                for (int r = 0; r * 32 < n; ++r) {
+                    const int i = r * 32 + lane;
+                    const int a = i < n ? legal_kth_words(lw, i) : -1;
+                    if (r == 0) act0 = a; else if (r == 1) act1 = a; else if (r == 2) act2 = a;
+                    const float pv = a >= 0 ? spri[a] : 0.0f;
+                    const int m = n - r * 32 < 32 ? n - r * 32 : 32;
+                    for (int j0 = 0; j0 < m; j0 += 8) {            // eight shuffles in flight, then the eight ordered adds
+                        float v[8];
 #pragma unroll
-                        for (int d = 0; d < 4; ++d)
-                            if ((L.mv[d] >> from) & 1) prior_sum = __dadd_rn(prior_sum, (double)spri[36 + from * 4 + d]);
+                        for (int j = 0; j < 8; ++j) v[j] = __shfl_sync(0xffffffffu, pv, (j0 + j) & 31);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j0 + j < m) prior_sum = __dadd_rn(prior_sum, (double)v[j]);
                     }
-                    for (uint64_t m = L.sel; m; m &= m - 1) prior_sum = __dadd_rn(prior_sum, (double)spri[180 + ctz64(m)]);
-                    if (L.process) prior_sum = __dadd_rn(prior_sum, (double)spri[216]);
-                    fc = atomicAdd(&A.counters[0], n);
+                }
+                LZB_TSTAMP(4);
+                if (lane == 0) {
                     // the bump pointer only grows: after the first failure every later allocation fails too, so
                     // [num_trees, first failed index) is exactly the set of valid nodes (advance_roots relies on it)
                     if ((int64_t)fc + n > A.capacity) { atomicOr(&A.counters[1], 1); atomicMin(&A.counters[6], fc); fc = -1; }
                     else atomicAdd(&A.counters[2], 1);
                 }
-                prior_sum = __shfl_sync(0xffffffffu, prior_sum, 0);
                 fc = __shfl_sync(0xffffffffu, fc, 0);
+                LZB_TSTAMP(5);
                 if (fc >= 0) {
                     const bool uniform = !(prior_sum > 0.0) || isinf(prior_sum);      // :919
-                    for (int i = lane; i < n; i += 32) {      // child i <-> i-th legal action in ascending index order
+                    for (int i = lane, r = 0; i < n; i += 32, ++r) {   // child i <-> i-th legal action in ascending index order
                         {
-                            const int a = legal_kth(L, i);
+                            const int a = r == 0 ? act0 : r == 1 ? act1 : r == 2 ? act2 : legal_kth_words(lw, i);
                             const int c = fc + i;
                             State<int> cs = s;
                             apply_index(cs, a);
@@ -390,11 +458,19 @@ __device__ __forceinline__ void expand_tree(const lzb_tree& A, int64_t t, int K,
                 }
             }
             __syncwarp();
+            LZB_TSTAMP(6);
             if (do_backup) {
-                if (path_depth >= 0) backup_recorded(A, lane, path_node, path_white, path_depth, value);
+                if (pre_backup) {                 // backup_recorded with the statistics fetched at the top: stores only
+                    if (lane <= path_depth) {
+                        const bool same = ((path_white >> lane) & 1u) == ((path_white >> path_depth) & 1u);
+                        A.visit[path_node] = pre_visit + 1;
+                        A.value_sum[path_node] = __dadd_rn(pre_sum, same ? value : -value);
+                    }
+                } else if (path_depth >= 0) backup_recorded(A, lane, path_node, path_white, path_depth, value);
                 else if (lane == 0) backup_path(A, node, value);
             }
             __syncwarp();
+            LZB_TSTAMP(7);
         }
     }
 }
@@ -720,7 +796,7 @@ encode_inputs_c64_kernel(const uint64_t* __restrict__ states, int64_t n, uint4* 
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
-    for (int64_t i = warp; i < n; i += nwarps) encode_c64_row(load_packed(states, i), out + i * 288, lane);
+    for (int64_t i = warp; i < n; i += nwarps) encode_c64_row<true>(load_packed(states, i), out + i * 288, lane);
 }
 
 // Policy heads -> dense priors over the legal actions of each leaf (masked softmax, fp32) and bucketed value
@@ -887,6 +963,13 @@ extern "C" int lzb_tree_expand_backup(const lzb_tree* tree, int32_t K, const int
     return check_launch("tree_expand_kernel");
 }
 
+static unsigned long long* g_tree_trace_buf = nullptr;
+// debug: copy the stamps of the last tree_expand_select_kernel launch (LZB_TREE_TRACE=1) to host memory (256 u64)
+extern "C" __attribute__((visibility("default"))) int lzb_tree_debug_trace(unsigned long long* host_out) {
+    if (!g_tree_trace_buf) return LZB_ERR_INVALID_ARGUMENT;
+    return cudaMemcpy(host_out, g_tree_trace_buf, 256 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? LZB_OK : LZB_ERR_CUDA;
+}
+
 extern "C" int lzb_tree_expand_select(const lzb_tree* tree, int32_t K, int32_t* leaf_node, int32_t* leaf_status,
                                       const float* priors, const float* values, double c_puct, double virtual_loss,
                                       uint64_t* leaf_states, int32_t* leaf_path, void* inputs_c64, void* stream) {
@@ -897,6 +980,12 @@ extern "C" int lzb_tree_expand_select(const lzb_tree* tree, int32_t K, int32_t* 
     LZB_REQUIRE(leaf_node && leaf_status && priors && values && leaf_states && leaf_path, "null pointer");
     LZB_REQUIRE((reinterpret_cast<uintptr_t>(inputs_c64) & 15) == 0, "inputs must be 16-byte aligned");
     static const int variant = getenv("LZB_TREE_VARIANT") ? atoi(getenv("LZB_TREE_VARIANT")) : 0;
+    static const bool trace = getenv("LZB_TREE_TRACE") && atoi(getenv("LZB_TREE_TRACE")) != 0;
+    if (trace && !g_tree_trace_buf) {
+        cudaMalloc(&g_tree_trace_buf, 256 * 8);
+        cudaMemset(g_tree_trace_buf, 0, 256 * 8);
+        cudaMemcpyToSymbol(d_tree_trace, &g_tree_trace_buf, sizeof(g_tree_trace_buf));
+    }
     uint4* enc = reinterpret_cast<uint4*>(inputs_c64);
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t T = tree->num_trees;

@@ -377,7 +377,8 @@ def test_tree_advance_roots_reset_deactivate_and_errors():
 
 def test_select_with_fused_input_encoding():
     """select_leaves / prepare_roots with encode_out: the rows of the pending (status 0) slots equal the separate
-    lzb_encode_inputs_packed launch bit for bit, other rows are left untouched, tree statistics are unaffected."""
+    lzb_encode_inputs_packed launch bit for bit (channels 0..15 written, the zero padding left alone), other rows are left
+    untouched, tree statistics are unaffected."""
     from liuzhou_b200 import native
     from liuzhou_b200.tree import DeviceTreeBatch, encode_inputs
 
@@ -386,7 +387,10 @@ def test_select_with_fused_input_encoding():
     packed = native.pack_states(to_torch(st, DEV))
     trees = [DeviceTreeBatch(n, DEV, exploration_weight=1.0, nodes_per_tree_hint=40 * 64) for _ in range(2)]
     sentinel = 0.25
-    buf = torch.full((n, 64, 6, 6), sentinel, dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last)
+    # contract of the fused encoding: channels 16..63 are zero padding that the caller zero-fills once and the kernels
+    # never write; the sentinel sits in the 16 channels they do write
+    buf = torch.zeros((n, 64, 6, 6), dtype=torch.bfloat16, device=DEV).contiguous(memory_format=torch.channels_last)
+    buf[:, :16] = sentinel
     for t in trees:
         t.reset(packed)
     trees[0].prepare_roots()
@@ -399,7 +403,8 @@ def test_select_with_fused_input_encoding():
         live = torch.from_numpy(status == 0).to(DEV)
         assert torch.equal(buf[live], want[live])
         if wave == 0 and (~live).any():
-            assert bool((buf[~live] == sentinel).all())                 # untouched rows
+            assert bool((buf[~live][:, :16] == sentinel).all())         # untouched rows
+            assert bool((buf[:, 16:] == 0).all())
         rows, inputs, masks = _pending_from_device(trees[1], native)
         pri, val = fake_net(inputs, masks, 1)
         for t in trees:
