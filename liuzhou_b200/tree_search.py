@@ -78,6 +78,8 @@ class TreeMCTS:
         self._root_val = torch.zeros((tp,), dtype=torch.float32, device=dev)
         self._wave_pri = self._root_pri if k == 1 else torch.zeros((sp, ACTION_DIM), dtype=torch.float32, device=dev)
         self._wave_val = self._root_val if k == 1 else torch.zeros((sp,), dtype=torch.float32, device=dev)
+        self._unroll = max(1, int(os.environ.get("LZB_WAVE_UNROLL", "1")))
+        self._unrolled: dict = {}
         self._wave_graph: Optional[torch.cuda.CUDAGraph] = None
         self._root_graph: Optional[torch.cuda.CUDAGraph] = None
         self.root_graph_launches = self.wave_graph_launches = self.search_extra_launches = 0
@@ -120,6 +122,7 @@ class TreeMCTS:
             return
         for b in self.bucket_ladder():
             self._graphs_for(b)
+            self._unrolled_for(b)
         self._buckets_warm = True
 
     def set_live(self, active: Optional[torch.Tensor]) -> None:
@@ -203,6 +206,21 @@ class TreeMCTS:
                 self._wave_last(bucket)
             pair = self._bucket_graphs[bucket] = (g_mid, g_last)
         return pair
+
+    def _unrolled_for(self, bucket: int):
+        """A graph of ``_unroll`` consecutive waves (kernel -> kernel edges inside one graph are cheaper than graph -> graph
+        launches), or None when unrolling is off."""
+        if self._unroll <= 1:
+            return None
+        g = self._unrolled.get(bucket)
+        if g is None:
+            self._graphs_for(bucket)                 # warm-up at this size + the single-wave graphs for the remainder
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._root_graph.pool()):
+                for _ in range(self._unroll):
+                    self._wave_mid(None if bucket >= self.num_trees else bucket)
+            self._unrolled[bucket] = g
+        return g
 
     def _wave_step(self) -> None:
         """One stand-alone wave (select -> network -> expand + backup); used by tools and the tree-kernel timing."""
@@ -304,8 +322,14 @@ class TreeMCTS:
             self._apply_root_noise()
         if use_graph:
             g_mid, g_last = self._graphs_for(bucket)
+            g_many = self._unrolled_for(bucket)
             self._first_graph.replay()
-            for _ in range(self.waves - 1):
+            left = self.waves - 1
+            if g_many is not None:
+                for _ in range(left // self._unroll):
+                    g_many.replay()
+                left %= self._unroll
+            for _ in range(left):
                 g_mid.replay()
             g_last.replay()
         else:
