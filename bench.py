@@ -741,7 +741,7 @@ def time_tree_kernels(stepper, peaks, reps: int = 20) -> dict:
         tree.complete_pending(m._wave_pri, m._wave_val)
         torch.cuda.synchronize()
         fused_ms = sum(a.elapsed_time(b) for a, b in fe[reps:]) / (2 * reps)
-    per_wave_bytes = (sel_bytes + exp_bytes) / reps + tree.num_trees * tree.k * 4608          # + the encoded inputs
+    per_wave_bytes = (sel_bytes + exp_bytes) / reps + tree.num_trees * tree.k * 1152          # + the encoded inputs (16 of 64 channels)
     return {"bound": "hbm (latency-limited: one dependent HBM round trip per tree level, one warp per tree)",
             "expand_select_fused_ms": fused_ms,
             "expand_select_fused_gbs": None if not fused_ms else per_wave_bytes / (fused_ms / 1e3) / 1e9,
@@ -751,7 +751,7 @@ def time_tree_kernels(stepper, peaks, reps: int = 20) -> dict:
             "expand_backup_frac": exp_gbs / peaks["hbm_gbs"],
             "bytes_per_simulation": (sel_bytes + exp_bytes) / max(1, sims), "avg_depth": levels / max(1, sims),
             "avg_siblings_per_level": sibs / max(1, levels), "children_per_expansion": new_nodes / max(1, expansions),
-            "ncu": "profiles/r01_tree_kernels_ncu_full_v2.csv (DRAM bytes, occupancy, issue utilisation)"}
+            "ncu": "profiles/r02_tree_heads_ncu_full.csv (DRAM bytes, occupancy, issue utilisation); timeline: tools/trace_tree.py"}
 
 
 def run_selfplay(args, world, rank, local_rank):
