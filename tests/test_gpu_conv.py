@@ -208,3 +208,29 @@ def test_fused_trunk_kernel_matches_per_layer_path_and_fp32(n, blocks):
         assert ef <= max(1.5e-2, 1.2 * el), (ef, el)
         assert (f.exp() - l.exp()).abs().max().item() <= 3e-2
     torch.testing.assert_close(fused[3], out_ref[3].reshape(fused[3].shape), rtol=8e-2, atol=8e-2)
+
+
+@pytest.mark.gpu
+def test_fused_trunk_copy_handoff_soak():
+    """The trunk kernel hands operand copies from the epilogue warps to the MMA thread with a CTA-scope release
+    (csrc/lz_trunk.cu: strict_sync off).  A lost or early hand-off would change at least one output element: the same input
+    through the kernel 300 times per batch size, while another stream keeps the memory system busy, must give bit-identical
+    outputs every time (tools/soak_trunk.py runs 6,000 launches)."""
+    from liuzhou_b200.net import ChessNet, InferenceNet
+
+    torch.manual_seed(5)
+    net = InferenceNet(ChessNet(), DEV)
+    side = torch.cuda.Stream()
+    junk = torch.empty(32 << 20, dtype=torch.float32, device=DEV)
+    for n in (192, 4096):
+        x = net.new_input(n)
+        x[:, :11] = (torch.rand((n, 11, 6, 6), device=DEV) > 0.6).to(torch.bfloat16)
+        ref = net._trunk_heads_conv(x).clone()
+        bad = torch.zeros((), dtype=torch.int64, device=DEV)
+        for i in range(300):
+            if i % 8 == 0:
+                with torch.cuda.stream(side):
+                    junk.add_(1.0)
+            bad += (net._trunk_heads_conv(x) != ref).any().to(torch.int64)
+        torch.cuda.synchronize()
+        assert int(bad) == 0, f"{int(bad)} of 300 launches differ at batch {n}"
