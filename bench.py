@@ -277,37 +277,24 @@ def cpu_playout_baseline(budget_s: float = 12.0, threads: int | None = None) -> 
                       f"oracle/lz_oracle.c scalar-engine loop, {cores} threads"}
 
 
-def ref_engine_playout_baseline(budget_s: float = 6.0) -> dict:
-    """The reference's OWN compiled scalar engine (oracle/_ref/v0_core: rule_engine.cpp / move_generator.cpp built from
-    its unmodified sources) playing uniform-random games through its Python API -- generate_all_legal_moves_struct +
-    apply_move_struct per ply, the way the reference's tests drive it.  One thread (the calls hold the GIL)."""
-    ref_dir = ROOT / "oracle" / "_ref"
-    if not list(ref_dir.glob("v0_core*.so")):
-        return {"unavailable": "oracle/_ref/v0_core not present on this box"}
-    import random
-    if str(ref_dir) not in sys.path:
-        sys.path.insert(0, str(ref_dir))
+def ref_engine_playout_baseline(budget_s: float = 10.0, threads: int | None = None) -> dict:
+    """The reference's OWN scalar engine (rule_engine.cpp / move_generator.cpp / game_state.cpp compiled from its
+    unmodified sources by oracle/build_ref.py, driven by oracle/ref_playout_harness.cpp) playing uniform-random games --
+    v0::GenerateAllLegalMoves + v0::ApplyMove per ply -- on all host threads for a bounded wall-clock sample."""
+    exe = ROOT / "oracle" / "_ref" / "ref_playout"
+    if not exe.exists():
+        return {"unavailable": "oracle/_ref/ref_playout not present on this box"}
+    import subprocess
+    cores = threads or os.cpu_count() or 1
     try:
-        import torch  # noqa: F401  (the extension links libtorch)
-        import v0_core as ref_core
+        res = subprocess.run([str(exe), str(cores), f"{budget_s:.1f}", str(SEED)], capture_output=True, text=True,
+                             timeout=budget_s * 3 + 30)
+        r = json.loads(res.stdout.strip().splitlines()[-1])
     except Exception as exc:  # pragma: no cover
-        return {"unavailable": f"reference v0_core failed to import: {exc!r}"[:200]}
-    rng = random.Random(SEED)
-    t0 = time.perf_counter()
-    plies = games = 0
-    while time.perf_counter() - t0 < budget_s:
-        st = ref_core.GameState()
-        for _ in range(512):
-            moves = ref_core.generate_all_legal_moves_struct(st)
-            if not moves:
-                break
-            st = ref_core.apply_move_struct(st, moves[rng.randrange(len(moves))], True)
-            plies += 1
-        games += 1
-    dt = time.perf_counter() - t0
-    return {"value": plies / dt, "unit": "positions/s", "cores": 1, "kind": "reference",
-            "sample": f"{games} uniform-random games ({plies} plies) in {dt:.1f}s through the reference's compiled v0_core "
-                      f"scalar engine and its Python API, 1 thread"}
+        return {"unavailable": f"ref_playout failed: {exc!r}"[:200]}
+    return {"value": r["plies_per_sec"], "unit": "positions/s", "cores": cores, "kind": "reference",
+            "sample": f"{r['games']} uniform-random games ({r['plies']} plies) in {r['seconds']:.1f}s: the reference's compiled "
+                      f"scalar engine (v0::GenerateAllLegalMoves + v0::ApplyMove per ply), {cores} threads"}
 
 
 def run_playout(args, world, rank, local_rank):
@@ -389,7 +376,10 @@ def run_playout(args, world, rank, local_rank):
     k_ms = sum(kernel_ms) / len(kernel_ms)
     plies_per_launch = total_plies / args.steps
     achieved = plies_per_launch * PLAYOUT_BYTES_PER_PLY / (k_ms / 1e3) / 1e9
-    cpu = cpu_playout_baseline()
+    cpu_port = cpu_playout_baseline()
+    cpu = ref_engine_playout_baseline()
+    if "unavailable" in cpu:                    # no reference binary on this box: the oracle port stands in
+        cpu = cpu_port
     return {
         "metric": "selfplay_positions_per_sec", "value": value, "unit": "positions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -405,7 +395,7 @@ def run_playout(args, world, rank, local_rank):
                      "kernel": "playout_kernel", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_unit": PLAYOUT_BYTES_PER_PLY, "units_per_launch": plies_per_launch},
         "cpu_baseline": cpu,
-        "cpu_reference_engine": ref_engine_playout_baseline(),
+        "cpu_port": cpu_port,
     }
 
 
@@ -415,7 +405,9 @@ def run_reference_playout(args):
     vals = []
     last = None
     for it in range(args.warmup + args.steps):
-        last = cpu_playout_baseline(budget_s=per_step)
+        last = ref_engine_playout_baseline(budget_s=per_step)
+        if "unavailable" in last:
+            last = cpu_playout_baseline(budget_s=per_step)
         if it >= args.warmup:
             vals.append(last["value"])
     value = sum(vals) / len(vals)

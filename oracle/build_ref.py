@@ -107,6 +107,18 @@ def build_portable(force: bool) -> Path:
     return target
 
 
+def build_ref_playout(force: bool) -> Path:
+    """oracle/_ref/ref_playout: oracle/ref_playout_harness.cpp (ours: a random-playout driver) + the reference's scalar
+    engine sources where they lie.  The CPU arm of BASELINE configs[1] with cpu_baseline.kind = "reference"."""
+    target = OUT / "ref_playout"
+    if target.exists() and not force:
+        return target
+    OUT.mkdir(parents=True, exist_ok=True)
+    srcs = [str(HERE / "ref_playout_harness.cpp")] + [str(REF / s) for s in PORTABLE_CPP[1:]]
+    _run(["g++", "-O3", "-std=c++17", "-pthread", f"-I{REF / 'v0/include'}", *srcs, "-o", str(target)])
+    return target
+
+
 def build_v0_core(force: bool, cuda: bool) -> Path:
     target = OUT / f"v0_core{EXT}"
     stamp = OUT / ("v0_core.cuda" if cuda else "v0_core.cpu")
@@ -177,7 +189,7 @@ def main() -> int:
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--cuda", action="store_true", help="also compile the reference .cu kernels (sm_100)")
     ap.add_argument("--no-pysrc", action="store_true", help="skip the copy of the reference's python packages")
-    ap.add_argument("--only", choices=["portable", "v0_core"], default=None)
+    ap.add_argument("--only", choices=["portable", "v0_core", "playout"], default=None)
     args = ap.parse_args()
     if not REF.is_dir():
         print(f"[build_ref] {REF} not present (GPU box?) -- keeping prebuilt oracle/_ref as is")
@@ -185,6 +197,8 @@ def main() -> int:
     OUT.mkdir(parents=True, exist_ok=True)
     if args.only in (None, "portable"):
         print("[build_ref] portable tree MCTS ->", build_portable(args.force))
+    if args.only in (None, "playout"):
+        print("[build_ref] scalar-engine playout driver ->", build_ref_playout(args.force))
     if args.only in (None, "v0_core"):
         print("[build_ref] v0_core ->", build_v0_core(args.force, args.cuda))
     if args.only is None and not args.no_pysrc:
