@@ -62,46 +62,8 @@ __device__ __forceinline__ uint64_t ballot36(bool lo_pred, bool hi_pred) {
     return (uint64_t)lo | ((uint64_t)hi << 32);
 }
 
-// 16 cells (bits 0..15) -> bits 0, 4, 8, ..., 60
-__device__ __forceinline__ uint64_t spread16x4(uint64_t x) {
-    x = (x | (x << 24)) & 0x000000FF000000FFULL;
-    x = (x | (x << 12)) & 0x000F000F000F000FULL;
-    x = (x | (x << 6)) & 0x0303030303030303ULL;
-    x = (x | (x << 3)) & 0x1111111111111111ULL;
-    return x;
-}
-__device__ __forceinline__ void legal_to_words(const lz::Legal& L, uint64_t w[4]) {
-    // bit a of word a/64, a in [0,220): place 0..35 | movement 36..179 (from*4+dir) | select 180..215 | 216
-    // movement bits m = from * 4 + dir as a 144-bit vector (m0: cells 0..15, m1: 16..31, m2: 32..35), branch-free
-    uint64_t m0 = 0, m1 = 0, m2 = 0;
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-        m0 |= spread16x4(L.mv[d] & 0xFFFFULL) << d;
-        m1 |= spread16x4((L.mv[d] >> 16) & 0xFFFFULL) << d;
-        m2 |= spread16x4((L.mv[d] >> 32) & 0xFULL) << d;
-    }
-    w[0] = L.place | (m0 << 36);
-    w[1] = (m0 >> 28) | (m1 << 36);
-    w[2] = (m1 >> 28) | (m2 << 36) | ((L.sel & 0xFFFULL) << 52);   // m2: 16 bits -> 164..179; select cells 0..11 -> 180..191
-    w[3] = (L.sel >> 12) | (L.process ? (1ULL << (216 - 192)) : 0ULL);   // cells 12..35 -> 192..215; process 216
-}
-
-// k-th legal action in ascending index order (0 <= k < legal_count) from the 220-bit mask words: prefix popcounts over the
-// seven 32-bit pieces, then find-n-th-set (fns) inside the piece -- ~40 instructions whatever the phase, where
-// lz::legal_kth peels bits one at a time.
-__device__ __forceinline__ int legal_kth_words(const uint64_t (&w)[4], int k) {
-    uint32_t p[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) p[j] = (uint32_t)(w[j >> 1] >> (32 * (j & 1)));
-    int base = 0, piece = 0;
-    uint32_t word = p[0];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        const int c = __popc(p[j]);
-        if (piece == j && k >= base + c) { base += c; piece = j + 1; word = p[j + 1]; }
-    }
-    return 32 * piece + (int)__fns(word, 0, k - base + 1);
-}
+using lz::legal_to_words;
+using lz::legal_kth_words;
 
 // The same load split in two, so that a kernel can have the NEXT state's loads in flight while it works on (and stores
 // the wide outputs of) the current one: under saturating write traffic a dependent load costs several thousand cycles.

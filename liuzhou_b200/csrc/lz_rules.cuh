@@ -297,7 +297,10 @@ LZ_HD bool has_unmarked_normal(uint64_t own, uint64_t marked) {
 
 // Returns true if applied, false for a silent no-op.  move_count / moves_since_capture bookkeeping of the
 // kernel body (fast_apply_moves_cuda.cu:624-743) included.
-template <typename I>
+// kTrusted = true: the action is known to come from legal_actions() on this very state (playouts, tree expansion), so the
+// "is the piece inside a shape while a normal piece exists" re-validation -- two in_shape() evaluations per removal -- is
+// compiled out; the legal set has already applied exactly that preference.  Everything else is unchanged.
+template <typename I, bool kTrusted = false>
 LZ_HD bool apply_action(State<I>& s, int kind, int primary, int secondary) {
     const I phase_before = s.phase;
     const int old_total = popc64(occupied(s));
@@ -334,7 +337,7 @@ LZ_HD bool apply_action(State<I>& s, int kind, int primary, int secondary) {
         uint64_t& opp_marked = (oppv == -1) ? s.mw : s.mb;
         const uint64_t opp = pieces(s, oppv);
         if (!(opp & bit(cell)) || (opp_marked & bit(cell))) break;
-        if ((in_shape(opp, opp_marked) & bit(cell)) && has_unmarked_normal(opp, opp_marked)) break;
+        if (!kTrusted && (in_shape(opp, opp_marked) & bit(cell)) && has_unmarked_normal(opp, opp_marked)) break;
         opp_marked |= bit(cell);
         s.pm_rem -= 1;
         ok = true;
@@ -360,12 +363,12 @@ LZ_HD bool apply_action(State<I>& s, int kind, int primary, int secondary) {
         if (s.phase != kForced || cell < 0 || cell >= 36) break;
         if (s.forced == 0) {
             if (s.player != -1 || !(s.black & bit(cell))) break;
-            if (in_shape(s.black, 0) & bit(cell)) break;
+            if (!kTrusted && (in_shape(s.black, 0) & bit(cell))) break;
             s.black &= ~bit(cell);
             s.forced = 1; s.player = 1; ok = true;
         } else if (s.forced == 1) {
             if (s.player != 1 || !(s.white & bit(cell))) break;
-            if (in_shape(s.white, 0) & bit(cell)) break;
+            if (!kTrusted && (in_shape(s.white, 0) & bit(cell))) break;
             s.white &= ~bit(cell);
             s.forced = 2; s.phase = kMovement; s.player = -1; ok = true;
         }
@@ -397,7 +400,7 @@ LZ_HD bool apply_action(State<I>& s, int kind, int primary, int secondary) {
         const long long oppv = (long long)(int)(-cur);
         const uint64_t opp = pieces(s, oppv);
         if (!(opp & bit(cell)) || oppv == 0) break;
-        if ((in_shape(opp, 0) & bit(cell)) && has_unmarked_normal(opp, 0)) break;
+        if (!kTrusted && (in_shape(opp, 0) & bit(cell)) && has_unmarked_normal(opp, 0)) break;
         set_piece(s, cell, 0);
         ok = true;
         if (popc64(pieces(s, oppv)) < kLoseThreshold) break;
@@ -412,7 +415,7 @@ LZ_HD bool apply_action(State<I>& s, int kind, int primary, int secondary) {
         const uint64_t opp_marked = (oppv == -1) ? s.mw : s.mb;
         const uint64_t opp = pieces(s, oppv);
         if (!(opp & bit(cell)) || oppv == 0) break;
-        if ((in_shape(opp, opp_marked) & bit(cell)) && has_unmarked_normal(opp, opp_marked)) break;
+        if (!kTrusted && (in_shape(opp, opp_marked) & bit(cell)) && has_unmarked_normal(opp, opp_marked)) break;
         set_piece(s, cell, 0);
         s.pc_rem -= 1;
         ok = true;
@@ -428,7 +431,7 @@ LZ_HD bool apply_action(State<I>& s, int kind, int primary, int secondary) {
         const long long stuckv = (long long)(int)(-cur);
         const uint64_t stuck = pieces(s, stuckv);
         if (!(stuck & bit(cell)) || stuckv == 0) break;
-        if ((in_shape(stuck, 0) & bit(cell)) && has_unmarked_normal(stuck, 0)) break;
+        if (!kTrusted && (in_shape(stuck, 0) & bit(cell)) && has_unmarked_normal(stuck, 0)) break;
         set_piece(s, cell, 0);
         ok = true;
         if (popc64(pieces(s, stuckv)) < kLoseThreshold) break;
@@ -447,7 +450,7 @@ LZ_HD bool apply_action(State<I>& s, int kind, int primary, int secondary) {
 }
 
 // Apply by 220-d action index (kind resolved from the phase, as the mask encoder would emit it).
-template <typename I>
+template <typename I, bool kTrusted = false>
 LZ_HD bool apply_index(State<I>& s, int a) {
     int kind, primary = -1, secondary = -1;
     if (a < 36) { kind = kActPlace; primary = a; }
@@ -458,7 +461,7 @@ LZ_HD bool apply_index(State<I>& s, int a) {
         kind = ph == kMark ? kActMark : ph == kCapture ? kActCapture : ph == kForced ? kActForced
              : ph == kCounter ? kActCounter : kActNoMoves;
     } else { kind = kActProcess; }
-    return apply_action(s, kind, primary, secondary);
+    return apply_action<I, kTrusted>(s, kind, primary, secondary);
 }
 
 // ---- packed native state: 4 x u64 = 32 B ---------------------------------------------------------------
@@ -512,6 +515,51 @@ LZ_HD uint64_t state_hash(const State<int>& s) {
     return h;
 }
 
+#if defined(__CUDACC__)
+// ---- device-only helpers: the legal set as a 220-bit mask, k-th legal action by popcount + fns ---------------------
+// 16 cells (bits 0..15) -> bits 0, 4, 8, ..., 60
+__device__ __forceinline__ uint64_t spread16x4(uint64_t x) {
+    x = (x | (x << 24)) & 0x000000FF000000FFULL;
+    x = (x | (x << 12)) & 0x000F000F000F000FULL;
+    x = (x | (x << 6)) & 0x0303030303030303ULL;
+    x = (x | (x << 3)) & 0x1111111111111111ULL;
+    return x;
+}
+__device__ __forceinline__ void legal_to_words(const Legal& L, uint64_t w[4]) {
+    // bit a of word a/64, a in [0,220): place 0..35 | movement 36..179 (from*4+dir) | select 180..215 | 216
+    // movement bits m = from * 4 + dir as a 144-bit vector (m0: cells 0..15, m1: 16..31, m2: 32..35), branch-free
+    uint64_t m0 = 0, m1 = 0, m2 = 0;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        m0 |= spread16x4(L.mv[d] & 0xFFFFULL) << d;
+        m1 |= spread16x4((L.mv[d] >> 16) & 0xFFFFULL) << d;
+        m2 |= spread16x4((L.mv[d] >> 32) & 0xFULL) << d;
+    }
+    w[0] = L.place | (m0 << 36);
+    w[1] = (m0 >> 28) | (m1 << 36);
+    w[2] = (m1 >> 28) | (m2 << 36) | ((L.sel & 0xFFFULL) << 52);   // m2: 16 bits -> 164..179; select cells 0..11 -> 180..191
+    w[3] = (L.sel >> 12) | (L.process ? (1ULL << (216 - 192)) : 0ULL);   // cells 12..35 -> 192..215; process 216
+}
+
+// k-th legal action in ascending index order (0 <= k < legal_count) from the 220-bit mask words: prefix popcounts over the
+// seven 32-bit pieces, then find-n-th-set (fns) inside the piece -- ~40 instructions whatever the phase, where
+// lz::legal_kth peels bits one at a time.
+__device__ __forceinline__ int legal_kth_words(const uint64_t (&w)[4], int k) {
+    uint32_t p[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) p[j] = (uint32_t)(w[j >> 1] >> (32 * (j & 1)));
+    int base = 0, piece = 0;
+    uint32_t word = p[0];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const int c = __popc(p[j]);
+        if (piece == j && k >= base + c) { base += c; piece = j + 1; word = p[j + 1]; }
+    }
+    return 32 * piece + (int)__fns(word, 0, k - base + 1);
+}
+
+#endif
+
 // Config-2 workload step loop: legal set (scalar-engine semantics) -> counter-based uniform pick -> apply ->
 // terminal check, for up to max_steps plies.  res: 2 = still running, else result_from_black.
 template <bool kHash>
@@ -524,8 +572,15 @@ LZ_HD void playout_advance(State<int>& s, int& ply, int& res, uint64_t& h, uint6
         legal_actions<int, true>(s, L, true);
         const int n = legal_count(L);
         if (n == 0) { res = -s.player; return; }                  // module.cpp:733-735: side to move loses
-        const int a = legal_kth(L, (int)playout_pick(seed, game, (uint32_t)ply, (uint32_t)n));
-        apply_index(s, a);
+        const int k = (int)playout_pick(seed, game, (uint32_t)ply, (uint32_t)n);
+#if defined(__CUDA_ARCH__)
+        uint64_t lw[4];                       // branch-free on the device: threads of a warp pick different ranks
+        legal_to_words(L, lw);
+        const int a = legal_kth_words(lw, k);
+#else
+        const int a = legal_kth(L, k);
+#endif
+        apply_index<int, true>(s, a);         // the action comes from this state's legal set
         ++ply;
         if (kHash) h = mix64(h ^ state_hash(s));
     }

@@ -437,7 +437,7 @@ __device__ __forceinline__ void expand_tree(const lzb_tree& A, int64_t t, int K,
                             const int a = r == 0 ? act0 : r == 1 ? act1 : r == 2 ? act2 : legal_kth_words(lw, i);
                             const int c = fc + i;
                             State<int> cs = s;
-                            apply_index(cs, a);
+                            apply_index<int, true>(cs, a);      // a comes from this state's legal set
                             store_packed(A.state, c, pack(cs));
                             A.visit[c] = 0; A.value_sum[c] = 0.0;
                             A.prior[c] = uniform ? __ddiv_rn(1.0, (double)n) : __ddiv_rn((double)spri[a], prior_sum);
