@@ -326,7 +326,8 @@ LZB_API int lzb_conv_bf16(const void *x, const void *w, int64_t n, int32_t cin, 
  * conv, the 2 x blocks residual-block convs with their BatchNorm / ReLU / residual adds, and PolicyHead.conv1 +
  * ValueHead.conv1 with their BatchNorm + ReLU (src/neural_network.py:83-96,98-151,213-259).  Activations stay in shared
  * memory / tensor memory across all layers; the residual stream is kept in fp32.
- * planes bf16 [n,6,6,64] (lzb_encode_inputs_packed layout 2); w_stem bf16 [9][128][64]; w_trunk bf16 [2*blocks*9+1][128][128]
+ * planes bf16 [n,6,6,64] (lzb_encode_inputs_packed layout 2; channels 16..63 MUST be zero -- the stem only multiplies the
+ * first 16 channels, the network has 11); w_stem bf16 [9][128][64]; w_trunk bf16 [2*blocks*9+1][128][128]
  * (conv1_0, conv2_0, ..., heads 1x1; tap-major, K-major rows, BatchNorm folded where it follows a conv), stored w_copies
  * times back to back (cluster c streams copy c % w_copies: spreads the L2 traffic of the hot weight lines); params f32 in
  * DEVICE memory, compact: stem bias | scale | shift (384), per block conv1 bias (128) + conv2 scale | shift (256), heads

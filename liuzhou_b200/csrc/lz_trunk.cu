@@ -292,6 +292,7 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                                 tc_fence_after();
                                 if (elect_one()) {
                                     const bool first_tap = c == 0 && d == 0;
+                                    const int stem_ksteps = (P.debug & 512) ? 4 : 1;      // debug bit 512: all four (A/B timing)
                                     const bool last_tap = c == nc - 1 && d == nc - 1;
 #pragma unroll
                                     for (int kc = 0; kc < 2; ++kc) {
@@ -299,9 +300,12 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                                             const uint64_t adesc = umma_desc_sw128(a_smem + buf * kCopyBytes + kc * kChunkBytes +
                                                                                    (uint32_t)(dyi * 6) * 128u);
                                             const uint64_t bdesc = umma_desc_sw128(w_smem + wst * kWStageBytes + kc * 8192);
+                                            // the stem's operand has 11 real channels in a 64-channel row: channels 16..63
+                                            // are zero in the input AND in the packed weights, so only the first K = 16
+                                            // step contributes (9 MMAs instead of 36 for the layer)
 #pragma unroll
                                             for (int k = 0; k < 4; ++k)
-                                                if (!(P.debug & 4))
+                                                if (!(P.debug & 4) && (k < stem_ksteps || l != 0))
                                                     umma_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k,
                                                              (uint32_t)(conv2 || !first_tap || (kc | k) != 0));
                                         }

@@ -478,6 +478,7 @@ class InferenceNet:
         # LZB_TRUNK_IMPL: 1 (default) = the whole trunk + heads conv as ONE persistent kernel (csrc/lz_trunk.cu: activations
         # stay in shared memory / TMEM across all layers); 0 = one kernel launch per convolution (csrc/lz_conv.cu)
         self.fused_trunk = (self._tc_ready() and len(self.model.blocks) <= 10
+                            and self.model.num_input_channels <= 16      # the kernel's stem multiplies 16 input channels
                             and os.environ.get("LZB_TRUNK_IMPL", "1") != "0")
         self._ft = {}
         self._pv = {}
