@@ -1250,6 +1250,27 @@ def run_config4(args, world, rank, local_rank):
     }
 
 
+def reference_cpu_entry_line(games: int = 64, sims: int = SELFPLAY_SIMS, plies: int = 1, timeout_s: float = 240.0):
+    """The reference's OWN CPU full-tree self-play entry, unmodified (`self_play_v1_portable_cpp`,
+    v1/python/portable_cpp_self_play.py:26, via oracle/ref_runner.py portable): a bounded run next to the CPU arm, which
+    drives the same compiled tree from a leaner loop of ours and is the faster -- hence the more conservative -- baseline."""
+    if not (ROOT / "oracle" / "_ref" / "pysrc").is_dir():
+        return {"unavailable": "oracle/_ref/pysrc not present on this box"}
+    import subprocess
+    try:
+        res = subprocess.run([sys.executable, str(ROOT / "oracle" / "ref_runner.py"), "portable", "--games", str(games),
+                              "--sims", str(sims), "--max-plies", str(plies), "--warmup-games", "8"],
+                             capture_output=True, text=True, timeout=timeout_s)
+        r = json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as exc:  # pragma: no cover
+        return {"unavailable": f"ref_runner portable failed: {exc!r}"[:200]}
+    if "positions_per_sec" not in r:
+        return r
+    return {"value": r["positions_per_sec"], "unit": "positions/s", "sims_per_sec": r["sims_per_sec"], "cores": r["cores"],
+            "positions": r["positions"], "seconds": r["seconds"],
+            "what": f"{r['what']}: {games} games x {sims} sims, {plies} ply per game"}
+
+
 def run_reference_selfplay(args):
     """--impl reference: the reference's CPU implementation of the path on all host cores, ONE continuous session (no
     restarts between steps); a step = one move of every game of the session, its duration is measured.  The session is
@@ -1293,6 +1314,7 @@ def run_reference_selfplay(args):
         "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_cpu_entry": reference_cpu_entry_line(sims=args.sims) if args.ref_entry else None,
     }
 
 
@@ -1363,6 +1385,8 @@ def main() -> int:
     ap.add_argument("--no-root-line", action="store_true", help="skip the extra root-PUCT iteration in the default line")
     ap.add_argument("--search", choices=["tree", "root"], default="tree",
                     help="tree: device-resident full tree (north_star, default); root: the reference's root-PUCT backend")
+    ap.add_argument("--ref-entry", type=int, default=1,
+                    help="--impl reference: also time the reference's own self_play_v1_portable_cpp entry (64 games x 1 ply)")
     ap.add_argument("--profile-only", action="store_true",
                     help="for ncu launch lists: only the device-timed steps (no e2e iteration, no reference / CPU legs)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)

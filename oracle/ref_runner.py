@@ -7,6 +7,7 @@ liuzhou_b200/.
                                          [--sample 0|1] [--seed N] [--warmup-games W] [--dump out.pt]
     python oracle/ref_runner.py search   --v0core {ref,shim} --states in.pt --sims S [--dump out.pt]
     python oracle/ref_runner.py legacy   --games 1 --sims 64          (BASELINE configs[0]: legacy src/mcts.py self-play on CPU)
+    python oracle/ref_runner.py portable --games 256 --sims 200 --max-plies 3   (the reference's CPU full-tree self-play entry)
 
 `--v0core ref`  : `import v0_core` resolves to the reference's own extension (oracle/_ref/v0_core*.so, its three .cu kernels
                   compiled for sm_100 from the unmodified sources)      -> "the v1 reference on the same B200".
@@ -139,9 +140,39 @@ def cmd_legacy(a) -> dict:
             "what": "src.mcts.self_play, legacy python engine + python MCTS, tiny net, 1 CPU thread"}
 
 
+def cmd_portable(a) -> dict:
+    """The reference's own full-tree self-play on the CPU: `self_play_v1_portable_cpp` (v1/python/portable_cpp_self_play.py:26)
+    over its compiled `_liuzhou_portable_cpp` tree (oracle/_ref) and its fp32 PyTorch ChessNet, `--threads` CPU threads,
+    `--concurrent` games per network batch -- the reference's `--search_backend portable --portable_mcts_backend cpp` path,
+    the only full-tree search it has.  Bounded by --max-plies (every game is cut after that many moves)."""
+    sys.path.insert(0, str(PYSRC))
+    sys.path.insert(0, str(REF_DIR))
+    import torch
+    from v1.python.portable_cpp_self_play import self_play_v1_portable_cpp
+
+    threads = a.threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = _model(a.model_seed, "cpu", a.small_net)
+    kw = dict(num_games=a.games, mcts_simulations=a.sims, temperature_init=1.0, temperature_final=0.1,
+              temperature_threshold=10, exploration_weight=1.0, device="cpu", add_dirichlet_noise=bool(a.noise),
+              soft_value_k=2.0, sample_moves=bool(a.sample), concurrent_games=a.concurrent or a.games, cpu_threads=threads)
+    torch.manual_seed(a.seed)
+    if a.warmup_games:
+        self_play_v1_portable_cpp(model, **{**kw, "num_games": a.warmup_games, "concurrent_games": a.warmup_games,
+                                            "max_game_plies": 1})
+    t0 = time.perf_counter()
+    batch, stats = self_play_v1_portable_cpp(model, max_game_plies=a.max_plies, **kw)
+    dt = time.perf_counter() - t0
+    positions = int(batch.num_samples)
+    return {"mode": "portable", "games": a.games, "sims": a.sims, "max_plies": a.max_plies, "positions": positions,
+            "seconds": dt, "positions_per_sec": positions / dt, "sims_per_sec": positions * a.sims / dt, "cores": threads,
+            "what": "UNMODIFIED reference python self_play_v1_portable_cpp + its compiled C++ tree + fp32 ChessNet on the CPU"}
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["selfplay", "search", "legacy"])
+    ap.add_argument("mode", choices=["selfplay", "search", "legacy", "portable"])
+    ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--v0core", choices=["ref", "shim"], default="ref")
     ap.add_argument("--games", type=int, default=64)
     ap.add_argument("--concurrent", type=int, default=0)
@@ -158,7 +189,7 @@ def main() -> int:
     ap.add_argument("--dump", default=None)
     a = ap.parse_args()
     os.environ.setdefault("CUBLAS_WORKSPACE_CONFIG", ":4096:8")
-    out = {"selfplay": cmd_selfplay, "search": cmd_search, "legacy": cmd_legacy}[a.mode](a)
+    out = {"selfplay": cmd_selfplay, "search": cmd_search, "legacy": cmd_legacy, "portable": cmd_portable}[a.mode](a)
     print(json.dumps(out), flush=True)
     return 0
 
