@@ -401,7 +401,7 @@ def run_playout(args, world, rank, local_rank):
 
 def run_reference_playout(args):
     """--impl reference for the playout workload: the CPU engine on all host threads, bounded sample per step."""
-    per_step = max(2.0, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
+    per_step = max(1.0, min(10.0, min(60.0, float(args.ref_budget)) / max(1, args.steps + args.warmup)))
     vals = []
     last = None
     for it in range(args.warmup + args.steps):
