@@ -1,6 +1,7 @@
 """CPU tests of the host-side (torch tensor) logic that surrounds the kernels: policy from visit counts,
 deterministic move choice, packed-state status decoding, trajectory buffer bookkeeping."""
 import numpy as np
+import pytest
 import torch
 
 import oracle
@@ -108,3 +109,50 @@ def test_eval_game_count_normalisation_and_stats():
     assert st.color_breakdown["challenger_black"] == {"wins": 2, "losses": 1, "draws": 1, "games": 4}
     assert st.color_breakdown["challenger_white"] == {"wins": 1, "losses": 2, "draws": 1, "games": 4}
     assert abs(st.win_rate - 0.375) < 1e-12 and abs(st.draw_rate - 0.25) < 1e-12
+
+
+# ---- the three helper checks of the reference's tests/v1/test_v1_tensor_pipeline_smoke.py:20-70, same inputs and expectations,
+# ---- on our mirror of V1RootMCTS (plain torch host logic: runs on the CPU)
+def test_v1_soft_tanh_range_sign_and_scale():
+    import math
+
+    from liuzhou_b200.mcts_gpu import V1RootMCTS
+
+    board = torch.zeros((3, 6, 6), dtype=torch.int8)
+    board[0, :2, :] = 1
+    board[1, :2, :] = -1
+    soft = V1RootMCTS._soft_tanh_from_board_black(board, soft_value_k=2.0)
+    assert tuple(soft.shape) == (3,)
+    assert torch.all(soft <= 1.0 + 1e-6) and torch.all(soft >= -1.0 - 1e-6)
+    assert float(soft[0]) > float(soft[2]) > float(soft[1])
+    assert float(soft[0]) == pytest.approx(math.tanh(4.0 / 3.0))
+
+
+def test_v1_terminal_mask_next_state():
+    from liuzhou_b200.mcts_gpu import GpuStateBatch, V1RootMCTS
+
+    board = torch.zeros((3, 6, 6), dtype=torch.int8)
+    board[0, 0, 0] = 1          # white has no pieces, but mark selection is not a terminal phase
+    board[1, 0, 0] = 1
+    board[1, 0, 1] = -1
+    board[2, 0, 0] = 1
+    board[2, 0, 1] = -1
+    zeros = torch.zeros((3,), dtype=torch.int64)
+    batch = GpuStateBatch(
+        board=board, marks_black=torch.zeros((3, 6, 6), dtype=torch.bool), marks_white=torch.zeros((3, 6, 6), dtype=torch.bool),
+        phase=torch.tensor([2, 4, 1], dtype=torch.int64), current_player=torch.ones((3,), dtype=torch.int64),
+        pending_marks_required=zeros.clone(), pending_marks_remaining=zeros.clone(), pending_captures_required=zeros.clone(),
+        pending_captures_remaining=zeros.clone(), forced_removals_done=zeros.clone(),
+        move_count=torch.tensor([0, 144, 0], dtype=torch.int64),            # GameState.MAX_MOVE_COUNT (game_state.hpp:14)
+        moves_since_capture=torch.tensor([0, 0, 36], dtype=torch.int64))    # NO_CAPTURE_DRAW_LIMIT (game_state.hpp:16)
+    assert V1RootMCTS._terminal_mask_from_next_state(batch).tolist() == [False, True, True]
+
+
+def test_v1_child_value_perspective_alignment():
+    from liuzhou_b200.mcts_gpu import V1RootMCTS
+
+    aligned = V1RootMCTS._child_values_to_parent_perspective(
+        child_values=torch.tensor([0.2, -0.5, 0.8, -0.1], dtype=torch.float32),
+        parent_players=torch.tensor([1, 1, -1, -1], dtype=torch.int64),
+        child_players=torch.tensor([1, -1, -1, 1], dtype=torch.int64))
+    assert torch.allclose(aligned, torch.tensor([0.2, 0.5, 0.8, 0.1]), atol=1e-6, rtol=0.0)
