@@ -55,6 +55,7 @@ struct TrunkParams {
     int debug;
     int w_copies;              // the trunk weight tensor is stored w_copies times back to back; cluster c reads copy c % w_copies
     int w_stages;              // weight ring depth actually used (<= kWStages; fewer = latency experiment)
+    int* tile_done;            // optional: tile_done[i] = 1 once boards [3 i, 3 i + 3) of `out` are complete (heads overlap)
     unsigned long long* trace;   // debug bit 8: clock64 stamps of cluster 0's leader CTA ([0,4096) MMA thread, [4096,8192) epilogue warp 2)
 };
 
@@ -465,6 +466,14 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
                             if (P.trace && blockIdx.x == 0 && warp == 2 && lane == 0 && tr_e < 4090) P.trace[4096 + tr_e++] = clock64();   // copy published
                         }
                     }
+                    if (last && P.tile_done) {
+                        // the tile's rows of `out` are complete once all eight epilogue warps have stored their part: publish
+                        // it to the overlapped heads kernel (which acquires the flag before reading the rows)
+                        __threadfence();
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        if (warp == 2 && lane == 0 && board0 < P.images)
+                            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(P.tile_done + board0 / kBoards), "r"(1) : "memory");
+                    }
                     if (last) {                           // acc_h has been read: this slot's next tile may overwrite it
                         tc_fence_before();
                         __syncwarp();
@@ -486,6 +495,11 @@ trunk_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ C
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTrunkTmemCols) : "memory");
     }
+    if ((P.debug & 1024) && P.tile_done && threadIdx.x == 0 && blockIdx.x < 512) {   // debug: when did this CTA finish?
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        reinterpret_cast<unsigned long long*>(P.tile_done + 4096 + 2048)[blockIdx.x] = gt;
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -506,8 +520,22 @@ extern "C" __attribute__((visibility("default"))) int lzb_trunk_debug_trace(unsi
 // (conv1_0, conv2_0, ..., conv2_{blocks-1}, heads 1x1; BatchNorm folded where it follows a conv), params f32 (DEVICE
 // memory, compact: stem bias | scale | shift (384), then per block conv1 bias (128) + conv2 scale | shift (256), then the
 // heads conv bias (128)), out bf16 [n,6,6,128] = relu(heads conv + bias).  blocks <= 10.
+static int trunk_launch(const void* planes, int64_t n, const void* w_stem, const void* w_trunk, int32_t w_copies,
+                        const float* params, int32_t blocks, void* out, int32_t* tile_done, void* stream);
 extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem, const void* w_trunk, int32_t w_copies,
                               const float* params, int32_t blocks, void* out, void* stream) {
+    return trunk_launch(planes, n, w_stem, w_trunk, w_copies, params, blocks, out, nullptr, stream);
+}
+// The same launch that additionally publishes per-tile completion: tile_done (device, int32[ceil(n / 3) + 1], ALL ZERO on
+// entry) -- entry i becomes 1 when boards [3 i, 3 i + 3) of `out` are complete.  Consumed (and zeroed again) by
+// lzb_heads_tail_overlapped, which may then start on SMs whose trunk CTA has finished while other CTAs still run.
+extern "C" int lzb_trunk_bf16_signal(const void* planes, int64_t n, const void* w_stem, const void* w_trunk, int32_t w_copies,
+                                     const float* params, int32_t blocks, void* out, int32_t* tile_done, void* stream) {
+    LZB_REQUIRE(tile_done, "null tile_done");
+    return trunk_launch(planes, n, w_stem, w_trunk, w_copies, params, blocks, out, tile_done, stream);
+}
+static int trunk_launch(const void* planes, int64_t n, const void* w_stem, const void* w_trunk, int32_t w_copies,
+                        const float* params, int32_t blocks, void* out, int32_t* tile_done, void* stream) {
     using namespace lzb;
     LZB_REQUIRE(n > 0 && n < (1ll << 30), "bad batch size");
     LZB_REQUIRE(blocks >= 1 && blocks <= kMaxBlocks, "blocks must be in [1, 10]");
@@ -587,6 +615,7 @@ extern "C" int lzb_trunk_bf16(const void* planes, int64_t n, const void* w_stem,
     }
     TrunkParams P;
     P.out = reinterpret_cast<__nv_bfloat16*>(out); P.images = (int)n; P.blocks = blocks; P.w_copies = w_copies;
+    P.tile_done = tile_done;
     static const int debug = getenv("LZB_TRUNK_DEBUG") ? atoi(getenv("LZB_TRUNK_DEBUG")) : 0;
     P.debug = debug;
     static const int w_stages = getenv("LZB_TRUNK_W_STAGES") ? atoi(getenv("LZB_TRUNK_W_STAGES")) : kWStages;

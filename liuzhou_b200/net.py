@@ -400,7 +400,8 @@ class FusedHeads:
         self._set("bfc2", f(vh.fc2.bias))
 
     def __call__(self, a: Optional[torch.Tensor], states: Optional[torch.Tensor] = None, *, priors_out=None,
-                 values_out=None, want_raw: bool = False, pv: Optional[torch.Tensor] = None):
+                 values_out=None, want_raw: bool = False, pv: Optional[torch.Tensor] = None,
+                 tile_done: Optional[torch.Tensor] = None):
         """a: trunk output bf16 [n,C,6,6] channels-last.  With `states` (packed int64[n,4]) returns
         (priors f32[n,220], values f32[n]); with want_raw returns (log_p1, log_p2, log_pmc, value_logits) fp32."""
         import ctypes
@@ -431,14 +432,17 @@ class FusedHeads:
                 priors_out = torch.empty((n, 220), dtype=torch.float32, device=dev)
             if values_out is None:
                 values_out = torch.empty((n,), dtype=torch.float32, device=dev)
-        check(lib().lzb_heads_tail(ptr(pv), i64(n), ctypes.c_int32(self.pc), ctypes.c_int32(self.vc),
-                                   ctypes.c_int32(self.mlp), ctypes.c_int32(self.bins), ptr(t["wgl_t"]),
-                                   ptr(t["bn2_scale"]), ptr(t["bn2_shift"]), ptr(t["wout"]), ptr(t["wfc1_t"]),
-                                   ptr(t["bfc1"]), ptr(t["wfc2_t"]), ptr(t["bfc2"]),
-                                   ptr(states if states is not None else None),
-                                   ptr(priors_out if states is not None else None),
-                                   ptr(values_out if states is not None else None), ptr(log_heads), ptr(value_logits),
-                                   stream_ptr(dev)))
+        args = (ptr(pv), i64(n), ctypes.c_int32(self.pc), ctypes.c_int32(self.vc),
+                ctypes.c_int32(self.mlp), ctypes.c_int32(self.bins), ptr(t["wgl_t"]),
+                ptr(t["bn2_scale"]), ptr(t["bn2_shift"]), ptr(t["wout"]), ptr(t["wfc1_t"]),
+                ptr(t["bfc1"]), ptr(t["wfc2_t"]), ptr(t["bfc2"]),
+                ptr(states if states is not None else None),
+                ptr(priors_out if states is not None else None),
+                ptr(values_out if states is not None else None), ptr(log_heads), ptr(value_logits))
+        if tile_done is not None:     # overlapped with the tail of the trunk kernel that was launched with the same flags
+            check(lib().lzb_heads_tail_overlapped(*args, ptr(tile_done), stream_ptr(dev)))
+        else:
+            check(lib().lzb_heads_tail(*args, stream_ptr(dev)))
         if want_raw:
             return log_heads[:, 0], log_heads[:, 1], log_heads[:, 2], value_logits
         return priors_out, values_out
@@ -477,6 +481,10 @@ class InferenceNet:
         self.flops_per_state = flops_per_state(self.model)
         # LZB_TRUNK_IMPL: 1 (default) = the whole trunk + heads conv as ONE persistent kernel (csrc/lz_trunk.cu: activations
         # stay in shared memory / TMEM across all layers); 0 = one kernel launch per convolution (csrc/lz_conv.cu)
+        # LZB_HEADS_OVERLAP=1: the heads kernel starts under the trunk kernel's tail (per-tile completion flags + a
+        # programmatic dependent launch) instead of after it
+        self.heads_overlap = os.environ.get("LZB_HEADS_OVERLAP", "0") == "1"
+        self._flags: dict = {}
         self.fused_trunk = (self._tc_ready() and len(self.model.blocks) <= 10
                             and self.model.num_input_channels <= 16      # the kernel's stem multiplies 16 input channels
                             and os.environ.get("LZB_TRUNK_IMPL", "1") != "0")
@@ -528,7 +536,17 @@ class InferenceNet:
             else:
                 self._ft[name] = val.clone()
 
-    def _trunk_heads_conv(self, x: torch.Tensor) -> torch.Tensor:
+    def _tile_flags(self, n: int) -> Optional[torch.Tensor]:
+        """Completion flags shared by the trunk kernel and the overlapped heads kernel (LZB_HEADS_OVERLAP=1), or None."""
+        if not self.heads_overlap:
+            return None
+        f = self._flags.get(n)
+        if f is None:
+            extra = 4096 + 4096 if os.environ.get("LZB_OVERLAP_TRACE") else 0       # debug: block start / CTA end stamps
+            f = self._flags[n] = torch.zeros(((n + 2) // 3 + 1 + extra,), dtype=torch.int32, device=self.device)
+        return f
+
+    def _trunk_heads_conv(self, x: torch.Tensor, tile_done: Optional[torch.Tensor] = None) -> torch.Tensor:
         """planes bf16 [n,64,6,6] channels-last -> relu(bn(conv1)) of both heads, bf16 [n,128,6,6] channels-last: stem,
         every residual block and the heads' 1x1 conv in ONE kernel launch (lzb_trunk_bf16)."""
         import ctypes
@@ -543,9 +561,12 @@ class InferenceNet:
         if pv is None:
             pv = self._pv[n] = torch.empty((n, 128, 6, 6), dtype=torch.bfloat16, device=x.device,
                                            memory_format=torch.channels_last)
-        check(lib().lzb_trunk_bf16(ptr(x), i64(n), ptr(self.trunk._t["stem_wp"]), ptr(self._ft["w_trunk"]),
-                                   ctypes.c_int32(self.w_copies), ptr(self._ft["params"]),
-                                   ctypes.c_int32(len(self.model.blocks)), ptr(pv), stream_ptr(x.device)))
+        args = (ptr(x), i64(n), ptr(self.trunk._t["stem_wp"]), ptr(self._ft["w_trunk"]), ctypes.c_int32(self.w_copies),
+                ptr(self._ft["params"]), ctypes.c_int32(len(self.model.blocks)), ptr(pv))
+        if tile_done is not None:
+            check(lib().lzb_trunk_bf16_signal(*args, ptr(tile_done), stream_ptr(x.device)))
+        else:
+            check(lib().lzb_trunk_bf16(*args, stream_ptr(x.device)))
         return pv
 
     def load_state_dict(self, state_dict) -> None:
@@ -568,7 +589,8 @@ class InferenceNet:
         if self.trunk is not None:
             with torch.cuda.device(self.device):
                 if self.fused_trunk:
-                    return self.heads(None, want_raw=True, pv=self._trunk_heads_conv(x))
+                    fl = self._tile_flags(x.size(0))
+                    return self.heads(None, want_raw=True, pv=self._trunk_heads_conv(x, fl), tile_done=fl)
                 a = self.trunk(x)
                 if self.heads is not None:
                     return self.heads(a, want_raw=True)
@@ -584,8 +606,9 @@ class InferenceNet:
         (priors f32[n,220] = softmax over each state's legal actions, values f32[n] = bucket expectation)."""
         with torch.cuda.device(self.device):
             if self.fused_trunk:
+                fl = self._tile_flags(x.size(0))
                 return self.heads(None, states, priors_out=priors_out, values_out=values_out,
-                                  pv=self._trunk_heads_conv(x))
+                                  pv=self._trunk_heads_conv(x, fl), tile_done=fl)
             if self.trunk is not None and self.heads is not None:
                 return self.heads(self.trunk(x), states, priors_out=priors_out, values_out=values_out)
             from .tree import heads_to_priors
