@@ -102,9 +102,11 @@ def test_trunk_and_heads_tc_path_matches_cudnn_path():
     ref = model.to(DEV).float().eval()
     with torch.no_grad():
         out_ref = ref(x.float())
+    # measured (tools/net_error_probe.py, 10 blocks, perturbed BatchNorm): log-probs within 3.4e-3 of fp32, value logits
+    # within 1.5e-3; the bounds below leave a factor ~6
     for a, b, r in zip(out_tc, out_cudnn, out_ref):
-        torch.testing.assert_close(a, b, rtol=5e-2, atol=5e-2)
-        torch.testing.assert_close(a, r.float().reshape(a.shape), rtol=8e-2, atol=8e-2)
+        torch.testing.assert_close(a, b, rtol=0.0, atol=2.5e-2)
+        torch.testing.assert_close(a, r.float().reshape(a.shape), rtol=0.0, atol=2e-2)
 
 
 def test_encode_inputs_channel_padded_layout():
@@ -203,11 +205,14 @@ def test_fused_trunk_kernel_matches_per_layer_path_and_fp32(n, blocks):
     ref = model.to(DEV).float().eval()
     with torch.no_grad():
         out_ref = [o.float() for o in ref(planes.float())]
+    # measured max-abs errors against the fp32 module (tools/net_error_probe.py): head probabilities 4e-5 .. 1e-4 (fused) vs
+    # 5e-5 .. 1.3e-4 (per layer), log-probs <= 3.4e-3, value logits <= 1.5e-3 (fused) vs 1.8e-3 (per layer)
     for f, l, r in zip(fused[:3], layered[:3], out_ref[:3]):
         ef, el = (f.exp() - r.exp()).abs().max().item(), (l.exp() - r.exp()).abs().max().item()
-        assert ef <= max(1.5e-2, 1.2 * el), (ef, el)
-        assert (f.exp() - l.exp()).abs().max().item() <= 3e-2
-    torch.testing.assert_close(fused[3], out_ref[3].reshape(fused[3].shape), rtol=8e-2, atol=8e-2)
+        assert ef <= 5e-4 and ef <= 1.2 * el + 2e-5, (ef, el)
+        assert (f.exp() - l.exp()).abs().max().item() <= 5e-4
+        assert (f - r).abs().max().item() <= 1.5e-2                              # log-probabilities
+    torch.testing.assert_close(fused[3], out_ref[3].reshape(fused[3].shape), rtol=0.0, atol=6e-3)
 
 
 @pytest.mark.gpu
